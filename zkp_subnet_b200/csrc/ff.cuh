@@ -1,0 +1,148 @@
+// Montgomery prime-field arithmetic on 32-bit limbs for sm_100a (Fq: 12 limbs, Fr: 8 limbs).
+//
+// Multiplication is an interleaved (CIOS-order) Montgomery product that keeps TWO accumulators,
+// one aligned on even limb positions and one on odd positions, so that every 32x32->64 product
+// a[j]*b_i lands on an aligned (lo,hi) register pair: each mad.lo.cc/madc.hi.cc pair becomes one
+// IMAD.WIDE.U32 in SASS and the carry chains of the two accumulators are independent (ILP 2).
+// Work per product: 2*N^2 + N wide multiply-accumulates (300 for Fq, 136 for Fr) -- the figure the
+// roofline accounting in DESIGN.md uses.
+//
+// Values are kept fully reduced in [0, p).  All functions are __host__ __device__; the host
+// instantiation runs on the emulated carry flag of ptx_chain.cuh and exists for CPU unit tests.
+#pragma once
+#include "field_params.h"
+#include "ptx_chain.cuh"
+#include "mont_chains.cuh"
+
+namespace zkp {
+
+template <class P>
+struct Fp {
+    static constexpr int N = P::N;
+    uint32_t v[N];
+
+    // ---------------------------------------------------------------- constants
+    static ZKP_HD Fp zero() {
+        Fp r;
+#pragma unroll
+        for (int i = 0; i < N; i++) r.v[i] = 0;
+        return r;
+    }
+    static ZKP_HD Fp one() {
+        Fp r;
+#pragma unroll
+        for (int i = 0; i < N; i++) r.v[i] = P::one(i);
+        return r;
+    }
+    static ZKP_HD Fp r2() {
+        Fp r;
+#pragma unroll
+        for (int i = 0; i < N; i++) r.v[i] = P::r2(i);
+        return r;
+    }
+
+    // ---------------------------------------------------------------- predicates
+    ZKP_HD bool is_zero() const {
+        uint32_t acc = 0;
+#pragma unroll
+        for (int i = 0; i < N; i++) acc |= v[i];
+        return acc == 0;
+    }
+    friend ZKP_HD bool operator==(const Fp& a, const Fp& b) {
+        uint32_t acc = 0;
+#pragma unroll
+        for (int i = 0; i < N; i++) acc |= a.v[i] ^ b.v[i];
+        return acc == 0;
+    }
+    friend ZKP_HD bool operator!=(const Fp& a, const Fp& b) { return !(a == b); }
+
+    // ---------------------------------------------------------------- add / sub / neg
+    // (carry chains live in the generated mont_chains.cuh, one asm statement per chain)
+    friend ZKP_HD Fp operator+(const Fp& a, const Fp& b) {
+        Fp r;
+        if constexpr (N == 12) chains::fq_add(r.v, a.v, b.v);
+        else chains::fr_add(r.v, a.v, b.v);
+        return r;
+    }
+    friend ZKP_HD Fp operator-(const Fp& a, const Fp& b) {
+        Fp r;
+        if constexpr (N == 12) chains::fq_sub(r.v, a.v, b.v);
+        else chains::fr_sub(r.v, a.v, b.v);
+        return r;
+    }
+    ZKP_HD Fp neg() const { return zero() - *this; }  // 0 - a = p - a, and 0 for a == 0
+    // conditional negate (flag != 0 -> -a)
+    ZKP_HD Fp cneg(uint32_t flag) const {
+        Fp n = neg();
+        Fp r;
+#pragma unroll
+        for (int i = 0; i < N; i++) r.v[i] = flag ? n.v[i] : v[i];
+        return r;
+    }
+    ZKP_HD Fp dbl() const { return *this + *this; }
+
+    // ---------------------------------------------------------------- Montgomery product
+    // Row i adds a*b_i and m_i*p to the pair of accumulators and divides by 2^32; the accumulator
+    // aligned on even limb positions and the one aligned on odd positions swap roles every row.
+    friend ZKP_HD Fp operator*(const Fp& a, const Fp& b) {
+        uint32_t even[N], odd[N];
+        Fp r;
+        if constexpr (N == 12) {
+            chains::fq_row_first(even, odd, a.v, b.v[0]);
+            chains::fq_row(odd, even, a.v, b.v[1]);
+#pragma unroll
+            for (int i = 2; i < N; i += 2) {
+                chains::fq_row(even, odd, a.v, b.v[i]);
+                chains::fq_row(odd, even, a.v, b.v[i + 1]);
+            }
+            chains::fq_merge(r.v, odd, even);
+            chains::fq_reduce_once(r.v, 0);
+        } else {
+            chains::fr_row_first(even, odd, a.v, b.v[0]);
+            chains::fr_row(odd, even, a.v, b.v[1]);
+#pragma unroll
+            for (int i = 2; i < N; i += 2) {
+                chains::fr_row(even, odd, a.v, b.v[i]);
+                chains::fr_row(odd, even, a.v, b.v[i + 1]);
+            }
+            chains::fr_merge(r.v, odd, even);
+            chains::fr_reduce_once(r.v, 0);
+        }
+        return r;
+    }
+    ZKP_HD Fp sqr() const { return *this * *this; }
+
+    // ---------------------------------------------------------------- Montgomery domain
+    ZKP_HD Fp to_mont() const { return *this * r2(); }
+    ZKP_HD Fp from_mont() const {
+        Fp o = zero();
+        o.v[0] = 1;
+        return *this * o;
+    }
+
+    // x^e for a little-endian limb exponent (host/test helper; the device paths that need an
+    // inverse use batch inversion with one Fermat exponentiation per thread)
+    template <int EN>
+    ZKP_HD Fp pow_limbs(const uint32_t* e) const {
+        Fp acc = one();
+        for (int i = EN * 32 - 1; i >= 0; i--) {
+            acc = acc.sqr();
+            if ((e[i >> 5] >> (i & 31)) & 1) acc = acc * *this;
+        }
+        return acc;
+    }
+    ZKP_HD Fp inverse() const {
+        uint32_t e[N];
+        // p - 2
+        e[0] = ptx::sub_cc(P::mod(0), 2);
+#pragma unroll
+        for (int i = 1; i < N - 1; i++) e[i] = ptx::subc_cc(P::mod(i), 0);
+        e[N - 1] = ptx::subc(P::mod(N - 1), 0);
+        return pow_limbs<N>(e);
+    }
+};
+
+using Fq = Fp<FqParams>;
+using Fr = Fp<FrParams>;
+
+}  // namespace zkp
