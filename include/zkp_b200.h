@@ -1,0 +1,115 @@
+/*
+ * zkp_b200 -- C ABI of the B200-native KZG prover backend.
+ *
+ * This is the drop-in boundary for the hot path of apollozkp/zkp-subnet: everything the miner and
+ * validator neurons obtain from the external Rust prover through `fourier.Client`
+ * (reference base/miner.py:26,73-84; base/validator.py:28,80-91).  Each entry point names the
+ * reference call site it replaces.  Conventions:
+ *   - every function returns 0 on success or a negative zkp_status; no exceptions, no aborts;
+ *     zkp_last_error() gives a human-readable message for the calling thread's last failure;
+ *   - field elements cross the boundary as 32-byte BIG-ENDIAN canonical integers (< r), exactly the
+ *     bytes inside the reference's base64 `poly` / `alpha` / `eval` strings
+ *     (reference base/protocol.py:35-60, tests/test_miner.py:33-55);
+ *   - G1 points cross as 48-byte ZCash-compressed encodings (the bytes inside the reference's
+ *     base64 `commitment` / `proof` strings) or, for SRS import/export, 96-byte uncompressed;
+ *   - the caller owns every buffer; the library never returns heap pointers;
+ *   - a context is thread-safe (calls are serialised internally); several contexts may coexist
+ *     in one process (miner on port 1337 + validator on port 1338 in the reference).
+ * There is no CPU fallback: without a CUDA device zkp_ctx_create fails with ZKP_ERR_CUDA.
+ */
+#ifndef ZKP_B200_H
+#define ZKP_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct zkp_ctx zkp_ctx;
+
+typedef enum {
+    ZKP_OK = 0,
+    ZKP_ERR_ARG = -1,      /* bad argument (null pointer, size not a power of two, row out of range) */
+    ZKP_ERR_ENCODING = -2, /* non-canonical field element / malformed point */
+    ZKP_ERR_CUDA = -3,     /* CUDA runtime failure or no device */
+    ZKP_ERR_STATE = -4,    /* SRS not loaded / wrong size */
+    ZKP_ERR_IO = -5        /* file error */
+} zkp_status;
+
+/* ---- lifecycle: replaces Client(port, bin, uncompressed, setup_path, precompute_path),
+ *      client.start(scale, machines_scale) and client.stop()
+ *      (reference base/miner.py:73-84,155,181; base/validator.py:80-91,173,200) */
+int zkp_ctx_create(int device, zkp_ctx** out);
+void zkp_ctx_destroy(zkp_ctx* ctx);
+const char* zkp_last_error(void);
+int zkp_device_count(void);
+
+/* ---- SRS: replaces `prover setup --generate-setup --generate-precompute` and the
+ *      setup_path / precompute_path files (reference tests/conftest.py:50-65, Makefile:30-48).
+ *      Layout: 2^log_machines rows of 2^log_n points, U[i][j] = [R_i(tau_y) L_j(tau_x)]_1
+ *      (Lagrange basis over the natural-order domains), plus [R_i(tau_y)]_1 per row and [tau_x]_2. */
+int zkp_srs_generate(zkp_ctx* ctx, const uint8_t tau_x_be[32], const uint8_t tau_y_be[32],
+                     uint32_t log_n, uint32_t log_machines);
+/* import one row from 96-byte ZCash-uncompressed points (validated on curve), and its scale point */
+int zkp_srs_set_shape(zkp_ctx* ctx, uint32_t log_n, uint32_t log_machines);
+int zkp_srs_import_row(zkp_ctx* ctx, uint32_t row, const uint8_t* points96, size_t n,
+                       const uint8_t scale_point48[48]);
+int zkp_srs_import_g2_tau(zkp_ctx* ctx, const uint8_t tau_x_be[32]);
+int zkp_srs_export_row(zkp_ctx* ctx, uint32_t row, uint8_t* points96, size_t n);
+int zkp_srs_save(zkp_ctx* ctx, const char* path);
+int zkp_srs_load(zkp_ctx* ctx, const char* path);
+int zkp_srs_shape(zkp_ctx* ctx, uint32_t* log_n, uint32_t* log_machines);
+
+/* ---- the hot path */
+/* Client.worker_commit(i, poly)  (reference neurons/miner.py:38-45): poly = n evaluations, out = com_i */
+int zkp_worker_commit(zkp_ctx* ctx, uint32_t i, const uint8_t* poly_be, size_t n, uint8_t commitment48[48]);
+/* Client.worker_open(i, poly, x)  (reference neurons/miner.py:47-54): y = f_i(x), proof = [q_i]_1 */
+int zkp_worker_open(zkp_ctx* ctx, uint32_t i, const uint8_t* poly_be, size_t n, const uint8_t x_be[32],
+                    uint8_t eval_be[32], uint8_t proof48[48]);
+/* Miner.rpc_commit_and_open fused (reference neurons/miner.py:56-61): one upload, both MSMs */
+int zkp_worker_commit_open(zkp_ctx* ctx, uint32_t i, const uint8_t* poly_be, size_t n, const uint8_t x_be[32],
+                           uint8_t commitment48[48], uint8_t eval_be[32], uint8_t proof48[48]);
+/* Client.worker_verify(i, proof, alpha, eval, commitment)  (reference neurons/validator.py:77-86).
+ * Malformed / off-curve / wrong-subgroup points give *valid = 0 with status ZKP_OK
+ * (reference tests/test_validator.py:66,79-86 expect reward 0, not an exception). */
+int zkp_worker_verify(zkp_ctx* ctx, uint32_t i, const uint8_t proof48[48], const uint8_t alpha_be[32],
+                      const uint8_t eval_be[32], const uint8_t commitment48[48], int* valid);
+/* Client.fft(poly, left, inverse)  (reference neurons/validator.py:58-65): natural-order (i)NTT over the
+ * size-n X-domain (left != 0) or Y-domain (left == 0); n a power of two */
+int zkp_fft(zkp_ctx* ctx, const uint8_t* in_be, size_t n, int left, int inverse, uint8_t* out_be);
+/* Client.eval(poly, x)  (reference neurons/validator.py:97-104): coefficient-form Horner */
+int zkp_eval(zkp_ctx* ctx, const uint8_t* coeffs_be, size_t n, const uint8_t x_be[32], uint8_t y_be[32]);
+/* Client.random_poly() / random_point()  (reference neurons/validator.py:68-75,88-95) */
+int zkp_random_poly(zkp_ctx* ctx, uint64_t seed, uint8_t* out_be, size_t count);
+int zkp_random_point(zkp_ctx* ctx, uint64_t seed, uint8_t out_be[32]);
+
+/* ---- wire codec for the List[str] format of the Prove synapse (reference base/protocol.py:35-40):
+ *      `strs` holds `count` base64 strings of 43 (unpadded) or 44 (padded) characters each,
+ *      concatenated with a fixed stride; output is count x 32 bytes.  Encoding emits 43 chars/elt. */
+int zkp_b64_decode_fr(const char* strs, size_t stride, size_t count, uint8_t* out_be);
+int zkp_b64_encode_fr(const uint8_t* in_be, size_t count, char* out_strs /* count*43 */);
+
+/* ---- raw / benchmark entries (device-resident operands, CUDA-event timed inside the library) */
+/* G1 MSM over the first n points of SRS row `row` with n scalars (big-endian) */
+int zkp_msm_g1(zkp_ctx* ctx, uint32_t row, const uint8_t* scalars_be, size_t n, uint8_t out48[48]);
+/* upload scalars once, then run `reps` MSMs back to back; returns mean device ms per MSM */
+int zkp_bench_msm(zkp_ctx* ctx, uint32_t row, const uint8_t* scalars_be, size_t n, int reps, int flush_l2,
+                  float* ms_per_msm, uint8_t out48[48]);
+int zkp_bench_commit_open(zkp_ctx* ctx, uint32_t row, const uint8_t* poly_be, size_t n, const uint8_t x_be[32],
+                          int reps, int flush_l2, float* ms_per_iter, float* ms_msm_kernel, uint32_t* launches,
+                          uint8_t commitment48[48], uint8_t eval_be[32], uint8_t proof48[48]);
+int zkp_bench_ntt(zkp_ctx* ctx, size_t n, int reps, int inverse, float* ms_per_ntt);
+/* MSM tuning knobs: window bits (0 = automatic) */
+int zkp_set_msm_window(zkp_ctx* ctx, uint32_t c);
+int zkp_msm_info(zkp_ctx* ctx, size_t n, uint32_t* c, uint32_t* windows, uint64_t* fq_muls);
+
+/* ---- pairing check exposed for tests: prod e(P_k, Q_k) == 1, P compressed G1 (48 B), Q affine G2 as
+ *      4 x 48 B big-endian (x.c0, x.c1, y.c0, y.c1) */
+int zkp_pairing_check(const uint8_t* g1_48, const uint8_t* g2_192, size_t pairs, int* is_one);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ZKP_B200_H */

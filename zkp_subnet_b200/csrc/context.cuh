@@ -1,0 +1,87 @@
+// Context, device buffers and the MSM driver shared by the C-ABI entry points.
+#pragma once
+#include <cuda_runtime.h>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/zkp_b200.h"
+#include "host/curve.hpp"
+#include "msm.cuh"
+
+namespace zkp {
+
+// ---- error plumbing -----------------------------------------------------------------------
+inline std::string& tls_error() {
+    static thread_local std::string e;
+    return e;
+}
+inline int fail(int code, const std::string& msg) {
+    tls_error() = msg;
+    return code;
+}
+#define ZKP_CUDA(expr)                                                                                   \
+    do {                                                                                                 \
+        cudaError_t _e = (expr);                                                                         \
+        if (_e != cudaSuccess)                                                                           \
+            return fail(ZKP_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e));              \
+    } while (0)
+
+// ---- growable device buffer ------------------------------------------------------------------
+struct DevBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+    cudaError_t ensure(size_t bytes) {
+        if (bytes <= cap) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+        cudaError_t e = cudaMalloc(&p, bytes);
+        if (e == cudaSuccess) cap = bytes;
+        return e;
+    }
+    void release() {
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+    }
+    template <class T> T* as() const { return reinterpret_cast<T*>(p); }
+};
+
+struct MsmWorkspace {
+    DevBuf keys_a, keys_b, vals_a, vals_b, cub_temp, buckets, next_a, next_b, pool, sums_a, sums_b;
+    std::vector<DevBuf> slot_keys, slot_pts;
+    G1Xyzz* h_window = nullptr;  // pinned, W records
+    size_t h_window_cap = 0;
+    void release() {
+        for (DevBuf* b : {&keys_a, &keys_b, &vals_a, &vals_b, &cub_temp, &buckets, &next_a, &next_b, &pool, &sums_a, &sums_b})
+            b->release();
+        for (auto& b : slot_keys) b.release();
+        for (auto& b : slot_pts) b.release();
+        if (h_window) cudaFreeHost(h_window);
+        h_window = nullptr;
+        h_window_cap = 0;
+    }
+};
+
+}  // namespace zkp
+
+struct zkp_ctx {
+    int device = 0;
+    int sm_count = 148;
+    cudaStream_t stream = nullptr;
+    std::mutex mu;
+    // SRS
+    uint32_t log_n = 0, log_m = 0;
+    bool shaped = false;
+    zkp::DevBuf srs;                          // 2^log_m rows x 2^log_n G1Affine (Montgomery)
+    std::vector<uint8_t> row_loaded;          // per row flag
+    std::vector<zkp::host::G1J> scale_points; // [R_i(tau_y)]_1
+    bool have_g2_tau = false;
+    zkp::host::G2J g2_tau;                    // [tau_x]_2
+    // scratch
+    zkp::DevBuf scalars, fr_a, fr_b, fr_c, flush;
+    zkp::MsmWorkspace ws;
+    uint32_t c_override = 0;
+    uint64_t launches = 0;                    // kernels launched by this context (bench accounting)
+};

@@ -1,0 +1,131 @@
+// BLS12-381 G1 (y^2 = x^3 + 4 over Fq) point arithmetic for the MSM kernels.
+//
+// Buckets live in extended Jacobian "XYZZ" coordinates (x = X/ZZ, y = Y/ZZZ, ZZ^3 = ZZZ^2):
+// mixed add 8M+2S, full add 12M+2S, doubling of an affine point 3M+3S... (EFD madd-2008-s,
+// add-2008-s, mdbl-2008-s-1).  Every exceptional case (operand at infinity, P + P, P + (-P)) is
+// handled exactly -- the contract with the reference is bit-exact output, not "overwhelmingly
+// likely correct".  Infinity is ZZ == 0; an all-zero XYZZ record (fresh cudaMemset) is infinity.
+// Affine SRS points use (0, 0) as the infinity marker ((0,0) is not on the curve).
+//
+// __host__ __device__ like ff.cuh, so tests/host exercises these formulas on the CPU.
+#pragma once
+#include "ff.cuh"
+
+namespace zkp {
+
+struct G1Affine {
+    Fq x, y;  // Montgomery form
+    ZKP_HD bool is_inf() const { return x.is_zero() && y.is_zero(); }
+};
+
+struct G1Xyzz {
+    Fq x, y, zz, zzz;
+
+    static ZKP_HD G1Xyzz infinity() {
+        G1Xyzz r;
+        r.x = Fq::zero(); r.y = Fq::zero(); r.zz = Fq::zero(); r.zzz = Fq::zero();
+        return r;
+    }
+    ZKP_HD bool is_inf() const { return zz.is_zero(); }
+
+    // from an affine point, optionally negated
+    static ZKP_HD G1Xyzz from_affine(const G1Affine& p, uint32_t negate) {
+        G1Xyzz r;
+        if (p.is_inf()) return infinity();
+        r.x = p.x;
+        r.y = p.y.cneg(negate);
+        r.zz = Fq::one();
+        r.zzz = Fq::one();
+        return r;
+    }
+
+    // 2 * (affine p)   (mdbl-2008-s-1: 3M + 3S... here 2S + 3M + small)
+    static ZKP_HD G1Xyzz dbl_affine(const Fq& px, const Fq& py) {
+        G1Xyzz r;
+        Fq u = py.dbl();
+        Fq v = u.sqr();
+        Fq w = u * v;
+        Fq s = px * v;
+        Fq xx = px.sqr();
+        Fq m = xx.dbl() + xx;
+        r.x = m.sqr() - s.dbl();
+        r.y = m * (s - r.x) - w * py;
+        r.zz = v;
+        r.zzz = w;
+        return r;
+    }
+
+    // 2 * this   (dbl-2008-s-1, a = 0)
+    ZKP_HD G1Xyzz dbl() const {
+        if (is_inf()) return *this;
+        G1Xyzz r;
+        Fq u = y.dbl();
+        Fq v = u.sqr();
+        Fq w = u * v;
+        Fq s = x * v;
+        Fq xx = x.sqr();
+        Fq m = xx.dbl() + xx;
+        r.x = m.sqr() - s.dbl();
+        r.y = m * (s - r.x) - w * y;
+        r.zz = v * zz;
+        r.zzz = w * zzz;
+        return r;
+    }
+
+    // this += (px, +-py) affine, not infinity   (madd-2008-s: 8M + 2S)
+    ZKP_HD void madd(const Fq& px, const Fq& py_in, uint32_t negate) {
+        Fq py = py_in.cneg(negate);
+        if (is_inf()) {
+            x = px; y = py; zz = Fq::one(); zzz = Fq::one();
+            return;
+        }
+        Fq u2 = px * zz;
+        Fq s2 = py * zzz;
+        Fq p = u2 - x;
+        Fq r = s2 - y;
+        if (p.is_zero()) {
+            if (r.is_zero()) *this = dbl_affine(px, py);  // P + P
+            else *this = infinity();                      // P + (-P)
+            return;
+        }
+        Fq pp = p.sqr();
+        Fq ppp = p * pp;
+        Fq q = x * pp;
+        Fq x3 = r.sqr() - ppp - q.dbl();
+        y = r * (q - x3) - y * ppp;
+        x = x3;
+        zz = zz * pp;
+        zzz = zzz * ppp;
+    }
+    ZKP_HD void madd(const G1Affine& p, uint32_t negate) {
+        if (p.is_inf()) return;
+        madd(p.x, p.y, negate);
+    }
+
+    // this += o   (add-2008-s: 12M + 2S)
+    ZKP_HD void add(const G1Xyzz& o) {
+        if (o.is_inf()) return;
+        if (is_inf()) { *this = o; return; }
+        Fq u1 = x * o.zz;
+        Fq u2 = o.x * zz;
+        Fq s1 = y * o.zzz;
+        Fq s2 = o.y * zzz;
+        Fq p = u2 - u1;
+        Fq r = s2 - s1;
+        if (p.is_zero()) {
+            if (r.is_zero()) *this = dbl();
+            else *this = infinity();
+            return;
+        }
+        Fq pp = p.sqr();
+        Fq ppp = p * pp;
+        Fq q = u1 * pp;
+        Fq x3 = r.sqr() - ppp - q.dbl();
+        y = r * (q - x3) - s1 * ppp;
+        x = x3;
+        zz = zz * o.zz * pp;
+        zzz = zzz * o.zzz * ppp;
+    }
+};
+
+}  // namespace zkp

@@ -1,0 +1,139 @@
+// Host-side (CPU) Montgomery arithmetic on 64-bit limbs for the parts of the path that stay on the
+// host by design: the final fold of the W window sums of an MSM, affine conversion + ZCash
+// compression of the single result point, G1/G2 decompression and the pairing check of
+// worker_verify (reference neurons/validator.py:77-86 -> fourier Client.worker_verify).
+// Same Montgomery domain as the device code (R = 2^384 for Fq, 2^256 for Fr), so limbs can be
+// memcpy'd between the two.
+#pragma once
+#include <stdint.h>
+#include <string.h>
+#include "../field_params.h"
+
+namespace zkp {
+namespace host {
+
+typedef unsigned __int128 u128;
+
+template <class P>
+struct F64 {
+    static constexpr int N = P::N64;
+    uint64_t v[N];
+
+    static F64 zero() { F64 r; memset(r.v, 0, sizeof(r.v)); return r; }
+    static F64 one() { F64 r; memcpy(r.v, P::ONE64, sizeof(r.v)); return r; }
+    static F64 r2() { F64 r; memcpy(r.v, P::R264, sizeof(r.v)); return r; }
+    static F64 from_u64(uint64_t x) { F64 r = zero(); r.v[0] = x; return r.to_mont(); }
+
+    bool is_zero() const { uint64_t a = 0; for (int i = 0; i < N; i++) a |= v[i]; return a == 0; }
+    bool operator==(const F64& o) const { return memcmp(v, o.v, sizeof(v)) == 0; }
+    bool operator!=(const F64& o) const { return !(*this == o); }
+
+    static bool geq_mod(const uint64_t* a) {
+        for (int i = N - 1; i >= 0; i--) {
+            if (a[i] > P::MOD64[i]) return true;
+            if (a[i] < P::MOD64[i]) return false;
+        }
+        return true;
+    }
+    static void sub_mod_raw(uint64_t* a) {
+        uint64_t borrow = 0;
+        for (int i = 0; i < N; i++) {
+            u128 d = (u128)a[i] - P::MOD64[i] - borrow;
+            a[i] = (uint64_t)d;
+            borrow = (uint64_t)(d >> 64) & 1;
+        }
+    }
+    F64 operator+(const F64& o) const {
+        F64 r;
+        uint64_t c = 0;
+        for (int i = 0; i < N; i++) { u128 s = (u128)v[i] + o.v[i] + c; r.v[i] = (uint64_t)s; c = (uint64_t)(s >> 64); }
+        if (c || geq_mod(r.v)) sub_mod_raw(r.v);
+        return r;
+    }
+    F64 operator-(const F64& o) const {
+        F64 r;
+        uint64_t b = 0;
+        for (int i = 0; i < N; i++) { u128 d = (u128)v[i] - o.v[i] - b; r.v[i] = (uint64_t)d; b = (uint64_t)(d >> 64) & 1; }
+        if (b) {
+            uint64_t c = 0;
+            for (int i = 0; i < N; i++) { u128 s = (u128)r.v[i] + P::MOD64[i] + c; r.v[i] = (uint64_t)s; c = (uint64_t)(s >> 64); }
+        }
+        return r;
+    }
+    F64 neg() const { return zero() - *this; }
+    F64 dbl() const { return *this + *this; }
+    F64 operator*(const F64& o) const {
+        uint64_t t[N + 2];
+        memset(t, 0, sizeof(t));
+        for (int i = 0; i < N; i++) {
+            u128 c = 0;
+            for (int j = 0; j < N; j++) { c += (u128)v[j] * o.v[i] + t[j]; t[j] = (uint64_t)c; c >>= 64; }
+            c += t[N]; t[N] = (uint64_t)c; t[N + 1] = (uint64_t)(c >> 64);
+            uint64_t m = t[0] * P::INV64;
+            c = ((u128)m * P::MOD64[0] + t[0]) >> 64;
+            for (int j = 1; j < N; j++) { c += (u128)m * P::MOD64[j] + t[j]; t[j - 1] = (uint64_t)c; c >>= 64; }
+            c += t[N]; t[N - 1] = (uint64_t)c; t[N] = t[N + 1] + (uint64_t)(c >> 64);
+        }
+        F64 r;
+        memcpy(r.v, t, sizeof(r.v));
+        if (t[N] || geq_mod(r.v)) sub_mod_raw(r.v);
+        return r;
+    }
+    F64 sqr() const { return *this * *this; }
+    F64 to_mont() const { return *this * r2(); }
+    F64 from_mont() const { F64 o = zero(); o.v[0] = 1; return *this * o; }
+
+    // exponent: little-endian 64-bit limbs
+    F64 pow(const uint64_t* e, int elimbs) const {
+        F64 acc = one();
+        for (int i = elimbs * 64 - 1; i >= 0; i--) {
+            acc = acc.sqr();
+            if ((e[i >> 6] >> (i & 63)) & 1) acc = acc * *this;
+        }
+        return acc;
+    }
+    F64 inverse() const {  // a^(p-2); 0 -> 0
+        uint64_t e[N];
+        uint64_t borrow = 2;
+        for (int i = 0; i < N; i++) {
+            u128 d = (u128)P::MOD64[i] - borrow;
+            e[i] = (uint64_t)d;
+            borrow = (uint64_t)(d >> 64) & 1;
+        }
+        return pow(e, N);
+    }
+
+    // canonical big-endian bytes (N*8) <-> Montgomery form.  from_be returns false if >= modulus.
+    static bool from_be(F64& out, const uint8_t* be) {
+        F64 c;
+        for (int i = 0; i < N; i++) {
+            uint64_t w = 0;
+            for (int k = 0; k < 8; k++) w = (w << 8) | be[(N - 1 - i) * 8 + k];
+            c.v[i] = w;
+        }
+        if (geq_mod(c.v)) return false;
+        out = c.to_mont();
+        return true;
+    }
+    void to_be(uint8_t* be) const {
+        F64 c = from_mont();
+        for (int i = 0; i < N; i++)
+            for (int k = 0; k < 8; k++) be[(N - 1 - i) * 8 + k] = (uint8_t)(c.v[i] >> (56 - 8 * k));
+    }
+    // canonical value compare: this > (p-1)/2 ?   (this in Montgomery form)
+    bool lexicographically_largest() const {
+        F64 c = from_mont();
+        F64 n = neg().from_mont();
+        for (int i = N - 1; i >= 0; i--) {
+            if (c.v[i] > n.v[i]) return true;
+            if (c.v[i] < n.v[i]) return false;
+        }
+        return false;
+    }
+};
+
+using Fq64 = F64<FqParams>;
+using Fr64 = F64<FrParams>;
+
+}  // namespace host
+}  // namespace zkp

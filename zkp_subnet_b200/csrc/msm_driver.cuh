@@ -1,0 +1,140 @@
+// Host driver of the MSM pipeline described in msm.cuh.
+#pragma once
+#include "context.cuh"
+
+namespace zkp {
+
+inline uint64_t msm_fq_muls(const MsmPlan& p) {
+    // algorithmic Fq multiplications: 10 per mixed add into buckets, 14 per full add in
+    // the running-sum reduction (2 adds per bucket)
+    return 10ull * p.n * p.W + 14ull * 2ull * p.B * p.W;
+}
+
+// Launches the whole device pipeline on ctx->stream and copies the W window sums to pinned host
+// memory; synchronises the stream before returning.
+inline int msm_run(zkp_ctx* ctx, const MsmPlan& plan, const uint32_t* d_scalars, int big_endian,
+                   const G1Affine* d_points) {
+    MsmWorkspace& ws = ctx->ws;
+    cudaStream_t st = ctx->stream;
+    const size_t N = plan.N;
+    ZKP_CUDA(ws.keys_a.ensure(N * 4));
+    ZKP_CUDA(ws.keys_b.ensure(N * 4));
+    ZKP_CUDA(ws.vals_a.ensure(N * 4));
+    ZKP_CUDA(ws.vals_b.ensure(N * 4));
+    const size_t nb = (size_t)plan.W * plan.B;
+    ZKP_CUDA(ws.buckets.ensure(nb * sizeof(G1Xyzz)));
+    if (ws.slot_keys.size() < plan.levels.size()) {
+        ws.slot_keys.resize(plan.levels.size());
+        ws.slot_pts.resize(plan.levels.size());
+    }
+    for (size_t l = 0; l + 1 < plan.levels.size(); l++) {
+        ZKP_CUDA(ws.slot_keys[l].ensure(plan.levels[l].threads * 2 * 4));
+        ZKP_CUDA(ws.slot_pts[l].ensure(plan.levels[l].threads * 2 * sizeof(G1Xyzz)));
+    }
+    if (ws.h_window_cap < plan.W) {
+        if (ws.h_window) cudaFreeHost(ws.h_window);
+        ZKP_CUDA(cudaMallocHost(&ws.h_window, sizeof(G1Xyzz) * plan.W));
+        ws.h_window_cap = plan.W;
+    }
+
+    // 1. digits
+    k_decompose<<<(plan.n + 255) / 256, 256, 0, st>>>(d_scalars, plan.n, plan.c, plan.W, plan.B, plan.discard,
+                                                      big_endian, ws.keys_a.as<uint32_t>(), ws.vals_a.as<uint32_t>());
+    ctx->launches++;
+    // 2. sort by (window, bucket)
+    size_t temp_bytes = 0;
+    ZKP_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, temp_bytes, ws.keys_a.as<uint32_t>(), ws.keys_b.as<uint32_t>(),
+                                             ws.vals_a.as<uint32_t>(), ws.vals_b.as<uint32_t>(), (int64_t)N, 0,
+                                             (int)plan.key_bits, st));
+    ZKP_CUDA(ws.cub_temp.ensure(temp_bytes));
+    ZKP_CUDA(cub::DeviceRadixSort::SortPairs(ws.cub_temp.p, temp_bytes, ws.keys_a.as<uint32_t>(), ws.keys_b.as<uint32_t>(),
+                                             ws.vals_a.as<uint32_t>(), ws.vals_b.as<uint32_t>(), (int64_t)N, 0,
+                                             (int)plan.key_bits, st));
+    // 3. balanced accumulation, level by level
+    ZKP_CUDA(cudaMemsetAsync(ws.buckets.p, 0, nb * sizeof(G1Xyzz), st));
+    for (size_t l = 0; l < plan.levels.size(); l++) {
+        const auto& lv = plan.levels[l];
+        int last = l + 1 == plan.levels.size();
+        unsigned blocks = (unsigned)((lv.threads + 127) / 128);
+        if (l == 0) {
+            k_accumulate<true><<<blocks, 128, 0, st>>>(ws.keys_b.as<uint32_t>(), ws.vals_b.as<uint32_t>(), d_points, nullptr,
+                                                       lv.items, lv.L, plan.discard, ws.buckets.as<G1Xyzz>(),
+                                                       last ? nullptr : ws.slot_keys[0].as<uint32_t>(),
+                                                       last ? nullptr : ws.slot_pts[0].as<G1Xyzz>(), last);
+        } else {
+            k_accumulate<false><<<blocks, 128, 0, st>>>(ws.slot_keys[l - 1].as<uint32_t>(), nullptr, nullptr,
+                                                        ws.slot_pts[l - 1].as<G1Xyzz>(), lv.items, lv.L, plan.discard,
+                                                        ws.buckets.as<G1Xyzz>(),
+                                                        last ? nullptr : ws.slot_keys[l].as<uint32_t>(),
+                                                        last ? nullptr : ws.slot_pts[l].as<G1Xyzz>(), last);
+        }
+        ctx->launches++;
+    }
+    // 4. bucket reduction
+    ZKP_CUDA(ws.pool.ensure((size_t)plan.W * plan.pool_per_window * sizeof(G1Xyzz)));
+    size_t next_cap = (size_t)plan.W * plan.rlevels[0].chunks * sizeof(G1Xyzz);
+    ZKP_CUDA(ws.next_a.ensure(next_cap));
+    ZKP_CUDA(ws.next_b.ensure(next_cap));
+    const G1Xyzz* in = ws.buckets.as<G1Xyzz>();
+    uint32_t in_stride = plan.B, pool_off = 0;
+    for (size_t l = 0; l < plan.rlevels.size(); l++) {
+        const auto& rl = plan.rlevels[l];
+        bool last = l + 1 == plan.rlevels.size();
+        G1Xyzz* next = last ? nullptr : (l % 2 == 0 ? ws.next_a.as<G1Xyzz>() : ws.next_b.as<G1Xyzz>());
+        uint32_t log_m = 0;
+        while ((1u << log_m) < rl.m) log_m++;
+        uint32_t total = rl.chunks * plan.W;
+        k_bucket_reduce<<<(total + 127) / 128, 128, 0, st>>>(in, rl.n_in, in_stride, rl.m, log_m, rl.chunks, l == 0, next,
+                                                             rl.chunks, ws.pool.as<G1Xyzz>(), plan.pool_per_window,
+                                                             pool_off, plan.W);
+        ctx->launches++;
+        pool_off += rl.chunks;
+        in = next;
+        in_stride = rl.chunks;
+    }
+    // plain sum of the pool -> one point per window
+    uint32_t count = plan.pool_per_window;
+    const G1Xyzz* sin = ws.pool.as<G1Xyzz>();
+    uint32_t sstride = plan.pool_per_window;
+    uint32_t parts0 = (count + SUM_PART - 1) / SUM_PART;
+    ZKP_CUDA(ws.sums_a.ensure((size_t)plan.W * parts0 * sizeof(G1Xyzz)));
+    ZKP_CUDA(ws.sums_b.ensure((size_t)plan.W * parts0 * sizeof(G1Xyzz)));
+    int flip = 0;
+    for (;;) {
+        uint32_t parts = (count + SUM_PART - 1) / SUM_PART;
+        G1Xyzz* sout = flip ? ws.sums_b.as<G1Xyzz>() : ws.sums_a.as<G1Xyzz>();
+        k_sum_segments<<<dim3(parts, plan.W), SUM_THREADS, 0, st>>>(sin, count, sstride, sout, parts);
+        ctx->launches++;
+        sin = sout;
+        sstride = parts;
+        count = parts;
+        flip ^= 1;
+        if (parts == 1) break;
+    }
+    ZKP_CUDA(cudaMemcpyAsync(ws.h_window, sin, sizeof(G1Xyzz) * plan.W, cudaMemcpyDeviceToHost, st));
+    ZKP_CUDA(cudaStreamSynchronize(st));
+    ZKP_CUDA(cudaGetLastError());
+    return ZKP_OK;
+}
+
+// 5. host: fold the window sums, result in Jacobian coordinates
+inline host::G1J msm_fold(const MsmPlan& plan, const G1Xyzz* h_window) {
+    using namespace host;
+    G1J acc = G1J::infinity();
+    for (int w = (int)plan.W - 1; w >= 0; w--) {
+        for (uint32_t d = 0; d < plan.c; d++) acc = acc.dbl();
+        Fq64 x, y, zz, zzz;
+        memcpy(x.v, h_window[w].x.v, 48);
+        memcpy(y.v, h_window[w].y.v, 48);
+        memcpy(zz.v, h_window[w].zz.v, 48);
+        memcpy(zzz.v, h_window[w].zzz.v, 48);
+        if (!zz.is_zero()) {
+            // XYZZ (x = X/ZZ, y = Y/ZZZ, ZZ^3 = ZZZ^2)  ->  Jacobian with Z = ZZ
+            G1J p = {x * zz, y * zzz, zz};
+            acc = acc.add(p);
+        }
+    }
+    return acc;
+}
+
+}  // namespace zkp

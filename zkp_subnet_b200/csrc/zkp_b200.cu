@@ -1,0 +1,219 @@
+// C-ABI of the B200-native KZG prover backend (see include/zkp_b200.h for the contract and the
+// reference call site each entry replaces).  One translation unit: nvcc -gencode
+// arch=compute_100a,code=sm_100a.  No PyTorch, no CPU fallback: every entry needs a CUDA device.
+#include <cstdio>
+#include <cstring>
+#include <memory>
+
+#include "codec.hpp"
+#include "context.cuh"
+#include "kzg.cuh"
+#include "msm_driver.cuh"
+#include "ntt.cuh"
+#include "host/pairing.hpp"
+#include "srs.cuh"
+
+using namespace zkp;
+
+namespace {
+
+struct DeviceGuard {
+    int prev = -1;
+    explicit DeviceGuard(int dev) {
+        cudaGetDevice(&prev);
+        if (prev != dev) cudaSetDevice(dev);
+    }
+    ~DeviceGuard() {
+        if (prev >= 0) cudaSetDevice(prev);
+    }
+};
+
+bool is_pow2(size_t n) { return n && !(n & (n - 1)); }
+uint32_t ilog2(size_t n) {
+    uint32_t l = 0;
+    while (((size_t)1 << l) < n) l++;
+    return l;
+}
+
+int check_row(zkp_ctx* ctx, uint32_t row, size_t n) {
+    if (!ctx) return fail(ZKP_ERR_ARG, "null context");
+    if (!ctx->shaped) return fail(ZKP_ERR_STATE, "SRS not loaded (call zkp_srs_generate / zkp_srs_load / zkp_srs_import_row)");
+    if (row >= (1u << ctx->log_m)) return fail(ZKP_ERR_ARG, "worker index out of range");
+    if (!ctx->row_loaded[row]) return fail(ZKP_ERR_STATE, "SRS row not loaded");
+    if (n == 0 || n > ((size_t)1 << ctx->log_n)) return fail(ZKP_ERR_ARG, "polynomial longer than the SRS row");
+    return ZKP_OK;
+}
+
+const G1Affine* row_ptr(zkp_ctx* ctx, uint32_t row) { return ctx->srs.as<G1Affine>() + ((size_t)row << ctx->log_n); }
+
+// upload big-endian scalars and validate them (< r) on the device
+int upload_scalars(zkp_ctx* ctx, const uint8_t* be, size_t n, DevBuf& dst) {
+    ZKP_CUDA(dst.ensure(n * 32));
+    ZKP_CUDA(cudaMemcpyAsync(dst.p, be, n * 32, cudaMemcpyHostToDevice, ctx->stream));
+    return ZKP_OK;
+}
+
+int finish_point(const MsmPlan& plan, zkp_ctx* ctx, uint8_t out48[48]) {
+    host::G1J r = msm_fold(plan, ctx->ws.h_window);
+    host::g1_compress(out48, r);
+    return ZKP_OK;
+}
+
+// MSM over row `row` with device-resident scalars
+int msm_device(zkp_ctx* ctx, uint32_t row, const uint32_t* d_scalars, int big_endian, size_t n, uint8_t out48[48]) {
+    MsmPlan plan = msm_make_plan((uint32_t)n, ctx->sm_count, ctx->c_override);
+    int rc = msm_run(ctx, plan, d_scalars, big_endian, row_ptr(ctx, row));
+    if (rc) return rc;
+    return finish_point(plan, ctx, out48);
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* zkp_last_error(void) { return tls_error().c_str(); }
+
+int zkp_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
+    return n;
+}
+
+int zkp_ctx_create(int device, zkp_ctx** out) {
+    if (!out) return fail(ZKP_ERR_ARG, "null out pointer");
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0)
+        return fail(ZKP_ERR_CUDA, std::string("no CUDA device: ") + cudaGetErrorString(e) + " (this backend has no CPU fallback)");
+    if (device < 0 || device >= count) return fail(ZKP_ERR_ARG, "device index out of range");
+    DeviceGuard g(device);
+    std::unique_ptr<zkp_ctx> ctx(new zkp_ctx());
+    ctx->device = device;
+    cudaDeviceProp prop;
+    ZKP_CUDA(cudaGetDeviceProperties(&prop, device));
+    ctx->sm_count = prop.multiProcessorCount;
+    ZKP_CUDA(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+    *out = ctx.release();
+    return ZKP_OK;
+}
+
+void zkp_ctx_destroy(zkp_ctx* ctx) {
+    if (!ctx) return;
+    {
+        DeviceGuard g(ctx->device);
+        cudaStreamSynchronize(ctx->stream);
+        ctx->ws.release();
+        for (DevBuf* b : {&ctx->srs, &ctx->scalars, &ctx->fr_a, &ctx->fr_b, &ctx->fr_c, &ctx->flush}) b->release();
+        cudaStreamDestroy(ctx->stream);
+    }
+    delete ctx;
+}
+
+int zkp_set_msm_window(zkp_ctx* ctx, uint32_t c) {
+    if (!ctx || c > 24 || (c && c < 2)) return fail(ZKP_ERR_ARG, "window bits must be 0 (auto) or 2..24");
+    ctx->c_override = c;
+    return ZKP_OK;
+}
+
+int zkp_msm_info(zkp_ctx* ctx, size_t n, uint32_t* c, uint32_t* windows, uint64_t* fq_muls) {
+    if (!ctx || !n) return fail(ZKP_ERR_ARG, "bad argument");
+    MsmPlan plan = msm_make_plan((uint32_t)n, ctx->sm_count, ctx->c_override);
+    if (c) *c = plan.c;
+    if (windows) *windows = plan.W;
+    if (fq_muls) *fq_muls = msm_fq_muls(plan);
+    return ZKP_OK;
+}
+
+// ------------------------------------------------------------------------------------------ SRS
+int zkp_srs_set_shape(zkp_ctx* ctx, uint32_t log_n, uint32_t log_machines) {
+    if (!ctx || log_n > 28 || log_machines > 16) return fail(ZKP_ERR_ARG, "bad SRS shape");
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    DeviceGuard g(ctx->device);
+    size_t total = (size_t)1 << (log_n + log_machines);
+    ZKP_CUDA(ctx->srs.ensure(total * sizeof(G1Affine)));
+    ctx->log_n = log_n;
+    ctx->log_m = log_machines;
+    ctx->row_loaded.assign((size_t)1 << log_machines, 0);
+    ctx->scale_points.assign((size_t)1 << log_machines, host::G1J::infinity());
+    ctx->shaped = true;
+    return ZKP_OK;
+}
+
+int zkp_srs_shape(zkp_ctx* ctx, uint32_t* log_n, uint32_t* log_machines) {
+    if (!ctx || !ctx->shaped) return fail(ZKP_ERR_STATE, "SRS not loaded");
+    if (log_n) *log_n = ctx->log_n;
+    if (log_machines) *log_machines = ctx->log_m;
+    return ZKP_OK;
+}
+
+int zkp_srs_import_row(zkp_ctx* ctx, uint32_t row, const uint8_t* points96, size_t n, const uint8_t scale_point48[48]) {
+    if (!ctx || !points96) return fail(ZKP_ERR_ARG, "null argument");
+    if (!ctx->shaped) return fail(ZKP_ERR_STATE, "call zkp_srs_set_shape first");
+    if (row >= (1u << ctx->log_m) || n != ((size_t)1 << ctx->log_n)) return fail(ZKP_ERR_ARG, "row/size mismatch");
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    DeviceGuard g(ctx->device);
+    if (scale_point48) {
+        host::G1J s;
+        if (!host::g1_decompress(s, scale_point48)) return fail(ZKP_ERR_ENCODING, "bad scale point");
+        ctx->scale_points[row] = s;
+    } else {
+        ctx->scale_points[row] = host::g1_generator();
+    }
+    ZKP_CUDA(ctx->fr_a.ensure(n * 96));
+    ZKP_CUDA(ctx->fr_b.ensure(4));
+    ZKP_CUDA(cudaMemcpyAsync(ctx->fr_a.p, points96, n * 96, cudaMemcpyHostToDevice, ctx->stream));
+    ZKP_CUDA(cudaMemsetAsync(ctx->fr_b.p, 0, 4, ctx->stream));
+    G1Affine* dst = ctx->srs.as<G1Affine>() + ((size_t)row << ctx->log_n);
+    k_points_from_be96<<<(unsigned)((n + 127) / 128), 128, 0, ctx->stream>>>(ctx->fr_a.as<uint8_t>(), n, dst, ctx->fr_b.as<uint32_t>());
+    ctx->launches++;
+    uint32_t bad = 0;
+    ZKP_CUDA(cudaMemcpyAsync(&bad, ctx->fr_b.p, 4, cudaMemcpyDeviceToHost, ctx->stream));
+    ZKP_CUDA(cudaStreamSynchronize(ctx->stream));
+    if (bad) return fail(ZKP_ERR_ENCODING, "SRS row holds a malformed or off-curve point");
+    ctx->row_loaded[row] = 1;
+    return ZKP_OK;
+}
+
+int zkp_srs_export_row(zkp_ctx* ctx, uint32_t row, uint8_t* points96, size_t n) {
+    int rc = check_row(ctx, row, n);
+    if (rc) return rc;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    DeviceGuard g(ctx->device);
+    ZKP_CUDA(ctx->fr_a.ensure(n * 96));
+    k_points_to_be96<<<(unsigned)((n + 127) / 128), 128, 0, ctx->stream>>>(row_ptr(ctx, row), n, ctx->fr_a.as<uint8_t>());
+    ctx->launches++;
+    ZKP_CUDA(cudaMemcpyAsync(points96, ctx->fr_a.p, n * 96, cudaMemcpyDeviceToHost, ctx->stream));
+    ZKP_CUDA(cudaStreamSynchronize(ctx->stream));
+    return ZKP_OK;
+}
+
+int zkp_srs_import_g2_tau(zkp_ctx* ctx, const uint8_t tau_x_be[32]) {
+    if (!ctx || !tau_x_be) return fail(ZKP_ERR_ARG, "null argument");
+    host::Fr64 t;
+    if (!host::Fr64::from_be(t, tau_x_be)) return fail(ZKP_ERR_ENCODING, "tau not canonical");
+    host::Fr64 c = t.from_mont();
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    ctx->g2_tau = host::g2_generator().mul(c.v, 4);
+    ctx->have_g2_tau = true;
+    return ZKP_OK;
+}
+
+// ------------------------------------------------------------------------------------------ hot path
+int zkp_msm_g1(zkp_ctx* ctx, uint32_t row, const uint8_t* scalars_be, size_t n, uint8_t out48[48]) {
+    int rc = check_row(ctx, row, n);
+    if (rc) return rc;
+    if (!scalars_be || !out48) return fail(ZKP_ERR_ARG, "null argument");
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    DeviceGuard g(ctx->device);
+    rc = upload_scalars(ctx, scalars_be, n, ctx->scalars);
+    if (rc) return rc;
+    return msm_device(ctx, row, ctx->scalars.as<uint32_t>(), 1, n, out48);
+}
+
+int zkp_worker_commit(zkp_ctx* ctx, uint32_t i, const uint8_t* poly_be, size_t n, uint8_t commitment48[48]) {
+    return zkp_msm_g1(ctx, i, poly_be, n, commitment48);
+}
+
+}  // extern "C"
+
+#include "capi_rest.cuh"

@@ -1,0 +1,250 @@
+"""ctypes binding of libzkp_b200.so (the C ABI declared in include/zkp_b200.h).
+
+The library is CUDA-only.  There is no CPU fallback: if the shared object is missing this module
+raises at import of the first symbol, and if no GPU is present `Context()` raises `ZkpError`.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+from typing import Optional, Tuple
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libzkp_b200.so")
+
+ZKP_OK = 0
+ZKP_ERR_ARG = -1
+ZKP_ERR_ENCODING = -2
+ZKP_ERR_CUDA = -3
+ZKP_ERR_STATE = -4
+ZKP_ERR_IO = -5
+
+
+class ZkpError(RuntimeError):
+    def __init__(self, code: int, message: str):
+        super().__init__(f"zkp_b200 error {code}: {message}")
+        self.code = code
+
+
+_lib: Optional[ctypes.CDLL] = None
+
+_u8p = ctypes.c_char_p
+_ctxp = ctypes.c_void_p
+
+# name -> argtypes (restype is int unless listed in _RESTYPES)
+_SIGNATURES = {
+    "zkp_ctx_create": [ctypes.c_int, ctypes.POINTER(_ctxp)],
+    "zkp_ctx_destroy": [_ctxp],
+    "zkp_last_error": [],
+    "zkp_device_count": [],
+    "zkp_srs_generate": [_ctxp, _u8p, _u8p, ctypes.c_uint32, ctypes.c_uint32],
+    "zkp_srs_set_shape": [_ctxp, ctypes.c_uint32, ctypes.c_uint32],
+    "zkp_srs_import_row": [_ctxp, ctypes.c_uint32, _u8p, ctypes.c_size_t, _u8p],
+    "zkp_srs_import_g2_tau": [_ctxp, _u8p],
+    "zkp_srs_export_row": [_ctxp, ctypes.c_uint32, _u8p, ctypes.c_size_t],
+    "zkp_srs_save": [_ctxp, ctypes.c_char_p],
+    "zkp_srs_load": [_ctxp, ctypes.c_char_p],
+    "zkp_srs_shape": [_ctxp, ctypes.POINTER(ctypes.c_uint32), ctypes.POINTER(ctypes.c_uint32)],
+    "zkp_worker_commit": [_ctxp, ctypes.c_uint32, _u8p, ctypes.c_size_t, _u8p],
+    "zkp_worker_open": [_ctxp, ctypes.c_uint32, _u8p, ctypes.c_size_t, _u8p, _u8p, _u8p],
+    "zkp_worker_commit_open": [_ctxp, ctypes.c_uint32, _u8p, ctypes.c_size_t, _u8p, _u8p, _u8p, _u8p],
+    "zkp_worker_verify": [_ctxp, ctypes.c_uint32, _u8p, _u8p, _u8p, _u8p, ctypes.POINTER(ctypes.c_int)],
+    "zkp_fft": [_ctxp, _u8p, ctypes.c_size_t, ctypes.c_int, ctypes.c_int, _u8p],
+    "zkp_eval": [_ctxp, _u8p, ctypes.c_size_t, _u8p, _u8p],
+    "zkp_random_poly": [_ctxp, ctypes.c_uint64, _u8p, ctypes.c_size_t],
+    "zkp_random_point": [_ctxp, ctypes.c_uint64, _u8p],
+    "zkp_b64_decode_fr": [ctypes.c_char_p, ctypes.c_size_t, ctypes.c_size_t, _u8p],
+    "zkp_b64_encode_fr": [_u8p, ctypes.c_size_t, ctypes.c_char_p],
+    "zkp_msm_g1": [_ctxp, ctypes.c_uint32, _u8p, ctypes.c_size_t, _u8p],
+    "zkp_bench_msm": [_ctxp, ctypes.c_uint32, _u8p, ctypes.c_size_t, ctypes.c_int, ctypes.c_int,
+                      ctypes.POINTER(ctypes.c_float), _u8p],
+    "zkp_bench_commit_open": [_ctxp, ctypes.c_uint32, _u8p, ctypes.c_size_t, _u8p, ctypes.c_int, ctypes.c_int,
+                              ctypes.POINTER(ctypes.c_float), ctypes.POINTER(ctypes.c_float),
+                              ctypes.POINTER(ctypes.c_uint32), _u8p, _u8p, _u8p],
+    "zkp_bench_ntt": [_ctxp, ctypes.c_size_t, ctypes.c_int, ctypes.c_int, ctypes.POINTER(ctypes.c_float)],
+    "zkp_set_msm_window": [_ctxp, ctypes.c_uint32],
+    "zkp_msm_info": [_ctxp, ctypes.c_size_t, ctypes.POINTER(ctypes.c_uint32), ctypes.POINTER(ctypes.c_uint32),
+                     ctypes.POINTER(ctypes.c_uint64)],
+    "zkp_pairing_check": [_u8p, _u8p, ctypes.c_size_t, ctypes.POINTER(ctypes.c_int)],
+}
+_RESTYPES = {"zkp_ctx_destroy": None, "zkp_last_error": ctypes.c_char_p}
+
+EXPORTED_SYMBOLS = tuple(_SIGNATURES)
+
+
+def lib() -> ctypes.CDLL:
+    """Load libzkp_b200.so; fails loudly if it has not been built (`make` / __graft_entry__.build())."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise ZkpError(ZKP_ERR_STATE, f"{LIB_PATH} not built; run `make` (nvcc, sm_100a). No CPU fallback exists.")
+        handle = ctypes.CDLL(LIB_PATH)
+        for name, args in _SIGNATURES.items():
+            fn = getattr(handle, name)
+            fn.argtypes = args
+            fn.restype = _RESTYPES.get(name, ctypes.c_int)
+        _lib = handle
+    return _lib
+
+
+def last_error() -> str:
+    msg = lib().zkp_last_error()
+    return msg.decode() if msg else ""
+
+
+def check(rc: int) -> None:
+    if rc != ZKP_OK:
+        raise ZkpError(rc, last_error())
+
+
+class Context:
+    """Owns one zkp_ctx (one GPU, one resident SRS).  Mirrors the lifetime of the reference's prover
+    process started by Client.start() and killed by Client.stop() (reference base/miner.py:73-84,155)."""
+
+    def __init__(self, device: int = 0):
+        self._h = _ctxp()
+        check(lib().zkp_ctx_create(device, ctypes.byref(self._h)))
+
+    def close(self) -> None:
+        if self._h:
+            lib().zkp_ctx_destroy(self._h)
+            self._h = _ctxp()
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- SRS
+    def srs_generate(self, tau_x: int, tau_y: int, log_n: int, log_machines: int) -> None:
+        check(lib().zkp_srs_generate(self._h, tau_x.to_bytes(32, "big"), tau_y.to_bytes(32, "big"), log_n, log_machines))
+
+    def srs_set_shape(self, log_n: int, log_machines: int) -> None:
+        check(lib().zkp_srs_set_shape(self._h, log_n, log_machines))
+
+    def srs_import_row(self, row: int, points96: bytes, scale_point48: Optional[bytes] = None) -> None:
+        check(lib().zkp_srs_import_row(self._h, row, points96, len(points96) // 96, scale_point48))
+
+    def srs_import_g2_tau(self, tau_x: int) -> None:
+        check(lib().zkp_srs_import_g2_tau(self._h, tau_x.to_bytes(32, "big")))
+
+    def srs_export_row(self, row: int, n: int) -> bytes:
+        out = ctypes.create_string_buffer(96 * n)
+        check(lib().zkp_srs_export_row(self._h, row, out, n))
+        return out.raw
+
+    def srs_save(self, path: str) -> None:
+        check(lib().zkp_srs_save(self._h, path.encode()))
+
+    def srs_load(self, path: str) -> None:
+        check(lib().zkp_srs_load(self._h, path.encode()))
+
+    def srs_shape(self) -> Tuple[int, int]:
+        a, b = ctypes.c_uint32(), ctypes.c_uint32()
+        check(lib().zkp_srs_shape(self._h, ctypes.byref(a), ctypes.byref(b)))
+        return a.value, b.value
+
+    # ---- hot path (bytes in, bytes out)
+    def worker_commit(self, i: int, poly_be: bytes) -> bytes:
+        out = ctypes.create_string_buffer(48)
+        check(lib().zkp_worker_commit(self._h, i, poly_be, len(poly_be) // 32, out))
+        return out.raw
+
+    def worker_open(self, i: int, poly_be: bytes, x_be: bytes) -> Tuple[bytes, bytes]:
+        y = ctypes.create_string_buffer(32)
+        proof = ctypes.create_string_buffer(48)
+        check(lib().zkp_worker_open(self._h, i, poly_be, len(poly_be) // 32, x_be, y, proof))
+        return y.raw, proof.raw
+
+    def worker_commit_open(self, i: int, poly_be: bytes, x_be: bytes) -> Tuple[bytes, bytes, bytes]:
+        com = ctypes.create_string_buffer(48)
+        y = ctypes.create_string_buffer(32)
+        proof = ctypes.create_string_buffer(48)
+        check(lib().zkp_worker_commit_open(self._h, i, poly_be, len(poly_be) // 32, x_be, com, y, proof))
+        return com.raw, y.raw, proof.raw
+
+    def worker_verify(self, i: int, proof48: bytes, alpha_be: bytes, eval_be: bytes, commitment48: bytes) -> bool:
+        valid = ctypes.c_int(0)
+        check(lib().zkp_worker_verify(self._h, i, proof48, alpha_be, eval_be, commitment48, ctypes.byref(valid)))
+        return bool(valid.value)
+
+    def fft(self, vals_be: bytes, left: bool = True, inverse: bool = False) -> bytes:
+        out = ctypes.create_string_buffer(len(vals_be))
+        check(lib().zkp_fft(self._h, vals_be, len(vals_be) // 32, int(left), int(inverse), out))
+        return out.raw
+
+    def eval(self, coeffs_be: bytes, x_be: bytes) -> bytes:
+        out = ctypes.create_string_buffer(32)
+        check(lib().zkp_eval(self._h, coeffs_be, len(coeffs_be) // 32, x_be, out))
+        return out.raw
+
+    def random_poly(self, seed: int, count: int) -> bytes:
+        out = ctypes.create_string_buffer(32 * count)
+        check(lib().zkp_random_poly(self._h, seed, out, count))
+        return out.raw
+
+    def random_point(self, seed: int) -> bytes:
+        out = ctypes.create_string_buffer(32)
+        check(lib().zkp_random_point(self._h, seed, out))
+        return out.raw
+
+    def msm_g1(self, row: int, scalars_be: bytes) -> bytes:
+        out = ctypes.create_string_buffer(48)
+        check(lib().zkp_msm_g1(self._h, row, scalars_be, len(scalars_be) // 32, out))
+        return out.raw
+
+    # ---- bench / tuning
+    def set_msm_window(self, c: int) -> None:
+        check(lib().zkp_set_msm_window(self._h, c))
+
+    def msm_info(self, n: int) -> Tuple[int, int, int]:
+        c, w, m = ctypes.c_uint32(), ctypes.c_uint32(), ctypes.c_uint64()
+        check(lib().zkp_msm_info(self._h, n, ctypes.byref(c), ctypes.byref(w), ctypes.byref(m)))
+        return c.value, w.value, m.value
+
+    def bench_msm(self, row: int, scalars_be: bytes, reps: int, flush_l2: bool = True) -> Tuple[float, bytes]:
+        ms = ctypes.c_float()
+        out = ctypes.create_string_buffer(48)
+        check(lib().zkp_bench_msm(self._h, row, scalars_be, len(scalars_be) // 32, reps, int(flush_l2), ctypes.byref(ms), out))
+        return ms.value, out.raw
+
+    def bench_commit_open(self, row: int, poly_be: bytes, x_be: bytes, reps: int, flush_l2: bool = True):
+        ms, ms_k, launches = ctypes.c_float(), ctypes.c_float(), ctypes.c_uint32()
+        com = ctypes.create_string_buffer(48)
+        y = ctypes.create_string_buffer(32)
+        proof = ctypes.create_string_buffer(48)
+        check(lib().zkp_bench_commit_open(self._h, row, poly_be, len(poly_be) // 32, x_be, reps, int(flush_l2),
+                                          ctypes.byref(ms), ctypes.byref(ms_k), ctypes.byref(launches), com, y, proof))
+        return ms.value, ms_k.value, launches.value, com.raw, y.raw, proof.raw
+
+    def bench_ntt(self, n: int, reps: int, inverse: bool = False) -> float:
+        ms = ctypes.c_float()
+        check(lib().zkp_bench_ntt(self._h, n, reps, int(inverse), ctypes.byref(ms)))
+        return ms.value
+
+
+def b64_decode_fr(strs: bytes, stride: int, count: int) -> bytes:
+    out = ctypes.create_string_buffer(32 * count)
+    check(lib().zkp_b64_decode_fr(strs, stride, count, out))
+    return out.raw
+
+
+def b64_encode_fr(vals_be: bytes) -> bytes:
+    count = len(vals_be) // 32
+    out = ctypes.create_string_buffer(43 * count)
+    check(lib().zkp_b64_encode_fr(vals_be, count, out))
+    return out.raw
+
+
+def pairing_check(g1_48: bytes, g2_192: bytes) -> bool:
+    pairs = len(g1_48) // 48
+    res = ctypes.c_int(0)
+    check(lib().zkp_pairing_check(g1_48, g2_192, pairs, ctypes.byref(res)))
+    return bool(res.value)
