@@ -1,21 +1,636 @@
-// remaining C-ABI entries (filled in as the path widens)
+// C-ABI entries beyond the raw MSM: opening, fused commit+open, verify, fft, eval, RNG, SRS
+// generation / files, wire codec and the benchmark entries.  Included at the end of zkp_b200.cu.
 #pragma once
-extern "C" {
-#define ZKP_TODO(name, ...) int name(__VA_ARGS__) { return zkp::fail(ZKP_ERR_STATE, #name ": not implemented yet"); }
-ZKP_TODO(zkp_srs_generate, zkp_ctx*, const uint8_t*, const uint8_t*, uint32_t, uint32_t)
-ZKP_TODO(zkp_srs_save, zkp_ctx*, const char*)
-ZKP_TODO(zkp_srs_load, zkp_ctx*, const char*)
-ZKP_TODO(zkp_worker_open, zkp_ctx*, uint32_t, const uint8_t*, size_t, const uint8_t*, uint8_t*, uint8_t*)
-ZKP_TODO(zkp_worker_commit_open, zkp_ctx*, uint32_t, const uint8_t*, size_t, const uint8_t*, uint8_t*, uint8_t*, uint8_t*)
-ZKP_TODO(zkp_worker_verify, zkp_ctx*, uint32_t, const uint8_t*, const uint8_t*, const uint8_t*, const uint8_t*, int*)
-ZKP_TODO(zkp_fft, zkp_ctx*, const uint8_t*, size_t, int, int, uint8_t*)
-ZKP_TODO(zkp_eval, zkp_ctx*, const uint8_t*, size_t, const uint8_t*, uint8_t*)
-ZKP_TODO(zkp_random_poly, zkp_ctx*, uint64_t, uint8_t*, size_t)
-ZKP_TODO(zkp_random_point, zkp_ctx*, uint64_t, uint8_t*)
-ZKP_TODO(zkp_b64_decode_fr, const char*, size_t, size_t, uint8_t*)
-ZKP_TODO(zkp_b64_encode_fr, const uint8_t*, size_t, char*)
-ZKP_TODO(zkp_bench_msm, zkp_ctx*, uint32_t, const uint8_t*, size_t, int, int, float*, uint8_t*)
-ZKP_TODO(zkp_bench_commit_open, zkp_ctx*, uint32_t, const uint8_t*, size_t, const uint8_t*, int, int, float*, float*, uint32_t*, uint8_t*, uint8_t*, uint8_t*)
-ZKP_TODO(zkp_bench_ntt, zkp_ctx*, size_t, int, int, float*)
-ZKP_TODO(zkp_pairing_check, const uint8_t*, const uint8_t*, size_t, int*)
+#include <chrono>
+
+namespace {
+
+using host::Fr64;
+using host::Fq64;
+
+// ---- per-size domain tables ------------------------------------------------------------------
+Fr64 fr_root_of_unity(uint32_t log_n) {
+    // 7^((r-1) >> log_n)
+    uint64_t e[4];
+    memcpy(e, host::FR_MOD64, sizeof(e));
+    e[0] -= 1;
+    for (uint32_t s = 0; s < log_n; s++)
+        for (int i = 0; i < 4; i++) e[i] = (e[i] >> 1) | (i + 1 < 4 ? e[i + 1] << 63 : 0);
+    return Fr64::from_u64(7).pow(e, 4);
 }
+Fr to_dev(const Fr64& a) {
+    Fr r;
+    memcpy(r.v, a.v, 32);
+    return r;
+}
+
+int get_domain(zkp_ctx* ctx, uint32_t log_n, bool need_tw, zkp_ctx::Domain** out) {
+    if (log_n >= ctx->domains.size()) return fail(ZKP_ERR_ARG, "domain too large");
+    zkp_ctx::Domain& d = ctx->domains[log_n];
+    if (!d.ready) {
+        d.w = fr_root_of_unity(log_n);
+        d.w_inv = d.w.inverse();
+        d.n_inv = Fr64::from_u64(1ull << log_n).inverse();
+        std::vector<Fr64> wt(log_n + 1);
+        wt[0] = d.w;
+        for (uint32_t k = 1; k <= log_n; k++) wt[k] = wt[k - 1].sqr();
+        ZKP_CUDA(d.wt.ensure(32 * (log_n + 1)));
+        ZKP_CUDA(cudaMemcpyAsync(d.wt.p, wt.data(), 32 * (log_n + 1), cudaMemcpyHostToDevice, ctx->stream));
+        ZKP_CUDA(cudaStreamSynchronize(ctx->stream));
+        d.ready = true;
+    }
+    if (need_tw && !d.have_tw && log_n >= 1) {
+        uint32_t half = 1u << (log_n - 1);
+        ZKP_CUDA(d.tw.ensure((size_t)half * 32));
+        uint32_t threads = (half + 15) / 16;
+        k_build_twiddles<<<(threads + 127) / 128, 128, 0, ctx->stream>>>(d.tw.as<Fr>(), half, d.wt.as<Fr>());
+        ctx->launches++;
+        d.have_tw = true;
+    }
+    *out = &d;
+    return ZKP_OK;
+}
+
+// small device scratch layout (ctx->small): [0] bad flag, [4] hit, [32] y, [64] s1, [96] s2, [128] eval
+constexpr size_t SM_BAD = 0, SM_HIT = 4, SM_Y = 32, SM_S1 = 64, SM_S2 = 96, SM_EVAL = 128, SM_BYTES = 256;
+
+int ensure_small(zkp_ctx* ctx) {
+    ZKP_CUDA(ctx->small.ensure(SM_BYTES));
+    return ZKP_OK;
+}
+template <class T> T* small_at(zkp_ctx* ctx, size_t off) { return reinterpret_cast<T*>(ctx->small.as<uint8_t>() + off); }
+
+// ---- opening on device: f (Montgomery, n elements) -> y (device, SM_Y) and q (Montgomery, fr_c)
+int open_device(zkp_ctx* ctx, const Fr* d_f, uint32_t n, const Fr64& x) {
+    uint32_t log_n = ilog2(n);
+    zkp_ctx::Domain* dom;
+    int rc = get_domain(ctx, log_n, false, &dom);
+    if (rc) return rc;
+    cudaStream_t st = ctx->stream;
+    ZKP_CUDA(ctx->fr_b.ensure((size_t)n * 32));
+    ZKP_CUDA(ctx->fr_c.ensure((size_t)n * 32));
+    uint32_t E = n >> 14;
+    if (E < 8) E = 8;
+    if (E > 64) E = 64;
+    uint32_t threads = (n + E - 1) / E, blocks = (threads + 127) / 128;
+    uint32_t blocks2 = (n + 255) / 256;
+    ZKP_CUDA(ctx->partials.ensure((size_t)(blocks > blocks2 ? blocks : blocks2) * 32));
+    ZKP_CUDA(cudaMemsetAsync(small_at<uint32_t>(ctx, SM_HIT), 0xff, 4, st));
+    k_open_pass1<<<blocks, 128, 0, st>>>(d_f, n, E, to_dev(x), dom->wt.as<Fr>(), to_dev(dom->w_inv), ctx->fr_b.as<Fr>(),
+                                         ctx->partials.as<Fr>(), small_at<uint32_t>(ctx, SM_HIT));
+    k_fr_reduce<<<1, 256, 0, st>>>(ctx->partials.as<Fr>(), blocks, small_at<Fr>(ctx, SM_S1));
+    k_open_y<<<1, 32, 0, st>>>(d_f, log_n, to_dev(x), to_dev(dom->n_inv), small_at<Fr>(ctx, SM_S1), small_at<uint32_t>(ctx, SM_HIT),
+                               small_at<Fr>(ctx, SM_Y));
+    k_open_pass2<<<blocks2, 256, 0, st>>>(d_f, ctx->fr_b.as<Fr>(), n, small_at<Fr>(ctx, SM_Y), ctx->fr_c.as<Fr>());
+    // x in the domain (rare): q_m = -sum_{j != m} q_j w^(j-m); the kernels are no-ops otherwise
+    k_open_fix_partial<<<blocks2, 256, 0, st>>>(ctx->fr_c.as<Fr>(), n, dom->wt.as<Fr>(), small_at<uint32_t>(ctx, SM_HIT),
+                                                ctx->partials.as<Fr>());
+    k_fr_reduce<<<1, 256, 0, st>>>(ctx->partials.as<Fr>(), blocks2, small_at<Fr>(ctx, SM_S2));
+    k_open_fix_apply<<<1, 32, 0, st>>>(ctx->fr_c.as<Fr>(), small_at<uint32_t>(ctx, SM_HIT), small_at<Fr>(ctx, SM_S2));
+    ctx->launches += 7;
+    return ZKP_OK;
+}
+
+// upload poly (big-endian), convert to Montgomery in fr_a; leaves the raw bytes in ctx->scalars
+int upload_poly(zkp_ctx* ctx, const uint8_t* poly_be, size_t n) {
+    int rc = upload_scalars(ctx, poly_be, n, ctx->scalars);
+    if (rc) return rc;
+    rc = ensure_small(ctx);
+    if (rc) return rc;
+    ZKP_CUDA(ctx->fr_a.ensure(n * 32));
+    ZKP_CUDA(cudaMemsetAsync(small_at<uint32_t>(ctx, SM_BAD), 0, 4, ctx->stream));
+    k_fr_from_be<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(ctx->scalars.as<uint32_t>(), n, ctx->fr_a.as<Fr>(),
+                                                                       small_at<uint32_t>(ctx, SM_BAD));
+    ctx->launches++;
+    return ZKP_OK;
+}
+
+// read back y (big-endian) and the bad-encoding flag; synchronises
+int fetch_y(zkp_ctx* ctx, uint8_t eval_be[32]) {
+    k_fr_to_be<<<1, 32, 0, ctx->stream>>>(small_at<Fr>(ctx, SM_Y), 1, small_at<uint32_t>(ctx, SM_EVAL));
+    ctx->launches++;
+    ZKP_CUDA(cudaMemcpyAsync(ctx->h_small, small_at<uint8_t>(ctx, SM_EVAL), 32, cudaMemcpyDeviceToHost, ctx->stream));
+    ZKP_CUDA(cudaMemcpyAsync(ctx->h_small + 64, small_at<uint8_t>(ctx, SM_BAD), 4, cudaMemcpyDeviceToHost, ctx->stream));
+    ZKP_CUDA(cudaStreamSynchronize(ctx->stream));
+    if (*reinterpret_cast<uint32_t*>(ctx->h_small + 64)) return fail(ZKP_ERR_ENCODING, "polynomial holds a non-canonical field element");
+    memcpy(eval_be, ctx->h_small, 32);
+    return ZKP_OK;
+}
+
+int open_checks(zkp_ctx* ctx, uint32_t i, const void* poly, size_t n, const uint8_t* x_be, Fr64* x) {
+    int rc = check_row(ctx, i, n);
+    if (rc) return rc;
+    if (!poly || !x_be) return fail(ZKP_ERR_ARG, "null argument");
+    if (n != ((size_t)1 << ctx->log_n)) return fail(ZKP_ERR_ARG, "opening needs exactly one SRS row of evaluations");
+    if (!Fr64::from_be(*x, x_be)) return fail(ZKP_ERR_ENCODING, "evaluation point is not canonical");
+    return ZKP_OK;
+}
+
+// the full device part of commit (optional) + open with the polynomial already resident
+int commit_open_resident(zkp_ctx* ctx, uint32_t i, size_t n, const Fr64& x, uint8_t* commitment48, uint8_t eval_be[32],
+                         uint8_t proof48[48]) {
+    int rc;
+    if (commitment48) {
+        rc = msm_device(ctx, i, ctx->scalars.as<uint32_t>(), SCALAR_BE, n, commitment48);
+        if (rc) return rc;
+    }
+    rc = open_device(ctx, ctx->fr_a.as<Fr>(), (uint32_t)n, x);
+    if (rc) return rc;
+    rc = msm_device(ctx, i, ctx->fr_c.as<uint32_t>(), SCALAR_MONT, n, proof48);
+    if (rc) return rc;
+    return fetch_y(ctx, eval_be);
+}
+
+void flush_l2(zkp_ctx* ctx) {
+    const size_t bytes = 256ull << 20;  // > 126 MB L2
+    if (ctx->flush.ensure(bytes) == cudaSuccess) cudaMemsetAsync(ctx->flush.p, 0x5a, bytes, ctx->stream);
+}
+
+// NTT on device buffers (Montgomery form).  out may alias in.
+int ntt_device(zkp_ctx* ctx, const Fr* in, Fr* out, uint32_t log_n, int inverse) {
+    if (log_n == 0) {
+        if (in != out) ZKP_CUDA(cudaMemcpyAsync(out, in, 32, cudaMemcpyDeviceToDevice, ctx->stream));
+        return ZKP_OK;
+    }
+    if (log_n > 2 * NTT_MAX_TILE_LOG) return fail(ZKP_ERR_ARG, "NTT size above 2^24 not supported");
+    zkp_ctx::Domain* dom;
+    int rc = get_domain(ctx, log_n, true, &dom);
+    if (rc) return rc;
+    const Fr n_inv = to_dev(dom->n_inv);
+    const size_t smem_per_elt = 32;
+    if (log_n <= NTT_MAX_TILE_LOG) {
+        NttPass p = {log_n, 0, 1, 1, 0, 1, 0, 1, log_n, 0, (uint32_t)inverse, (uint32_t)inverse};
+        k_ntt_pass<<<1, NTT_THREADS, smem_per_elt << log_n, ctx->stream>>>(in, out, dom->tw.as<Fr>(), p, n_inv);
+        ctx->launches++;
+        return ZKP_OK;
+    }
+    uint32_t l1 = log_n / 2, l2 = log_n - l1;
+    uint64_t n1 = 1ull << l1, n2 = 1ull << l2;
+    ZKP_CUDA(ctx->ntt_tmp.ensure(32ull << log_n));
+    Fr* tmp = ctx->ntt_tmp.as<Fr>();
+    uint32_t lc1 = NTT_MAX_TILE_LOG - l1, lc2 = NTT_MAX_TILE_LOG - l2;
+    if (lc1 > 3) lc1 = 3;  // 8 columns = 256-byte runs; more columns only lengthen the tile
+    if (lc2 > 3) lc2 = 3;
+    // pass 1: columns i2 (n2 of them), rows i1; element (r, c) at r*n2 + c; twiddle w^(c*k)
+    NttPass p1 = {l1, lc1, (uint32_t)n2, n2, 1, n2, 1, 0, log_n, 1, (uint32_t)inverse, 0};
+    k_ntt_pass<<<(unsigned)(n2 >> lc1), NTT_THREADS, smem_per_elt << (l1 + lc1), ctx->stream>>>(in, tmp, dom->tw.as<Fr>(), p1, n_inv);
+    // pass 2: columns k1 (n1 of them), rows i2; element (r, c) at c*n2 + r; output (k2, c) at k2*n1 + c
+    NttPass p2 = {l2, lc2, (uint32_t)n1, 1, n2, n1, 1, 1, log_n, 0, (uint32_t)inverse, (uint32_t)inverse};
+    k_ntt_pass<<<(unsigned)(n1 >> lc2), NTT_THREADS, smem_per_elt << (l2 + lc2), ctx->stream>>>(tmp, out, dom->tw.as<Fr>(), p2, n_inv);
+    ctx->launches += 2;
+    return ZKP_OK;
+}
+
+// fixed-base table [d * 256^w]G, d < 256, w < 32 (affine, Montgomery), built on the host once
+int ensure_fixed_base(zkp_ctx* ctx) {
+    if (ctx->fixed_base.p) return ZKP_OK;
+    using namespace host;
+    std::vector<G1J> jac(32 * 256);
+    G1J base = g1_generator();
+    for (int w = 0; w < 32; w++) {
+        jac[w * 256] = G1J::infinity();
+        for (int d = 1; d < 256; d++) jac[w * 256 + d] = jac[w * 256 + d - 1].add(base);
+        base = jac[w * 256 + 255].add(base);
+    }
+    // batch to affine
+    std::vector<Fq64> pre(jac.size());
+    Fq64 run = Fq64::one();
+    for (size_t k = 0; k < jac.size(); k++) {
+        pre[k] = run;
+        if (!jac[k].is_inf()) run = run * jac[k].z;
+    }
+    Fq64 inv = run.inverse();
+    std::vector<uint8_t> tab(jac.size() * 96, 0);
+    for (size_t k = jac.size(); k-- > 0;) {
+        if (jac[k].is_inf()) continue;
+        Fq64 zi = inv * pre[k];
+        inv = inv * jac[k].z;
+        Fq64 zi2 = zi.sqr();
+        Fq64 ax = jac[k].x * zi2, ay = jac[k].y * zi2 * zi;
+        memcpy(&tab[k * 96], ax.v, 48);
+        memcpy(&tab[k * 96 + 48], ay.v, 48);
+    }
+    ZKP_CUDA(ctx->fixed_base.ensure(tab.size()));
+    ZKP_CUDA(cudaMemcpy(ctx->fixed_base.p, tab.data(), tab.size(), cudaMemcpyHostToDevice));
+    return ZKP_OK;
+}
+
+void set_pairing_lines(zkp_ctx* ctx) {
+    ctx->lines_g2 = host::g2_precompute(host::g2_generator());
+    ctx->lines_tau = host::g2_precompute(ctx->g2_tau);
+    ctx->have_lines = true;
+}
+
+}  // namespace
+
+extern "C" {
+
+// ---------------------------------------------------------------------------------------------- SRS
+int zkp_srs_generate(zkp_ctx* ctx, const uint8_t tau_x_be[32], const uint8_t tau_y_be[32], uint32_t log_n,
+                     uint32_t log_machines) {
+    if (!ctx || !tau_x_be || !tau_y_be) return fail(ZKP_ERR_ARG, "null argument");
+    Fr64 tx, ty;
+    if (!Fr64::from_be(tx, tau_x_be) || !Fr64::from_be(ty, tau_y_be)) return fail(ZKP_ERR_ENCODING, "trapdoor not canonical");
+    int rc = zkp_srs_set_shape(ctx, log_n, log_machines);
+    if (rc) return rc;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    DeviceGuard g(ctx->device);
+    rc = ensure_small(ctx);
+    if (rc) return rc;
+    rc = ensure_fixed_base(ctx);
+    if (rc) return rc;
+    const uint32_t n = 1u << log_n, M = 1u << log_machines;
+    cudaStream_t st = ctx->stream;
+    zkp_ctx::Domain* dom;
+    rc = get_domain(ctx, log_n, false, &dom);
+    if (rc) return rc;
+    // inv_d[j] = 1/(w^j - tau_x) in fr_b
+    ZKP_CUDA(ctx->fr_b.ensure((size_t)n * 32));
+    ZKP_CUDA(ctx->fr_c.ensure((size_t)n * 32));
+    uint32_t E = 16, threads = (n + E - 1) / E, blocks = (threads + 127) / 128;
+    ZKP_CUDA(ctx->partials.ensure((size_t)blocks * 32));
+    ZKP_CUDA(cudaMemsetAsync(small_at<uint32_t>(ctx, SM_HIT), 0xff, 4, st));
+    k_open_pass1<<<blocks, 128, 0, st>>>(nullptr, n, E, to_dev(tx), dom->wt.as<Fr>(), to_dev(dom->w_inv), ctx->fr_b.as<Fr>(),
+                                         ctx->partials.as<Fr>(), small_at<uint32_t>(ctx, SM_HIT));
+    ctx->launches++;
+    uint32_t hit = 0;
+    ZKP_CUDA(cudaMemcpyAsync(&hit, small_at<uint32_t>(ctx, SM_HIT), 4, cudaMemcpyDeviceToHost, st));
+    ZKP_CUDA(cudaStreamSynchronize(st));
+    if (hit != HIT_NONE) return fail(ZKP_ERR_ARG, "tau_x lies in the evaluation domain");
+    // zn = (tau_x^n - 1)/n
+    Fr64 zn = tx;
+    for (uint32_t k = 0; k < log_n; k++) zn = zn.sqr();
+    zn = (zn - Fr64::one()) * dom->n_inv;
+    // R_i(tau_y) over the size-M domain
+    std::vector<Fr64> R(M);
+    if (M == 1) {
+        R[0] = Fr64::one();
+    } else {
+        Fr64 wM = fr_root_of_unity(log_machines), zm = ty;
+        for (uint32_t k = 0; k < log_machines; k++) zm = zm.sqr();
+        zm = (zm - Fr64::one()) * Fr64::from_u64(M).inverse();
+        Fr64 wi = Fr64::one();
+        for (uint32_t i = 0; i < M; i++) {
+            Fr64 d = ty - wi;
+            if (d.is_zero()) return fail(ZKP_ERR_ARG, "tau_y lies in the machine domain");
+            R[i] = zm * wi * d.inverse();
+            wi = wi * wM;
+        }
+    }
+    // rows
+    size_t xyzz_bytes = (size_t)n * sizeof(G1Xyzz);
+    ZKP_CUDA(ctx->ws.buckets.ensure(xyzz_bytes));
+    ZKP_CUDA(ctx->ws.pool.ensure((size_t)n * sizeof(Fq)));
+    for (uint32_t i = 0; i < M; i++) {
+        Fr64 coef = (zn * R[i]).neg();
+        k_lagrange_scalars<<<((n + 7) / 8 + 127) / 128, 128, 0, st>>>(ctx->fr_b.as<Fr>(), n, dom->wt.as<Fr>(), to_dev(coef),
+                                                                      ctx->fr_c.as<Fr>());
+        k_fixed_base_mul<<<(n + 127) / 128, 128, 0, st>>>(ctx->fr_c.as<Fr>(), n, ctx->fixed_base.as<G1Affine>(),
+                                                          ctx->ws.buckets.as<G1Xyzz>());
+        uint32_t EA = 16, ta = (n + EA - 1) / EA;
+        k_xyzz_to_affine<<<(ta + 127) / 128, 128, 0, st>>>(ctx->ws.buckets.as<G1Xyzz>(), n, EA, ctx->ws.pool.as<Fq>(),
+                                                           ctx->srs.as<G1Affine>() + ((size_t)i << log_n));
+        ctx->launches += 3;
+        Fr64 rc_canon = R[i].from_mont();
+        ctx->scale_points[i] = host::g1_generator().mul(rc_canon.v, 4);
+        ctx->row_loaded[i] = 1;
+    }
+    ZKP_CUDA(cudaStreamSynchronize(st));
+    ZKP_CUDA(cudaGetLastError());
+    Fr64 txc = tx.from_mont();
+    ctx->g2_tau = host::g2_generator().mul(txc.v, 4);
+    ctx->have_g2_tau = true;
+    set_pairing_lines(ctx);
+    return ZKP_OK;
+}
+
+int zkp_srs_import_g2_tau(zkp_ctx* ctx, const uint8_t tau_x_be[32]) {
+    if (!ctx || !tau_x_be) return fail(ZKP_ERR_ARG, "null argument");
+    Fr64 t;
+    if (!Fr64::from_be(t, tau_x_be)) return fail(ZKP_ERR_ENCODING, "tau not canonical");
+    Fr64 c = t.from_mont();
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    ctx->g2_tau = host::g2_generator().mul(c.v, 4);
+    ctx->have_g2_tau = true;
+    set_pairing_lines(ctx);
+    return ZKP_OK;
+}
+
+// file: "ZKPB200S" | u32 version | u32 log_n | u32 log_m | G2 tau affine (4 x 48 B BE) |
+//       M x 48 B compressed scale points | M*n x 96 B uncompressed points
+int zkp_srs_save(zkp_ctx* ctx, const char* path) {
+    if (!ctx || !path) return fail(ZKP_ERR_ARG, "null argument");
+    if (!ctx->shaped || !ctx->have_g2_tau) return fail(ZKP_ERR_STATE, "SRS incomplete");
+    FILE* f = fopen(path, "wb");
+    if (!f) return fail(ZKP_ERR_IO, std::string("cannot open ") + path);
+    uint32_t hdr[3] = {1, ctx->log_n, ctx->log_m};
+    bool ok = fwrite("ZKPB200S", 1, 8, f) == 8 && fwrite(hdr, 4, 3, f) == 3;
+    host::Fq2 gx, gy;
+    ctx->g2_tau.to_affine(gx, gy);
+    uint8_t g2[192];
+    gx.c0.to_be(g2); gx.c1.to_be(g2 + 48); gy.c0.to_be(g2 + 96); gy.c1.to_be(g2 + 144);
+    ok = ok && fwrite(g2, 1, 192, f) == 192;
+    size_t M = (size_t)1 << ctx->log_m, n = (size_t)1 << ctx->log_n;
+    for (size_t i = 0; i < M && ok; i++) {
+        uint8_t sp[48];
+        host::g1_compress(sp, ctx->scale_points[i]);
+        ok = fwrite(sp, 1, 48, f) == 48;
+    }
+    std::vector<uint8_t> row(n * 96);
+    for (size_t i = 0; i < M && ok; i++) {
+        int rc = zkp_srs_export_row(ctx, (uint32_t)i, row.data(), n);
+        if (rc) { fclose(f); return rc; }
+        ok = fwrite(row.data(), 1, row.size(), f) == row.size();
+    }
+    fclose(f);
+    return ok ? ZKP_OK : fail(ZKP_ERR_IO, "short write");
+}
+
+int zkp_srs_load(zkp_ctx* ctx, const char* path) {
+    if (!ctx || !path) return fail(ZKP_ERR_ARG, "null argument");
+    FILE* f = fopen(path, "rb");
+    if (!f) return fail(ZKP_ERR_IO, std::string("cannot open ") + path);
+    char magic[8];
+    uint32_t hdr[3];
+    uint8_t g2[192];
+    if (fread(magic, 1, 8, f) != 8 || memcmp(magic, "ZKPB200S", 8) || fread(hdr, 4, 3, f) != 3 || hdr[0] != 1 ||
+        fread(g2, 1, 192, f) != 192) {
+        fclose(f);
+        return fail(ZKP_ERR_IO, "not a zkp_b200 SRS file");
+    }
+    int rc = zkp_srs_set_shape(ctx, hdr[1], hdr[2]);
+    if (rc) { fclose(f); return rc; }
+    host::Fq2 gx, gy;
+    if (!Fq64::from_be(gx.c0, g2) || !Fq64::from_be(gx.c1, g2 + 48) || !Fq64::from_be(gy.c0, g2 + 96) ||
+        !Fq64::from_be(gy.c1, g2 + 144) || !host::g2_on_curve(gx, gy)) {
+        fclose(f);
+        return fail(ZKP_ERR_ENCODING, "bad G2 point in SRS file");
+    }
+    size_t M = (size_t)1 << hdr[2], n = (size_t)1 << hdr[1];
+    std::vector<uint8_t> sp(M * 48), row(n * 96);
+    if (fread(sp.data(), 1, sp.size(), f) != sp.size()) { fclose(f); return fail(ZKP_ERR_IO, "short read"); }
+    for (size_t i = 0; i < M; i++) {
+        if (fread(row.data(), 1, row.size(), f) != row.size()) { fclose(f); return fail(ZKP_ERR_IO, "short read"); }
+        rc = zkp_srs_import_row(ctx, (uint32_t)i, row.data(), n, &sp[i * 48]);
+        if (rc) { fclose(f); return rc; }
+    }
+    fclose(f);
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    ctx->g2_tau = host::G2J::from_affine(gx, gy);
+    ctx->have_g2_tau = true;
+    set_pairing_lines(ctx);
+    return ZKP_OK;
+}
+
+// ---------------------------------------------------------------------------------------------- open
+int zkp_worker_open(zkp_ctx* ctx, uint32_t i, const uint8_t* poly_be, size_t n, const uint8_t x_be[32], uint8_t eval_be[32],
+                    uint8_t proof48[48]) {
+    Fr64 x;
+    int rc = open_checks(ctx, i, poly_be, n, x_be, &x);
+    if (rc) return rc;
+    if (!eval_be || !proof48) return fail(ZKP_ERR_ARG, "null output");
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    DeviceGuard g(ctx->device);
+    rc = upload_poly(ctx, poly_be, n);
+    if (rc) return rc;
+    return commit_open_resident(ctx, i, n, x, nullptr, eval_be, proof48);
+}
+
+int zkp_worker_commit_open(zkp_ctx* ctx, uint32_t i, const uint8_t* poly_be, size_t n, const uint8_t x_be[32],
+                           uint8_t commitment48[48], uint8_t eval_be[32], uint8_t proof48[48]) {
+    Fr64 x;
+    int rc = open_checks(ctx, i, poly_be, n, x_be, &x);
+    if (rc) return rc;
+    if (!commitment48 || !eval_be || !proof48) return fail(ZKP_ERR_ARG, "null output");
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    DeviceGuard g(ctx->device);
+    rc = upload_poly(ctx, poly_be, n);
+    if (rc) return rc;
+    return commit_open_resident(ctx, i, n, x, commitment48, eval_be, proof48);
+}
+
+// ---------------------------------------------------------------------------------------------- verify
+int zkp_worker_verify(zkp_ctx* ctx, uint32_t i, const uint8_t proof48[48], const uint8_t alpha_be[32], const uint8_t eval_be[32],
+                      const uint8_t commitment48[48], int* valid) {
+    if (!ctx || !proof48 || !alpha_be || !eval_be || !commitment48 || !valid) return fail(ZKP_ERR_ARG, "null argument");
+    *valid = 0;
+    if (!ctx->shaped || !ctx->have_lines) return fail(ZKP_ERR_STATE, "SRS (G2 part) not loaded");
+    if (i >= (1u << ctx->log_m)) return fail(ZKP_ERR_ARG, "worker index out of range");
+    using namespace host;
+    G1J proof, com;
+    Fr64 alpha, y;
+    // malformed inputs are a failed verification, not an error (reference tests/test_validator.py:66,79-86)
+    if (!g1_decompress(proof, proof48) || !g1_decompress(com, commitment48)) return ZKP_OK;
+    if (!Fr64::from_be(alpha, alpha_be) || !Fr64::from_be(y, eval_be)) return ZKP_OK;
+    Fr64 ac = alpha.from_mont(), yc = y.from_mont();
+    G1J scale;
+    {
+        std::lock_guard<std::mutex> lk(ctx->mu);
+        scale = ctx->scale_points[i];
+    }
+    // A = C - y*S_i + alpha*pi ;  e(A, g2) * e(-pi, [tau]_2) == 1
+    G1J a = com.add(scale.mul(yc.v, 4).neg()).add(proof.mul(ac.v, 4));
+    std::vector<G1AffineHost> ps = {g1_affine_host(a), g1_affine_host(proof.neg())};
+    std::vector<const G2Lines*> qs = {&ctx->lines_g2, &ctx->lines_tau};
+    *valid = pairing_product_is_one(ps, qs) ? 1 : 0;
+    return ZKP_OK;
+}
+
+int zkp_pairing_check(const uint8_t* g1_48, const uint8_t* g2_192, size_t pairs, int* is_one) {
+    if (!g1_48 || !g2_192 || !is_one) return fail(ZKP_ERR_ARG, "null argument");
+    using namespace host;
+    std::vector<G1AffineHost> ps;
+    std::vector<G2Lines> lines(pairs);
+    std::vector<const G2Lines*> qs;
+    for (size_t k = 0; k < pairs; k++) {
+        G1J p;
+        if (!g1_decompress(p, g1_48 + 48 * k)) return fail(ZKP_ERR_ENCODING, "bad G1 point");
+        Fq2 x, y;
+        const uint8_t* q = g2_192 + 192 * k;
+        if (!Fq64::from_be(x.c0, q) || !Fq64::from_be(x.c1, q + 48) || !Fq64::from_be(y.c0, q + 96) || !Fq64::from_be(y.c1, q + 144) ||
+            !g2_on_curve(x, y))
+            return fail(ZKP_ERR_ENCODING, "bad G2 point");
+        lines[k] = g2_precompute(G2J::from_affine(x, y));
+        ps.push_back(g1_affine_host(p));
+    }
+    for (size_t k = 0; k < pairs; k++) qs.push_back(&lines[k]);
+    *is_one = pairing_product_is_one(ps, qs) ? 1 : 0;
+    return ZKP_OK;
+}
+
+// ---------------------------------------------------------------------------------------------- fft / eval / rng
+int zkp_fft(zkp_ctx* ctx, const uint8_t* in_be, size_t n, int left, int inverse, uint8_t* out_be) {
+    (void)left;  // a 1-D transform of length n uses w_n whichever axis of the bivariate grid it is
+    if (!ctx || !in_be || !out_be) return fail(ZKP_ERR_ARG, "null argument");
+    if (!is_pow2(n)) return fail(ZKP_ERR_ARG, "fft length must be a power of two");
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    DeviceGuard g(ctx->device);
+    int rc = upload_poly(ctx, in_be, n);
+    if (rc) return rc;
+    rc = ntt_device(ctx, ctx->fr_a.as<Fr>(), ctx->fr_a.as<Fr>(), ilog2(n), inverse);
+    if (rc) return rc;
+    k_fr_to_be<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(ctx->fr_a.as<Fr>(), n, ctx->scalars.as<uint32_t>());
+    ctx->launches++;
+    ZKP_CUDA(cudaMemcpyAsync(out_be, ctx->scalars.p, n * 32, cudaMemcpyDeviceToHost, ctx->stream));
+    ZKP_CUDA(cudaMemcpyAsync(ctx->h_small + 64, small_at<uint8_t>(ctx, SM_BAD), 4, cudaMemcpyDeviceToHost, ctx->stream));
+    ZKP_CUDA(cudaStreamSynchronize(ctx->stream));
+    ZKP_CUDA(cudaGetLastError());
+    if (*reinterpret_cast<uint32_t*>(ctx->h_small + 64)) return fail(ZKP_ERR_ENCODING, "non-canonical field element");
+    return ZKP_OK;
+}
+
+int zkp_eval(zkp_ctx* ctx, const uint8_t* coeffs_be, size_t n, const uint8_t x_be[32], uint8_t y_be[32]) {
+    if (!ctx || !coeffs_be || !x_be || !y_be || !n) return fail(ZKP_ERR_ARG, "bad argument");
+    Fr64 x;
+    if (!Fr64::from_be(x, x_be)) return fail(ZKP_ERR_ENCODING, "evaluation point is not canonical");
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    DeviceGuard g(ctx->device);
+    int rc = upload_poly(ctx, coeffs_be, n);
+    if (rc) return rc;
+    // x^(2^k) table
+    std::vector<Fr64> xt(34);
+    xt[0] = x;
+    for (size_t k = 1; k < xt.size(); k++) xt[k] = xt[k - 1].sqr();
+    ZKP_CUDA(ctx->fr_b.ensure(xt.size() * 32));
+    memcpy(ctx->h_small + 128, xt.data(), xt.size() * 32);
+    ZKP_CUDA(cudaMemcpyAsync(ctx->fr_b.p, ctx->h_small + 128, xt.size() * 32, cudaMemcpyHostToDevice, ctx->stream));
+    uint32_t E = 16, threads = (uint32_t)((n + E - 1) / E), blocks = (threads + 127) / 128;
+    ZKP_CUDA(ctx->partials.ensure((size_t)blocks * 32));
+    k_eval_partial<<<blocks, 128, 0, ctx->stream>>>(ctx->fr_a.as<Fr>(), (uint32_t)n, E, to_dev(x), ctx->fr_b.as<Fr>(), ctx->partials.as<Fr>());
+    k_fr_reduce<<<1, 256, 0, ctx->stream>>>(ctx->partials.as<Fr>(), blocks, small_at<Fr>(ctx, SM_Y));
+    ctx->launches += 2;
+    return fetch_y(ctx, y_be);
+}
+
+int zkp_random_poly(zkp_ctx* ctx, uint64_t seed, uint8_t* out_be, size_t count) {
+    if (!ctx || !out_be || !count) return fail(ZKP_ERR_ARG, "bad argument");
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    DeviceGuard g(ctx->device);
+    ZKP_CUDA(ctx->scalars.ensure(count * 32));
+    k_random_fr<<<(unsigned)((count + 255) / 256), 256, 0, ctx->stream>>>(seed, count, ctx->scalars.as<uint32_t>());
+    ctx->launches++;
+    ZKP_CUDA(cudaMemcpyAsync(out_be, ctx->scalars.p, count * 32, cudaMemcpyDeviceToHost, ctx->stream));
+    ZKP_CUDA(cudaStreamSynchronize(ctx->stream));
+    return ZKP_OK;
+}
+
+int zkp_random_point(zkp_ctx* ctx, uint64_t seed, uint8_t out_be[32]) { return zkp_random_poly(ctx, seed ^ 0x706f696e74ull, out_be, 1); }
+
+// ---------------------------------------------------------------------------------------------- codec
+int zkp_b64_decode_fr(const char* strs, size_t stride, size_t count, uint8_t* out_be) {
+    if (!strs || !out_be || stride < 43) return fail(ZKP_ERR_ARG, "bad argument");
+    for (size_t i = 0; i < count; i++)
+        if (!codec::b64_decode32(strs + i * stride, out_be + 32 * i)) return fail(ZKP_ERR_ENCODING, "invalid base64 field element");
+    return ZKP_OK;
+}
+int zkp_b64_encode_fr(const uint8_t* in_be, size_t count, char* out_strs) {
+    if (!in_be || !out_strs) return fail(ZKP_ERR_ARG, "null argument");
+    for (size_t i = 0; i < count; i++) codec::b64_encode32(in_be + 32 * i, out_strs + 43 * i);
+    return ZKP_OK;
+}
+
+// ---------------------------------------------------------------------------------------------- bench
+int zkp_bench_msm(zkp_ctx* ctx, uint32_t row, const uint8_t* scalars_be, size_t n, int reps, int do_flush, float* ms_per_msm,
+                  uint8_t out48[48]) {
+    int rc = check_row(ctx, row, n);
+    if (rc) return rc;
+    if (!scalars_be || !ms_per_msm || !out48 || reps < 1) return fail(ZKP_ERR_ARG, "bad argument");
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    DeviceGuard g(ctx->device);
+    rc = upload_scalars(ctx, scalars_be, n, ctx->scalars);
+    if (rc) return rc;
+    cudaEvent_t e0, e1;
+    ZKP_CUDA(cudaEventCreate(&e0));
+    ZKP_CUDA(cudaEventCreate(&e1));
+    double total = 0;
+    for (int r = 0; r < reps && !rc; r++) {
+        if (do_flush) flush_l2(ctx);
+        cudaEventRecord(e0, ctx->stream);
+        rc = msm_device(ctx, row, ctx->scalars.as<uint32_t>(), SCALAR_BE, n, out48);
+        cudaEventRecord(e1, ctx->stream);
+        cudaEventSynchronize(e1);
+        float ms = 0;
+        cudaEventElapsedTime(&ms, e0, e1);
+        total += ms;
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    *ms_per_msm = (float)(total / reps);
+    return rc;
+}
+
+int zkp_bench_commit_open(zkp_ctx* ctx, uint32_t row, const uint8_t* poly_be, size_t n, const uint8_t x_be[32], int reps, int do_flush,
+                          float* ms_per_iter, float* ms_msm_kernel, uint32_t* launches, uint8_t commitment48[48], uint8_t eval_be[32],
+                          uint8_t proof48[48]) {
+    Fr64 x;
+    int rc = open_checks(ctx, row, poly_be, n, x_be, &x);
+    if (rc) return rc;
+    if (!ms_per_iter || !commitment48 || !eval_be || !proof48 || reps < 1) return fail(ZKP_ERR_ARG, "bad argument");
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    DeviceGuard g(ctx->device);
+    rc = upload_poly(ctx, poly_be, n);  // resident in HBM before the timed region
+    if (rc) return rc;
+    ZKP_CUDA(cudaStreamSynchronize(ctx->stream));
+    cudaEvent_t e0, e1;
+    ZKP_CUDA(cudaEventCreate(&e0));
+    ZKP_CUDA(cudaEventCreate(&e1));
+    double total = 0;
+    uint64_t launches0 = ctx->launches;
+    ctx->time_acc = true;
+    ctx->acc_ms_total = 0;
+    ctx->acc_count = 0;
+    for (int r = 0; r < reps && !rc; r++) {
+        if (do_flush) flush_l2(ctx);
+        cudaEventRecord(e0, ctx->stream);
+        rc = commit_open_resident(ctx, row, n, x, commitment48, eval_be, proof48);
+        cudaEventRecord(e1, ctx->stream);
+        cudaEventSynchronize(e1);
+        float ms = 0;
+        cudaEventElapsedTime(&ms, e0, e1);
+        total += ms;
+    }
+    ctx->time_acc = false;
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    *ms_per_iter = (float)(total / reps);
+    if (ms_msm_kernel) *ms_msm_kernel = ctx->acc_count ? (float)(ctx->acc_ms_total / ctx->acc_count) : 0.f;
+    if (launches) *launches = (uint32_t)((ctx->launches - launches0) / reps);
+    return rc;
+}
+
+int zkp_bench_ntt(zkp_ctx* ctx, size_t n, int reps, int inverse, float* ms_per_ntt) {
+    if (!ctx || !ms_per_ntt || !is_pow2(n) || reps < 1) return fail(ZKP_ERR_ARG, "bad argument");
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    DeviceGuard g(ctx->device);
+    ZKP_CUDA(ctx->fr_a.ensure(n * 32));
+    ZKP_CUDA(ctx->fr_b.ensure(n * 32));
+    ZKP_CUDA(ctx->scalars.ensure(n * 32));
+    k_random_fr<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(0xB200, n, ctx->scalars.as<uint32_t>());
+    int rc = ensure_small(ctx);
+    if (rc) return rc;
+    k_fr_from_be<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(ctx->scalars.as<uint32_t>(), n, ctx->fr_a.as<Fr>(),
+                                                                       small_at<uint32_t>(ctx, SM_BAD));
+    rc = ntt_device(ctx, ctx->fr_a.as<Fr>(), ctx->fr_b.as<Fr>(), ilog2(n), inverse);  // warm-up, builds tables
+    if (rc) return rc;
+    cudaEvent_t e0, e1;
+    ZKP_CUDA(cudaEventCreate(&e0));
+    ZKP_CUDA(cudaEventCreate(&e1));
+    double total = 0;
+    for (int r = 0; r < reps && !rc; r++) {
+        flush_l2(ctx);
+        cudaEventRecord(e0, ctx->stream);
+        rc = ntt_device(ctx, ctx->fr_a.as<Fr>(), ctx->fr_b.as<Fr>(), ilog2(n), inverse);
+        cudaEventRecord(e1, ctx->stream);
+        cudaEventSynchronize(e1);
+        float ms = 0;
+        cudaEventElapsedTime(&ms, e0, e1);
+        total += ms;
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    ZKP_CUDA(cudaGetLastError());
+    *ms_per_ntt = (float)(total / reps);
+    return rc;
+}
+
+}  // extern "C"

@@ -6,7 +6,7 @@
 #include <vector>
 
 #include "../../include/zkp_b200.h"
-#include "host/curve.hpp"
+#include "host/pairing.hpp"
 #include "msm.cuh"
 
 namespace zkp {
@@ -49,12 +49,15 @@ struct DevBuf {
 };
 
 struct MsmWorkspace {
-    DevBuf keys_a, keys_b, vals_a, vals_b, cub_temp, buckets, next_a, next_b, pool, sums_a, sums_b;
+    DevBuf keys_a, keys_b, vals_a, vals_b, cub_temp, buckets, next_a, next_b, pool, sums_a, sums_b, bad;
     std::vector<DevBuf> slot_keys, slot_pts;
     G1Xyzz* h_window = nullptr;  // pinned, W records
     size_t h_window_cap = 0;
+    uint32_t* h_bad = nullptr;   // pinned
     void release() {
-        for (DevBuf* b : {&keys_a, &keys_b, &vals_a, &vals_b, &cub_temp, &buckets, &next_a, &next_b, &pool, &sums_a, &sums_b})
+        if (h_bad) cudaFreeHost(h_bad);
+        h_bad = nullptr;
+        for (DevBuf* b : {&keys_a, &keys_b, &vals_a, &vals_b, &cub_temp, &buckets, &next_a, &next_b, &pool, &sums_a, &sums_b, &bad})
             b->release();
         for (auto& b : slot_keys) b.release();
         for (auto& b : slot_pts) b.release();
@@ -84,4 +87,21 @@ struct zkp_ctx {
     zkp::MsmWorkspace ws;
     uint32_t c_override = 0;
     uint64_t launches = 0;                    // kernels launched by this context (bench accounting)
+    // per-size domain tables: wt[k] = w_n^(2^k) (k <= log_n), tw[e] = w_n^e (e < n/2, built on demand)
+    struct Domain {
+        bool ready = false, have_tw = false;
+        zkp::DevBuf wt, tw;
+        zkp::host::Fr64 w, w_inv, n_inv;
+    };
+    std::vector<Domain> domains = std::vector<Domain>(32);
+    zkp::DevBuf small, partials, ntt_tmp, fixed_base;  // device scalars / block partial sums / NTT scratch / [d*256^w]G table
+    uint8_t* h_small = nullptr;               // pinned scratch (>= 256 B)
+    // pairing data fixed per SRS
+    zkp::host::G2Lines lines_g2, lines_tau;
+    bool have_lines = false;
+    // kernel timing of the dominant kernel (k_accumulate level 0), enabled by the bench entries
+    bool time_acc = false;
+    cudaEvent_t ev_acc0 = nullptr, ev_acc1 = nullptr;
+    double acc_ms_total = 0;
+    uint64_t acc_count = 0;
 };

@@ -1,1 +1,215 @@
+// Fr-side kernels of the KZG path: wire codec (32-byte big-endian <-> Montgomery limbs), the
+// evaluation-form opening  y = f(x),  q_j = (f_j - y)/(w^j - x)  behind worker_open
+// (reference neurons/miner.py:47-54), coefficient-form Horner behind Client.eval
+// (reference neurons/validator.py:97-104; pinned by tests/test_miner.py:33-55) and the challenge RNG.
+//
+// Opening math (barycentric form on the natural-order domain {w^j}):
+//     f(x) = (x^n - 1)/n * sum_j f_j w^j / (x - w^j)            x outside the domain
+//     q_j  = (f_j - y) / (w^j - x)
+//     x = w^m:  y = f_m,  q_m = - sum_{j != m} q_j w^(j-m)
+// The n inversions use Montgomery's trick per thread over a run of E consecutive elements
+// (prefix products parked in the output buffer, one Fermat inversion per run).
 #pragma once
+#include <cuda_runtime.h>
+
+#include "ff.cuh"
+
+namespace zkp {
+
+constexpr uint32_t HIT_NONE = 0xffffffffu;
+
+__device__ __forceinline__ Fr load_fr(const Fr* p) {
+    const uint4* s = reinterpret_cast<const uint4*>(p);
+    uint4 a = s[0], b = s[1];
+    Fr r;
+    r.v[0] = a.x; r.v[1] = a.y; r.v[2] = a.z; r.v[3] = a.w;
+    r.v[4] = b.x; r.v[5] = b.y; r.v[6] = b.z; r.v[7] = b.w;
+    return r;
+}
+__device__ __forceinline__ void store_fr(Fr* p, const Fr& r) {
+    uint4* d = reinterpret_cast<uint4*>(p);
+    d[0] = make_uint4(r.v[0], r.v[1], r.v[2], r.v[3]);
+    d[1] = make_uint4(r.v[4], r.v[5], r.v[6], r.v[7]);
+}
+__device__ __forceinline__ bool fr_lt_mod(const Fr& a) {
+    for (int i = 7; i >= 0; i--) {
+        uint32_t m = FrParams::mod(i);
+        if (a.v[i] < m) return true;
+        if (a.v[i] > m) return false;
+    }
+    return false;
+}
+__device__ __forceinline__ Fr fr_bswap_load(const uint32_t* w) {
+    const uint4* s = reinterpret_cast<const uint4*>(w);
+    uint4 a = s[0], b = s[1];
+    Fr r;
+    r.v[7] = __byte_perm(a.x, 0, 0x0123); r.v[6] = __byte_perm(a.y, 0, 0x0123);
+    r.v[5] = __byte_perm(a.z, 0, 0x0123); r.v[4] = __byte_perm(a.w, 0, 0x0123);
+    r.v[3] = __byte_perm(b.x, 0, 0x0123); r.v[2] = __byte_perm(b.y, 0, 0x0123);
+    r.v[1] = __byte_perm(b.z, 0, 0x0123); r.v[0] = __byte_perm(b.w, 0, 0x0123);
+    return r;
+}
+__device__ __forceinline__ void fr_bswap_store(uint32_t* w, const Fr& r) {
+    uint4* d = reinterpret_cast<uint4*>(w);
+    d[0] = make_uint4(__byte_perm(r.v[7], 0, 0x0123), __byte_perm(r.v[6], 0, 0x0123),
+                      __byte_perm(r.v[5], 0, 0x0123), __byte_perm(r.v[4], 0, 0x0123));
+    d[1] = make_uint4(__byte_perm(r.v[3], 0, 0x0123), __byte_perm(r.v[2], 0, 0x0123),
+                      __byte_perm(r.v[1], 0, 0x0123), __byte_perm(r.v[0], 0, 0x0123));
+}
+
+// 32-byte big-endian canonical -> Montgomery limbs; *bad |= 1 if any value >= r
+__global__ void k_fr_from_be(const uint32_t* __restrict__ in, size_t n, Fr* __restrict__ out, uint32_t* __restrict__ bad) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    Fr c = fr_bswap_load(in + i * 8);
+    if (!fr_lt_mod(c)) atomicOr(bad, 1u);
+    store_fr(out + i, c.to_mont());
+}
+__global__ void k_fr_to_be(const Fr* __restrict__ in, size_t n, uint32_t* __restrict__ out) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    fr_bswap_store(out + i * 8, load_fr(in + i).from_mont());
+}
+
+// w^e from the table wt[k] = w^(2^k)
+__device__ __forceinline__ Fr pow_from_table(const Fr* __restrict__ wt, uint64_t e) {
+    Fr acc = Fr::one();
+    for (int k = 0; e; k++, e >>= 1)
+        if (e & 1) acc = acc * load_fr(wt + k);
+    return acc;
+}
+
+// block-wide sum of one Fr per thread -> partial[blockIdx.x] (blockDim.x <= 256, power of two)
+__device__ __forceinline__ void block_sum_store(const Fr& v, Fr* __restrict__ partial) {
+    __shared__ Fr sh[256];
+    sh[threadIdx.x] = v;
+    __syncthreads();
+    for (int s = blockDim.x / 2; s > 0; s >>= 1) {
+        if ((int)threadIdx.x < s) sh[threadIdx.x] = sh[threadIdx.x] + sh[threadIdx.x + s];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) store_fr(partial + blockIdx.x, sh[0]);
+}
+// single block: out[0] = sum of count partials
+__global__ void k_fr_reduce(const Fr* __restrict__ partial, uint32_t count, Fr* __restrict__ out) {
+    Fr acc = Fr::zero();
+    for (uint32_t i = threadIdx.x; i < count; i += blockDim.x) acc = acc + load_fr(partial + i);
+    block_sum_store(acc, out);
+}
+
+// ---- opening, pass 1: inv_d[j] = 1/(w^j - x), partial sums of f_j w^j / (w^j - x).
+// Thread t owns elements [t*E, (t+1)*E).  wt[k] = w^(2^k), wt_inv[0] = w^-1.
+__global__ void __launch_bounds__(128)
+k_open_pass1(const Fr* __restrict__ f, uint32_t n, uint32_t E, Fr x, const Fr* __restrict__ wt, Fr w_inv,
+             Fr* __restrict__ inv_d, Fr* __restrict__ partial, uint32_t* __restrict__ hit) {
+    uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    uint64_t lo = (uint64_t)t * E;
+    Fr s1 = Fr::zero();
+    if (lo < n) {
+        uint32_t cnt = n - lo < E ? (uint32_t)(n - lo) : E;
+        const Fr w = load_fr(wt);
+        Fr a = pow_from_table(wt, lo);  // w^lo
+        Fr run = Fr::one();
+        // forward: prefix products of d_j parked in inv_d
+        for (uint32_t i = 0; i < cnt; i++) {
+            Fr d = a - x;
+            if (d.is_zero()) {
+                atomicMin(hit, (uint32_t)(lo + i));
+                d = Fr::one();
+            }
+            run = run * d;
+            store_fr(inv_d + lo + i, run);
+            if (i + 1 < cnt) a = a * w;
+        }
+        Fr u = run.inverse();  // 1 / (d_0 ... d_{cnt-1})
+        // backward: a currently holds w^(lo+cnt-1)
+        for (int i = (int)cnt - 1; i >= 0; i--) {
+            Fr d = a - x;
+            bool zero = d.is_zero();
+            if (zero) d = Fr::one();
+            Fr inv = i > 0 ? u * load_fr(inv_d + lo + i - 1) : u;
+            u = u * d;
+            store_fr(inv_d + lo + i, inv);
+            if (f && !zero) s1 = s1 + load_fr(f + lo + i) * a * inv;
+            if (i > 0) a = a * w_inv;
+        }
+    }
+    block_sum_store(s1, partial);
+}
+
+// y = f(x):  hit -> f[hit], else -(x^n - 1)/n * S1.   Single thread.
+__global__ void k_open_y(const Fr* __restrict__ f, uint32_t log_n, Fr x, Fr n_inv, const Fr* __restrict__ s1,
+                         const uint32_t* __restrict__ hit, Fr* __restrict__ y) {
+    if (threadIdx.x || blockIdx.x) return;
+    if (*hit != HIT_NONE) {
+        store_fr(y, load_fr(f + *hit));
+        return;
+    }
+    Fr xn = x;
+    for (uint32_t k = 0; k < log_n; k++) xn = xn.sqr();
+    Fr zn = (xn - Fr::one()) * n_inv;
+    store_fr(y, (zn * load_fr(s1)).neg());
+}
+
+// ---- opening, pass 2: q_j = (f_j - y) * inv_d_j   (Montgomery form; the MSM's digit kernel converts)
+__global__ void k_open_pass2(const Fr* __restrict__ f, const Fr* __restrict__ inv_d, uint32_t n, const Fr* __restrict__ y,
+                             Fr* __restrict__ q) {
+    uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n) return;
+    Fr yy = load_fr(y);
+    store_fr(q + j, (load_fr(f + j) - yy) * load_fr(inv_d + j));
+}
+
+// ---- x = w^m: partial sums of q_j w^(j-m), j != m; then q_m = -sum
+__global__ void k_open_fix_partial(const Fr* __restrict__ q, uint32_t n, const Fr* __restrict__ wt,
+                                   const uint32_t* __restrict__ hit, Fr* __restrict__ partial) {
+    uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+    Fr v = Fr::zero();
+    uint32_t m = *hit;
+    if (m != HIT_NONE && j < n && j != m) v = load_fr(q + j) * pow_from_table(wt, (uint64_t)((j + n - m) & (n - 1)));
+    block_sum_store(v, partial);
+}
+__global__ void k_open_fix_apply(Fr* __restrict__ q, const uint32_t* __restrict__ hit, const Fr* __restrict__ s2) {
+    if (threadIdx.x || blockIdx.x) return;
+    if (*hit != HIT_NONE) store_fr(q + *hit, load_fr(s2).neg());
+}
+
+// ---- Horner on coefficient form: thread t evaluates its run of E coefficients and scales by x^(tE)
+// xt[k] = x^(2^k)
+__global__ void __launch_bounds__(128)
+k_eval_partial(const Fr* __restrict__ c, uint32_t n, uint32_t E, Fr x, const Fr* __restrict__ xt, Fr* __restrict__ partial) {
+    uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    uint64_t lo = (uint64_t)t * E;
+    Fr acc = Fr::zero();
+    if (lo < n) {
+        uint32_t cnt = n - lo < E ? (uint32_t)(n - lo) : E;
+        for (int i = (int)cnt - 1; i >= 0; i--) acc = acc * x + load_fr(c + lo + i);
+        acc = acc * pow_from_table(xt, lo);
+    }
+    block_sum_store(acc, partial);
+}
+
+// ---- challenge RNG: counter-based SplitMix64, 255-bit candidates, rejection until < r
+__global__ void k_random_fr(uint64_t seed, size_t n, uint32_t* __restrict__ out_be) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    Fr v;
+    for (uint64_t attempt = 0;; attempt++) {
+        uint64_t s = seed + 0x9e3779b97f4a7c15ull * (4 * (i * 64 + attempt) + 1);
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            s += 0x9e3779b97f4a7c15ull;
+            uint64_t z = s;
+            z = (z ^ (z >> 30)) * 0xbf58476d1ce4e5b9ull;
+            z = (z ^ (z >> 27)) * 0x94d049bb133111ebull;
+            z ^= z >> 31;
+            v.v[2 * k] = (uint32_t)z;
+            v.v[2 * k + 1] = (uint32_t)(z >> 32);
+        }
+        v.v[7] &= 0x7fffffffu;
+        if (fr_lt_mod(v)) break;
+    }
+    fr_bswap_store(out_be + i * 8, v);
+}
+
+}  // namespace zkp

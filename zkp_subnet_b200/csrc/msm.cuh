@@ -101,23 +101,42 @@ inline MsmPlan msm_make_plan(uint32_t n, int sm_count, uint32_t c_override = 0) 
 // ------------------------------------------------------------------------------------------------
 // 1. signed-digit decomposition
 // ------------------------------------------------------------------------------------------------
-// scalars: 8 x u32 per scalar.  big_endian != 0: the 32 bytes are the big-endian wire format
-// (reference base/protocol.py:35-40 poly strings after base64 decoding); else little-endian limbs.
+// scalars: 8 x u32 per scalar.  fmt: SCALAR_BE = the 32-byte big-endian wire format (reference
+// base/protocol.py:35-40 poly strings after base64 decoding), SCALAR_LE = canonical little-endian limbs,
+// SCALAR_MONT = little-endian Montgomery limbs (output of the opening kernels).  Non-canonical
+// inputs (>= r) set *bad.
+enum { SCALAR_LE = 0, SCALAR_BE = 1, SCALAR_MONT = 2 };
 __global__ void k_decompose(const uint32_t* __restrict__ scalars, uint32_t n, uint32_t c, uint32_t W,
-                            uint32_t B, uint32_t discard, int big_endian, uint32_t* __restrict__ keys,
-                            uint32_t* __restrict__ vals) {
+                            uint32_t B, uint32_t discard, int fmt, uint32_t* __restrict__ keys,
+                            uint32_t* __restrict__ vals, uint32_t* __restrict__ bad) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     uint32_t s[9];
     const uint4* src = reinterpret_cast<const uint4*>(scalars + (size_t)i * 8);
     uint4 a = src[0], b = src[1];
-    if (big_endian) {
+    if (fmt == SCALAR_BE) {
         s[7] = __byte_perm(a.x, 0, 0x0123); s[6] = __byte_perm(a.y, 0, 0x0123);
         s[5] = __byte_perm(a.z, 0, 0x0123); s[4] = __byte_perm(a.w, 0, 0x0123);
         s[3] = __byte_perm(b.x, 0, 0x0123); s[2] = __byte_perm(b.y, 0, 0x0123);
         s[1] = __byte_perm(b.z, 0, 0x0123); s[0] = __byte_perm(b.w, 0, 0x0123);
     } else {
         s[0] = a.x; s[1] = a.y; s[2] = a.z; s[3] = a.w; s[4] = b.x; s[5] = b.y; s[6] = b.z; s[7] = b.w;
+    }
+    if (fmt == SCALAR_MONT) {
+        Fr m;
+#pragma unroll
+        for (int k = 0; k < 8; k++) m.v[k] = s[k];
+        m = m.from_mont();
+#pragma unroll
+        for (int k = 0; k < 8; k++) s[k] = m.v[k];
+    } else {
+        bool lt = false, decided = false;
+#pragma unroll
+        for (int k = 7; k >= 0; k--) {
+            uint32_t mk = FrParams::mod(k);
+            if (!decided && s[k] != mk) { decided = true; lt = s[k] < mk; }
+        }
+        if (!lt) atomicOr(bad, 1u);
     }
     s[8] = 0;
     uint32_t carry = 0;

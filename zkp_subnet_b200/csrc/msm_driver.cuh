@@ -12,7 +12,7 @@ inline uint64_t msm_fq_muls(const MsmPlan& p) {
 
 // Launches the whole device pipeline on ctx->stream and copies the W window sums to pinned host
 // memory; synchronises the stream before returning.
-inline int msm_run(zkp_ctx* ctx, const MsmPlan& plan, const uint32_t* d_scalars, int big_endian,
+inline int msm_run(zkp_ctx* ctx, const MsmPlan& plan, const uint32_t* d_scalars, int fmt,
                    const G1Affine* d_points) {
     MsmWorkspace& ws = ctx->ws;
     cudaStream_t st = ctx->stream;
@@ -36,10 +36,13 @@ inline int msm_run(zkp_ctx* ctx, const MsmPlan& plan, const uint32_t* d_scalars,
         ZKP_CUDA(cudaMallocHost(&ws.h_window, sizeof(G1Xyzz) * plan.W));
         ws.h_window_cap = plan.W;
     }
+    if (!ws.h_bad) ZKP_CUDA(cudaMallocHost(&ws.h_bad, 8));
 
     // 1. digits
+    ZKP_CUDA(ws.bad.ensure(8));
+    ZKP_CUDA(cudaMemsetAsync(ws.bad.p, 0, 4, st));
     k_decompose<<<(plan.n + 255) / 256, 256, 0, st>>>(d_scalars, plan.n, plan.c, plan.W, plan.B, plan.discard,
-                                                      big_endian, ws.keys_a.as<uint32_t>(), ws.vals_a.as<uint32_t>());
+                                                      fmt, ws.keys_a.as<uint32_t>(), ws.vals_a.as<uint32_t>(), ws.bad.as<uint32_t>());
     ctx->launches++;
     // 2. sort by (window, bucket)
     size_t temp_bytes = 0;
@@ -57,10 +60,12 @@ inline int msm_run(zkp_ctx* ctx, const MsmPlan& plan, const uint32_t* d_scalars,
         int last = l + 1 == plan.levels.size();
         unsigned blocks = (unsigned)((lv.threads + 127) / 128);
         if (l == 0) {
+            if (ctx->time_acc) cudaEventRecord(ctx->ev_acc0, st);
             k_accumulate<true><<<blocks, 128, 0, st>>>(ws.keys_b.as<uint32_t>(), ws.vals_b.as<uint32_t>(), d_points, nullptr,
                                                        lv.items, lv.L, plan.discard, ws.buckets.as<G1Xyzz>(),
                                                        last ? nullptr : ws.slot_keys[0].as<uint32_t>(),
                                                        last ? nullptr : ws.slot_pts[0].as<G1Xyzz>(), last);
+            if (ctx->time_acc) cudaEventRecord(ctx->ev_acc1, st);
         } else {
             k_accumulate<false><<<blocks, 128, 0, st>>>(ws.slot_keys[l - 1].as<uint32_t>(), nullptr, nullptr,
                                                         ws.slot_pts[l - 1].as<G1Xyzz>(), lv.items, lv.L, plan.discard,
@@ -112,8 +117,17 @@ inline int msm_run(zkp_ctx* ctx, const MsmPlan& plan, const uint32_t* d_scalars,
         if (parts == 1) break;
     }
     ZKP_CUDA(cudaMemcpyAsync(ws.h_window, sin, sizeof(G1Xyzz) * plan.W, cudaMemcpyDeviceToHost, st));
+    ZKP_CUDA(cudaMemcpyAsync(ws.h_bad, ws.bad.p, 4, cudaMemcpyDeviceToHost, st));
     ZKP_CUDA(cudaStreamSynchronize(st));
     ZKP_CUDA(cudaGetLastError());
+    if (ctx->time_acc) {
+        float ms = 0;
+        if (cudaEventElapsedTime(&ms, ctx->ev_acc0, ctx->ev_acc1) == cudaSuccess) {
+            ctx->acc_ms_total += ms;
+            ctx->acc_count++;
+        }
+    }
+    if (*ws.h_bad) return fail(ZKP_ERR_ENCODING, "scalar is not a canonical field element (>= r)");
     return ZKP_OK;
 }
 

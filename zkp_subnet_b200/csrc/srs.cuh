@@ -3,6 +3,7 @@
 // (replaces `prover setup --generate-setup --generate-precompute`, reference tests/conftest.py:50-65).
 #pragma once
 #include "g1.cuh"
+#include "kzg.cuh"
 
 namespace zkp {
 
@@ -70,6 +71,72 @@ __global__ void k_points_to_be96(const G1Affine* __restrict__ in, size_t n, uint
     for (int k = 0; k < 12; k++) {
         w[k] = __byte_perm(x.v[11 - k], 0, 0x0123);
         w[12 + k] = __byte_perm(y.v[11 - k], 0, 0x0123);
+    }
+}
+
+
+// ---- generation from a public test trapdoor ------------------------------------------------------
+// out[j] = coef * w^j * inv_d[j]   (Lagrange basis values: coef = -(tau^n - 1)/n * R_i(tau_y),
+// inv_d[j] = 1/(w^j - tau))
+__global__ void k_lagrange_scalars(const Fr* __restrict__ inv_d, uint32_t n, const Fr* __restrict__ wt, Fr coef,
+                                   Fr* __restrict__ out) {
+    constexpr uint32_t E = 8;
+    uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    uint64_t lo = (uint64_t)t * E;
+    if (lo >= n) return;
+    Fr a = pow_from_table(wt, lo) * coef;
+    const Fr w = load_fr(wt);
+    for (uint32_t i = 0; i < E && lo + i < n; i++) {
+        store_fr(out + lo + i, a * load_fr(inv_d + lo + i));
+        a = a * w;
+    }
+}
+
+// [s]G for Montgomery-form scalars with the fixed-base table tab[w*256 + d] = [d * 256^w]G (affine)
+__global__ void __launch_bounds__(128)
+k_fixed_base_mul(const Fr* __restrict__ scalars, size_t n, const G1Affine* __restrict__ tab, G1Xyzz* __restrict__ out) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    Fr s = load_fr(scalars + i).from_mont();
+    G1Xyzz acc = G1Xyzz::infinity();
+    for (int w = 0; w < 32; w++) {
+        uint32_t d = (s.v[w >> 2] >> ((w & 3) * 8)) & 0xff;
+        if (d) {
+            G1Affine p = tab[w * 256 + d];
+            acc.madd(p.x, p.y, 0);
+        }
+    }
+    out[i] = acc;
+}
+
+// XYZZ -> affine with one inversion per run of E points (prefix products parked in scratch)
+__global__ void __launch_bounds__(128)
+k_xyzz_to_affine(const G1Xyzz* __restrict__ in, size_t n, uint32_t E, Fq* __restrict__ scratch, G1Affine* __restrict__ out) {
+    size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    size_t lo = t * E;
+    if (lo >= n) return;
+    uint32_t cnt = n - lo < E ? (uint32_t)(n - lo) : E;
+    Fq run = Fq::one();
+    for (uint32_t i = 0; i < cnt; i++) {
+        Fq z = in[lo + i].zzz;
+        if (z.is_zero()) z = Fq::one();
+        run = run * z;
+        scratch[lo + i] = run;
+    }
+    Fq u = run.inverse();
+    for (int i = (int)cnt - 1; i >= 0; i--) {
+        G1Xyzz p = in[lo + i];
+        G1Affine a;
+        if (p.zz.is_zero()) {
+            a.x = Fq::zero(); a.y = Fq::zero();
+        } else {
+            Fq zzz_inv = i > 0 ? u * scratch[lo + i - 1] : u;
+            u = u * p.zzz;
+            Fq t2 = p.zz * zzz_inv;  // ZZ / ZZZ ; its square is 1 / ZZ
+            a.x = p.x * t2.sqr();
+            a.y = p.y * zzz_inv;
+        }
+        out[lo + i] = a;
     }
 }
 

@@ -60,9 +60,9 @@ int finish_point(const MsmPlan& plan, zkp_ctx* ctx, uint8_t out48[48]) {
 }
 
 // MSM over row `row` with device-resident scalars
-int msm_device(zkp_ctx* ctx, uint32_t row, const uint32_t* d_scalars, int big_endian, size_t n, uint8_t out48[48]) {
+int msm_device(zkp_ctx* ctx, uint32_t row, const uint32_t* d_scalars, int fmt, size_t n, uint8_t out48[48]) {
     MsmPlan plan = msm_make_plan((uint32_t)n, ctx->sm_count, ctx->c_override);
-    int rc = msm_run(ctx, plan, d_scalars, big_endian, row_ptr(ctx, row));
+    int rc = msm_run(ctx, plan, d_scalars, fmt, row_ptr(ctx, row));
     if (rc) return rc;
     return finish_point(plan, ctx, out48);
 }
@@ -93,6 +93,10 @@ int zkp_ctx_create(int device, zkp_ctx** out) {
     ZKP_CUDA(cudaGetDeviceProperties(&prop, device));
     ctx->sm_count = prop.multiProcessorCount;
     ZKP_CUDA(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+    ZKP_CUDA(cudaMallocHost(&ctx->h_small, 4096));
+    ZKP_CUDA(cudaEventCreate(&ctx->ev_acc0));
+    ZKP_CUDA(cudaEventCreate(&ctx->ev_acc1));
+    ZKP_CUDA(cudaFuncSetAttribute(k_ntt_pass, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * 16 * (1 << NTT_MAX_TILE_LOG)));
     *out = ctx.release();
     return ZKP_OK;
 }
@@ -103,7 +107,13 @@ void zkp_ctx_destroy(zkp_ctx* ctx) {
         DeviceGuard g(ctx->device);
         cudaStreamSynchronize(ctx->stream);
         ctx->ws.release();
-        for (DevBuf* b : {&ctx->srs, &ctx->scalars, &ctx->fr_a, &ctx->fr_b, &ctx->fr_c, &ctx->flush}) b->release();
+        for (DevBuf* b : {&ctx->srs, &ctx->scalars, &ctx->fr_a, &ctx->fr_b, &ctx->fr_c, &ctx->flush, &ctx->small, &ctx->partials,
+                          &ctx->ntt_tmp, &ctx->fixed_base})
+            b->release();
+        for (auto& d : ctx->domains) { d.wt.release(); d.tw.release(); }
+        if (ctx->h_small) cudaFreeHost(ctx->h_small);
+        cudaEventDestroy(ctx->ev_acc0);
+        cudaEventDestroy(ctx->ev_acc1);
         cudaStreamDestroy(ctx->stream);
     }
     delete ctx;
@@ -187,17 +197,6 @@ int zkp_srs_export_row(zkp_ctx* ctx, uint32_t row, uint8_t* points96, size_t n) 
     return ZKP_OK;
 }
 
-int zkp_srs_import_g2_tau(zkp_ctx* ctx, const uint8_t tau_x_be[32]) {
-    if (!ctx || !tau_x_be) return fail(ZKP_ERR_ARG, "null argument");
-    host::Fr64 t;
-    if (!host::Fr64::from_be(t, tau_x_be)) return fail(ZKP_ERR_ENCODING, "tau not canonical");
-    host::Fr64 c = t.from_mont();
-    std::lock_guard<std::mutex> lk(ctx->mu);
-    ctx->g2_tau = host::g2_generator().mul(c.v, 4);
-    ctx->have_g2_tau = true;
-    return ZKP_OK;
-}
-
 // ------------------------------------------------------------------------------------------ hot path
 int zkp_msm_g1(zkp_ctx* ctx, uint32_t row, const uint8_t* scalars_be, size_t n, uint8_t out48[48]) {
     int rc = check_row(ctx, row, n);
@@ -207,7 +206,7 @@ int zkp_msm_g1(zkp_ctx* ctx, uint32_t row, const uint8_t* scalars_be, size_t n, 
     DeviceGuard g(ctx->device);
     rc = upload_scalars(ctx, scalars_be, n, ctx->scalars);
     if (rc) return rc;
-    return msm_device(ctx, row, ctx->scalars.as<uint32_t>(), 1, n, out48);
+    return msm_device(ctx, row, ctx->scalars.as<uint32_t>(), SCALAR_BE, n, out48);
 }
 
 int zkp_worker_commit(zkp_ctx* ctx, uint32_t i, const uint8_t* poly_be, size_t n, uint8_t commitment48[48]) {
