@@ -52,6 +52,14 @@ int zkp_device_count(void);
  *      (Lagrange basis over the natural-order domains), plus [R_i(tau_y)]_1 per row and [tau_x]_2. */
 int zkp_srs_generate(zkp_ctx* ctx, const uint8_t tau_x_be[32], const uint8_t tau_y_be[32],
                      uint32_t log_n, uint32_t log_machines);
+/* point-range shard `shard` of 2^log_shards of the same SRS: rows hold points j in
+ * [shard*n/S, (shard+1)*n/S); an MSM over the row with the matching scalar slice is one GPU's partial
+ * commitment (MSM sharding by point range) */
+int zkp_srs_generate_shard(zkp_ctx* ctx, const uint8_t tau_x_be[32], const uint8_t tau_y_be[32],
+                           uint32_t log_n, uint32_t log_machines, uint32_t shard, uint32_t log_shards);
+/* sum of `count` compressed G1 points: the cross-GPU combine of partial commitments / Pianist
+ * aggregation com = sum_i com_i, pi = sum_i pi_i (host arithmetic, 48 bytes per GPU) */
+int zkp_g1_sum(const uint8_t* points48, size_t count, uint8_t out48[48]);
 /* import one row from 96-byte ZCash-uncompressed points (validated on curve), and its scale point */
 int zkp_srs_set_shape(zkp_ctx* ctx, uint32_t log_n, uint32_t log_machines);
 int zkp_srs_import_row(zkp_ctx* ctx, uint32_t row, const uint8_t* points96, size_t n,

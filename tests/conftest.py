@@ -1,0 +1,27 @@
+import json
+import os
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
+
+
+@pytest.fixture(scope="session")
+def golden():
+    with open(os.path.join(ROOT, "tests", "golden", "vectors.json")) as f:
+        return json.load(f)
+
+
+@pytest.fixture(scope="session")
+def gpu_ctx():
+    from zkp_subnet_b200 import native
+    ctx = native.Context(0)  # raises ZkpError without a GPU: there is no CPU fallback
+    yield ctx
+    ctx.close()

@@ -1,0 +1,141 @@
+"""GPU (-m gpu): the reference's own integration tests re-stated against the drop-in `fourier.Client`
+(reference tests/test_miner.py:84-121 and tests/test_validator.py:59-163), with the bittensor chain mocks
+removed (the prover is what is under test; the reference never mocks it either)."""
+import base64
+import threading
+
+import pytest
+
+from fourier import Client
+from oracle import bls12_381 as o
+from zkp_subnet_b200.miner import Miner
+from zkp_subnet_b200.protocol import Prove
+from zkp_subnet_b200.validator import Validator
+
+pytestmark = pytest.mark.gpu
+
+TEST_SCALE, TEST_MACHINES_SCALE = 6, 2  # reference tests/conftest.py:26-27
+TEST_MACHINE_COUNT = 2
+
+
+@pytest.fixture(scope="module")
+def client(tmp_path_factory):
+    path = str(tmp_path_factory.mktemp("srs") / "test_setup.compressed")
+    c = Client(port=1337, bin="./test_prover", uncompressed=False, setup_path=path, precompute_path=path + ".pre")
+    c.start(scale=TEST_SCALE, machines_scale=TEST_MACHINES_SCALE)
+    yield c
+    c.stop()
+
+
+@pytest.mark.parametrize("include_point", [True, False])
+def test_miner_forward(client, golden, include_point):
+    miner = Miner(client)
+    synapse = Prove(index=0, poly=golden["test_poly"], alpha=golden["test_point"], eval=golden["test_eval"])
+    with client.worker_commit(i=synapse.index, poly=synapse.poly) as resp:
+        assert resp.status_code == 200
+        commitment = resp.json().get("commitment")
+    with client.worker_open(i=synapse.index, poly=synapse.poly, x=synapse.alpha) as resp:
+        assert resp.status_code == 200
+        eval, proof = resp.json().get("eval"), resp.json().get("proof")
+    with client.worker_verify(i=synapse.index, proof=proof, alpha=synapse.alpha, eval=eval, commitment=commitment) as resp:
+        assert resp.status_code == 200
+        assert resp.json().get("valid")
+    # bytes pinned by the golden vectors (row 0 of the 4x16 Pianist SRS)
+    rec = golden["pianist_4x16"][0]
+    assert base64.b64decode(commitment).hex() == rec["commitment"] and base64.b64decode(proof).hex() == rec["proof"]
+    assert eval == rec["eval"] and len(commitment) == 64 and len(eval) == 43
+    if not include_point:
+        synapse.alpha = None
+    ret = miner.forward(synapse)
+    if include_point:
+        assert ret.commitment == commitment and ret.proof == proof and ret.eval == eval
+        assert ret.poly == [] and ret.alpha is None and ret.index == 0
+        # the non-fused path (two RPCs, as the reference's rpc_commit_and_open) gives the same bytes
+        assert Miner(client, fused=False).forward(synapse).proof == proof
+    else:
+        assert ret is synapse and ret.commitment is None  # exception swallowed, unfilled synapse returned
+
+
+def make_proofs(validator):
+    challenge = validator.generate_challenge(TEST_MACHINE_COUNT)
+    responses = []
+    for i in range(TEST_MACHINE_COUNT):
+        with validator.client.worker_commit(i, challenge.polys[i]) as resp:
+            commitment = resp.json().get("commitment")
+        with validator.client.worker_open(i, challenge.polys[i], challenge.alpha) as resp:
+            eval, proof = resp.json().get("eval"), resp.json().get("proof")
+        responses.append(Prove(index=i, poly=[], alpha=None, eval=eval, commitment=commitment, proof=proof))
+    for r in responses:
+        with validator.client.worker_verify(r.index, r.proof, challenge.alpha, challenge.evals[r.index], r.commitment) as resp:
+            assert resp.status_code == 200 and resp.json().get("valid")
+    return challenge, responses
+
+
+@pytest.mark.parametrize("missing_info,too_late,invalid_proof,half_time,expected_value", [
+    (False, False, False, False, [1.0, 1.0]),
+    (True, False, False, False, [0.0, 1.0]),
+    (False, True, False, False, [0.0, 1.0]),
+    (False, False, True, False, [0.0, 1.0]),
+    (False, False, False, True, [0.5, 1.0]),
+])
+def test_reward(client, missing_info, too_late, invalid_proof, half_time, expected_value):
+    def change_proof(proof):
+        raw = base64.b64decode(proof)
+        plus_one = int.from_bytes(raw, "big") + 1 % 2 ** (len(raw) * 8)
+        return base64.b64encode(plus_one.to_bytes(len(raw), "big")).decode()
+
+    validator = Validator(client)
+    challenge, responses = make_proofs(validator)
+    # the validator's eval (iNTT + Horner) equals the miner's barycentric eval
+    assert [r.eval for r in responses] == challenge.evals[:TEST_MACHINE_COUNT]
+    times = [0.0, 0.0]
+    timeout = 10.0
+    if missing_info:
+        responses[0].commitment = None
+    if too_late:
+        times[0] = 11.0
+    if invalid_proof:
+        responses[0].proof = change_proof(responses[0].proof)
+    if half_time:
+        times[0] = 5.0
+    assert validator.get_rewards(challenge, responses, times, timeout) == expected_value
+
+
+def test_challenge_shape_and_wire_format(client):
+    with client.random_poly() as r:
+        poly = r.json()["poly"]
+    assert len(poly) == 4 and all(len(row) == 16 for row in poly)
+    assert all(len(s) == 43 and o.fr_from_b64(s) < o.R for row in poly for s in row)
+    with client.random_point() as r:
+        assert o.fr_from_b64(r.json()["point"]) < o.R
+    with client.fft(poly[0], left=True, inverse=True) as r:
+        coeffs = r.json()["poly"]
+    with client.fft(coeffs, left=True, inverse=False) as r:
+        assert r.json()["poly"] == poly[0]
+    # error convention: non-200 rather than an exception, except verify which is 200/false
+    with client.worker_commit(0, ["not base64!"] * 16) as r:
+        assert r.status_code != 200
+    with client.worker_commit(9, poly[0]) as r:
+        assert r.status_code != 200
+    with client.worker_verify(0, "AAAA", "AAAA", "AAAA", "AAAA") as r:
+        assert r.status_code == 200 and r.json()["valid"] is False
+
+
+def test_concurrent_forwards(client, golden):
+    # the axon calls forward from several threads: results must not interfere
+    miner = Miner(client)
+    rec = golden["pianist_4x16"]
+    out = {}
+
+    def work(i):
+        s = Prove(index=i, poly=golden["test_poly"], alpha=golden["test_point"])
+        out[i] = miner.forward(s)
+
+    threads = [threading.Thread(target=work, args=(i % 4,)) for i in range(8)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    for i in range(4):
+        assert base64.b64decode(out[i].commitment).hex() == rec[i]["commitment"]
+        assert base64.b64decode(out[i].proof).hex() == rec[i]["proof"]

@@ -1,0 +1,246 @@
+"""GPU (-m gpu): parity of the CUDA path, called through the C ABI, against the oracle on the same
+seeded inputs -- bit-exact (integer work).  Small sizes are compared with the oracle's own MSM / NTT /
+quotient; sizes the oracle's MSM cannot finish in seconds use size-independent properties: the trapdoor
+identity commit == [sum_j f_j L_j(tau)]_1 (one oracle scalar product + one scalar multiplication),
+proof == [sum_j q_j L_j(tau)]_1, and the pairing check of every proof."""
+import pytest
+
+from oracle import bls12_381 as o
+from oracle import ref
+from zkp_subnet_b200 import native
+
+pytestmark = pytest.mark.gpu
+
+R = o.R
+TAU_X = o.TEST_SECRET
+TAU_Y = 0x1234567890ABCDEF1234567890ABCDEF
+
+
+def adversarial(n):
+    return {
+        "random": ref.random_scalars(0xB200 + n, n),
+        "zeros": bytes(32 * n),
+        "ones": ref.join32([1] * n),
+        "r_minus_1": ref.join32([R - 1] * n),
+        "single": ref.join32([0] * (n - 1) + [12345]),
+        "small": ref.join32([i % 7 for i in range(n)]),
+        "top_bits": ref.join32([(1 << 254) + i for i in range(n)]),
+        "half_window": ref.join32([(1 << 15) | (1 << 31) | (1 << 47) for _ in range(n)]),
+    }
+
+
+@pytest.mark.parametrize("log_n", [0, 1, 4, 8, 12])
+def test_msm_vs_oracle(gpu_ctx, log_n):
+    n = 1 << log_n
+    srs = ref.srs(n, TAU_X, "lagrange")
+    gpu_ctx.srs_set_shape(log_n, 0)
+    gpu_ctx.srs_import_row(0, srs)
+    assert gpu_ctx.srs_export_row(0, n) == srs
+    for name, sc in adversarial(n).items():
+        assert gpu_ctx.msm_g1(0, sc) == ref.msm(srs, sc, 8), name
+    if n > 4:  # ragged: fewer scalars than points
+        sc = ref.random_scalars(99, n - 3)
+        assert gpu_ctx.msm_g1(0, sc) == ref.msm(srs, sc, 8)
+
+
+def test_msm_special_points(gpu_ctx):
+    # SRS rows with repeated points, P and -P, and infinity: exercises the doubling / cancellation
+    # branches of the bucket adds (SURVEY.md section 7 "adversarial")
+    n = 64
+    g = o.G1_GEN
+    pts = [g] * 16 + [o.g1_neg(g)] * 16 + [None] * 8 + [o.g1_mul(g, k + 2) for k in range(24)]
+    raw = b"".join((b"\x40" + bytes(95)) if p is None else p[0].to_bytes(48, "big") + p[1].to_bytes(48, "big") for p in pts)
+    gpu_ctx.srs_set_shape(6, 0)
+    gpu_ctx.srs_import_row(0, raw)
+    for sc in (ref.join32([5] * n), ref.join32([1] * n), ref.random_scalars(3, n), ref.join32([R - 1] * 32 + [7] * 32)):
+        assert gpu_ctx.msm_g1(0, sc) == ref.msm(raw, sc, 1)
+
+
+def test_window_override_is_result_invariant(gpu_ctx):
+    n = 1 << 10
+    gpu_ctx.srs_generate(TAU_X, TAU_Y, 10, 0)
+    sc = ref.random_scalars(11, n)
+    base = gpu_ctx.msm_g1(0, sc)
+    try:
+        for c in (4, 7, 11, 13, 16):
+            gpu_ctx.set_msm_window(c)
+            assert gpu_ctx.msm_g1(0, sc) == base, c
+    finally:
+        gpu_ctx.set_msm_window(0)
+
+
+def test_srs_generate_matches_oracle(gpu_ctx):
+    gpu_ctx.srs_generate(TAU_X, TAU_Y, 4, 2)
+    Rs = ref.split32(ref.lagrange_scalars(4, TAU_Y))
+    for i in range(4):
+        assert gpu_ctx.srs_export_row(i, 16) == ref.srs(16, TAU_X, "lagrange", scale=Rs[i])
+    # point-range shards tile the full row
+    gpu_ctx.srs_generate(TAU_X, TAU_Y, 6, 0)
+    full = gpu_ctx.srs_export_row(0, 64)
+    for s in range(4):
+        gpu_ctx.srs_generate_shard(TAU_X, TAU_Y, 6, 0, s, 2)
+        assert gpu_ctx.srs_export_row(0, 16) == full[s * 16 * 96:(s + 1) * 16 * 96]
+
+
+def test_golden_vectors(gpu_ctx, golden):
+    poly = b"".join(o.b64_decode(s) for s in golden["test_poly"])
+    x = o.b64_decode(golden["test_point"])
+    gpu_ctx.srs_generate(TAU_X, TAU_Y, 4, 0)
+    B = golden["B_eval_form"]
+    assert gpu_ctx.worker_commit(0, poly).hex() == B["commitment"]
+    y, proof = gpu_ctx.worker_open(0, poly, x)
+    assert o.fr_to_b64(int.from_bytes(y, "big")) == B["eval"] and proof.hex() == B["proof"]
+    assert gpu_ctx.worker_commit_open(0, poly, x) == (bytes.fromhex(B["commitment"]), y, proof)
+    assert gpu_ctx.worker_verify(0, proof, x, y, bytes.fromhex(B["commitment"]))
+    D = golden["B_in_domain"]
+    y, proof = gpu_ctx.worker_open(0, poly, o.b64_decode(D["x"]))
+    assert o.fr_to_b64(int.from_bytes(y, "big")) == D["eval"] and proof.hex() == D["proof"]
+    # coefficient-form Horner: the reference's own known answer
+    assert o.fr_to_b64(int.from_bytes(gpu_ctx.eval(poly, x), "big")) == golden["test_eval"]
+    assert [o.fr_to_b64(v) for v in ref.split32(gpu_ctx.fft(poly, True, False))] == golden["ntt16"]
+    assert [o.fr_to_b64(v) for v in ref.split32(gpu_ctx.fft(poly, True, True))] == golden["intt16"]
+    # Pianist rows (scale 6 / machines_scale 2: the reference's unit-test shape)
+    gpu_ctx.srs_generate(TAU_X, TAU_Y, 4, 2)
+    for rec in golden["pianist_4x16"]:
+        i = rec["row"]
+        com, y, proof = gpu_ctx.worker_commit_open(i, poly, x)
+        assert (com.hex(), proof.hex(), o.fr_to_b64(int.from_bytes(y, "big"))) == (rec["commitment"], rec["proof"], rec["eval"])
+        assert gpu_ctx.worker_verify(i, proof, x, y, com)
+        assert not gpu_ctx.worker_verify((i + 1) % 4, proof, x, y, com)
+        tampered = (int.from_bytes(proof, "big") + 1).to_bytes(48, "big")  # reference tests/test_validator.py:79-86
+        assert not gpu_ctx.worker_verify(i, tampered, x, y, com)
+
+
+@pytest.mark.parametrize("log_n", [0, 1, 3, 9, 12, 13, 15, 17])
+def test_ntt_vs_oracle(gpu_ctx, log_n):
+    n = 1 << log_n
+    v = ref.random_scalars(1000 + log_n, n)
+    f = gpu_ctx.fft(v, True, False)
+    assert f == ref.ntt(v, False)
+    assert gpu_ctx.fft(v, False, True) == ref.ntt(v, True)
+    assert gpu_ctx.fft(f, True, True) == v  # round trip
+
+
+def test_ntt_large_properties(gpu_ctx):
+    # 2^20: linearity + round trip + agreement with Horner at a domain point (size-independent checks)
+    n = 1 << 20
+    a, b = ref.random_scalars(1, n), ref.random_scalars(2, n)
+    fa, fb = gpu_ctx.fft(a), gpu_ctx.fft(b)
+    assert gpu_ctx.fft(fa, True, True) == a
+    s = ref.join32([(x + y) % R for x, y in zip(ref.split32(a[:32 * 64]), ref.split32(b[:32 * 64]))])
+    ab = ref.join32([(x + y) % R for x, y in zip(ref.split32(a), ref.split32(b))])
+    fab = gpu_ctx.fft(ab)
+    assert ref.split32(fab[:32 * 64]) == [(x + y) % R for x, y in zip(ref.split32(fa[:32 * 64]), ref.split32(fb[:32 * 64]))]
+    assert len(s) == 32 * 64
+    w = o.root_of_unity(n)
+    for k in (0, 1, 12345, n - 1):
+        assert gpu_ctx.eval(a, pow(w, k, R).to_bytes(32, "big")) == fa[32 * k:32 * k + 32]
+
+
+@pytest.mark.parametrize("log_n", [5, 10, 13])
+def test_eval_vs_oracle(gpu_ctx, log_n):
+    n = (1 << log_n) - 3  # ragged length
+    c = ref.random_scalars(log_n, n)
+    for seed in (1, 2):
+        x = ref.random_scalars(500 + seed, 1)
+        assert gpu_ctx.eval(c, x) == ref.eval_coeffs(c, x)
+    assert gpu_ctx.eval(c, bytes(32)) == c[:32]
+
+
+@pytest.mark.parametrize("log_n", [10, 12])
+def test_commit_open_vs_oracle(gpu_ctx, log_n):
+    n = 1 << log_n
+    gpu_ctx.srs_generate(TAU_X, TAU_Y, log_n, 0)
+    srs = gpu_ctx.srs_export_row(0, n)
+    assert srs == ref.srs(n, TAU_X, "lagrange")
+    sc = ref.random_scalars(0xB200 + log_n, n)
+    x = ref.random_scalars(77, 1)
+    com, y, proof = gpu_ctx.worker_commit_open(0, sc, x)
+    assert com == ref.msm(srs, sc, 8)
+    ey, eproof = ref.open_evals(sc, x, srs, 8)
+    assert (y, proof) == (ey, eproof)
+    assert gpu_ctx.worker_open(0, sc, x) == (y, proof) and gpu_ctx.worker_commit(0, sc) == com
+    assert gpu_ctx.worker_verify(0, proof, x, y, com)
+    # constant polynomial: quotient is zero, proof is the point at infinity
+    const = ref.join32([42] * n)
+    y, proof = gpu_ctx.worker_open(0, const, x)
+    assert int.from_bytes(y, "big") == 42 and proof.hex() == "c0" + "00" * 47
+    assert gpu_ctx.worker_verify(0, proof, x, y, gpu_ctx.worker_commit(0, const))
+
+
+@pytest.mark.parametrize("log_n", [16, 20])
+def test_full_size_trapdoor_identity(gpu_ctx, log_n):
+    # BASELINE configs 2 and 3: sizes beyond the oracle's MSM, checked through the trapdoor
+    n = 1 << log_n
+    gpu_ctx.srs_generate(TAU_X, TAU_Y, log_n, 0)
+    sc = ref.random_scalars(0xB200 + log_n, n)
+    x = ref.random_scalars(77 + log_n, 1)
+    com, y, proof = gpu_ctx.worker_commit_open(0, sc, x)
+    ls = ref.lagrange_scalars(n, TAU_X)
+    assert com == ref.g1_mul_gen(ref.fr_dot(sc, ls))
+    ey, q = ref.quotient_evals(sc, x)
+    assert y == ey
+    assert proof == ref.g1_mul_gen(ref.fr_dot(q, ls))
+    assert gpu_ctx.worker_verify(0, proof, x, y, com)
+    assert not gpu_ctx.worker_verify(0, com, x, y, proof)
+    # evaluation-form commitment == coefficient-form commitment: iNTT on the GPU, monomial trapdoor on the CPU
+    coeffs = gpu_ctx.fft(sc, True, True)
+    f_tau = ref.eval_coeffs(coeffs, TAU_X.to_bytes(32, "big"))
+    assert com == ref.g1_mul_gen(f_tau)
+
+
+def test_sharded_commit_combines_to_full(gpu_ctx):
+    # point-range sharding: partial commitments of the 4 shards sum to the commitment
+    log_n, log_s = 12, 2
+    n, S = 1 << log_n, 1 << log_s
+    sc = ref.random_scalars(31337, n)
+    gpu_ctx.srs_generate(TAU_X, TAU_Y, log_n, 0)
+    full = gpu_ctx.worker_commit(0, sc)
+    parts = b""
+    for s in range(S):
+        gpu_ctx.srs_generate_shard(TAU_X, TAU_Y, log_n, 0, s, log_s)
+        parts += gpu_ctx.worker_commit(0, sc[s * (n // S) * 32:(s + 1) * (n // S) * 32])
+        with pytest.raises(native.ZkpError):
+            gpu_ctx.worker_open(0, sc[:(n // S) * 32], bytes(31) + b"\x05")
+    assert native.g1_sum(parts) == full
+
+
+def test_errors_and_edge_inputs(gpu_ctx):
+    gpu_ctx.srs_generate(TAU_X, TAU_Y, 4, 0)
+    with pytest.raises(native.ZkpError) as e:
+        gpu_ctx.worker_commit(0, R.to_bytes(32, "big") * 16)  # non-canonical scalar
+    assert e.value.code == native.ZKP_ERR_ENCODING
+    with pytest.raises(native.ZkpError):
+        gpu_ctx.worker_commit(1, bytes(32 * 16))  # row out of range
+    with pytest.raises(native.ZkpError):
+        gpu_ctx.worker_commit(0, bytes(32 * 17))  # longer than the row
+    with pytest.raises(native.ZkpError):
+        gpu_ctx.worker_open(0, bytes(32 * 8), bytes(32))  # opening needs a full row
+    with pytest.raises(native.ZkpError):
+        gpu_ctx.fft(bytes(32 * 3))  # not a power of two
+    assert not gpu_ctx.worker_verify(0, b"\xff" * 48, bytes(32), bytes(32), b"\xc0" + bytes(47))
+    assert not gpu_ctx.worker_verify(0, b"\xc0" + bytes(47), b"\xff" * 32, bytes(32), b"\xc0" + bytes(47))
+    rp = gpu_ctx.random_poly(7, 4096)
+    vals = ref.split32(rp)
+    assert all(v < R for v in vals) and len(set(vals)) == 4096
+    assert gpu_ctx.random_poly(7, 16) == rp[:512] and gpu_ctx.random_poly(8, 16) != rp[:512]
+
+
+def test_srs_file_roundtrip(gpu_ctx, tmp_path, golden):
+    gpu_ctx.srs_generate(TAU_X, TAU_Y, 4, 2)
+    path = str(tmp_path / "srs.bin")
+    gpu_ctx.srs_save(path)
+    rows = [gpu_ctx.srs_export_row(i, 16) for i in range(4)]
+    other = native.Context(0)  # a second context on the same GPU (miner + validator on one host)
+    try:
+        other.srs_load(path)
+        assert other.srs_shape() == (4, 2)
+        assert [other.srs_export_row(i, 16) for i in range(4)] == rows
+        poly = b"".join(o.b64_decode(s) for s in golden["test_poly"])
+        x = o.b64_decode(golden["test_point"])
+        rec = golden["pianist_4x16"][3]
+        com, y, proof = other.worker_commit_open(3, poly, x)
+        assert com.hex() == rec["commitment"] and proof.hex() == rec["proof"]
+        assert other.worker_verify(3, proof, x, y, com) and gpu_ctx.worker_verify(3, proof, x, y, com)
+    finally:
+        other.close()

@@ -1,0 +1,73 @@
+"""CPU: host-side parts of the product library that need no device -- the base64 wire codec, the G1 sum
+used to combine per-GPU partial points, and the pairing behind worker_verify -- against the oracle."""
+import base64
+
+import pytest
+
+from oracle import bls12_381 as o
+from zkp_subnet_b200 import native
+from zkp_subnet_b200.client import Response, decode_poly, encode_poly
+
+
+def test_b64_codec(golden):
+    strs = golden["test_poly"]
+    raw = native.b64_decode_fr("".join(strs).encode(), 43, len(strs))
+    assert raw == b"".join(o.b64_decode(s) for s in strs)
+    assert native.b64_encode_fr(raw).decode() == "".join(strs)
+    assert decode_poly(strs) == raw and encode_poly(raw) == strs
+    padded = [s + "=" for s in strs]
+    assert decode_poly(padded) == raw
+    assert decode_poly([]) == b""
+    with pytest.raises(native.ZkpError):
+        native.b64_decode_fr(b"!" * 43, 43, 1)
+    with pytest.raises(native.ZkpError):  # non-zero trailing bits
+        native.b64_decode_fr(("A" * 42 + "B").encode(), 43, 1)
+    for v in (0, 1, o.R - 1, 2**256 - 1):
+        b = v.to_bytes(32, "big")
+        assert native.b64_encode_fr(b).decode() == base64.b64encode(b).decode().rstrip("=")
+
+
+def test_g1_sum(golden):
+    pts = [bytes.fromhex(r["commitment"]) for r in golden["pianist_4x16"]]
+    assert native.g1_sum(b"".join(pts)).hex() == golden["B_eval_form"]["commitment"]
+    assert native.g1_sum(b"").hex() == "c0" + "00" * 47
+    g, ng = bytes.fromhex(golden["g1_encodings"]["G"]), bytes.fromhex(golden["g1_encodings"]["negG"])
+    assert native.g1_sum(g + ng).hex() == golden["g1_encodings"]["inf"]
+    assert native.g1_sum(g + g).hex() == golden["g1_encodings"]["2G"]
+    with pytest.raises(native.ZkpError):
+        native.g1_sum(b"\xff" * 48)
+
+
+def _g2(pt):
+    return b"".join(c.to_bytes(48, "big") for c in (pt[0][0], pt[0][1], pt[1][0], pt[1][1]))
+
+
+def test_pairing_check_bilinear():
+    a, b = 0x1234567, 0x89ABCDEF01
+    P1 = o.g1_compress(o.g1_mul(o.G1_GEN, a))
+    Q1 = _g2(o.g2_mul(o.G2_GEN, b))
+    P2 = o.g1_compress(o.g1_neg(o.g1_mul(o.G1_GEN, a * b % o.R)))
+    assert native.pairing_check(P1 + P2, Q1 + _g2(o.G2_GEN))
+    P3 = o.g1_compress(o.g1_neg(o.g1_mul(o.G1_GEN, (a * b + 1) % o.R)))
+    assert not native.pairing_check(P1 + P3, Q1 + _g2(o.G2_GEN))
+    # infinity contributes 1
+    assert native.pairing_check(o.g1_compress(None), Q1)
+
+
+def test_pairing_check_kzg_equation(golden):
+    # e(C - [y]_1, g2) * e(-pi, [tau - x]_2) == 1 on the golden evaluation-form vector
+    B = golden["B_eval_form"]
+    x = o.fr_from_b64(golden["test_point"])
+    y = o.fr_from_b64(B["eval"])
+    com = o.g1_decompress(bytes.fromhex(B["commitment"]))
+    proof = o.g1_decompress(bytes.fromhex(B["proof"]))
+    lhs = o.g1_add(com, o.g1_neg(o.g1_mul(o.G1_GEN, y)))
+    q2 = o.g2_add(o.g2_mul(o.G2_GEN, o.TEST_SECRET), o.g2_neg(o.g2_mul(o.G2_GEN, x)))
+    assert native.pairing_check(o.g1_compress(lhs) + o.g1_compress(o.g1_neg(proof)), _g2(o.G2_GEN) + _g2(q2))
+    lhs_bad = o.g1_add(com, o.g1_neg(o.g1_mul(o.G1_GEN, y + 1)))
+    assert not native.pairing_check(o.g1_compress(lhs_bad) + o.g1_compress(o.g1_neg(proof)), _g2(o.G2_GEN) + _g2(q2))
+
+
+def test_response_contract():
+    with Response(200, {"commitment": "x"}) as r:
+        assert r.status_code == 200 and r.json().get("commitment") == "x"

@@ -1,0 +1,205 @@
+"""Drop-in replacement for `fourier.Client` -- the only object through which the reference's miner and
+validator reach their prover (reference base/miner.py:26,73-84; base/validator.py:28,80-91).
+
+Same constructor keywords, same ten methods, same return convention: every call returns an object
+usable as `with client.method(...) as response:` exposing `response.status_code` (200 = OK) and
+`response.json()` (reference neurons/miner.py:38-54, neurons/validator.py:58-104).  Instead of
+HTTP -> Rust process, the methods call libzkp_b200.so (CUDA, sm_100a) through ctypes.  There is no
+CPU fallback: `start()` raises if the library or a GPU is missing.
+
+Wire format (reference base/protocol.py:35-60, tests/test_miner.py:33-55): field elements are
+unpadded standard base64 of 32 big-endian bytes; G1 points are base64 of the 48-byte ZCash
+compressed encoding.
+"""
+from __future__ import annotations
+
+import base64
+import os
+import secrets
+from typing import Any, Dict, List, Optional, Sequence
+
+from . import native
+
+# Public test trapdoors used when no SRS file exists (the reference's tests also generate a
+# throw-away SRS: tests/conftest.py:50-65).  A production deployment loads the ceremony SRS file.
+TEST_TAU_X = 1927409816240961209460912649124
+TEST_TAU_Y = 0x1234567890ABCDEF1234567890ABCDEF
+
+
+class Response:
+    """Mimics the slice of `requests.Response` the reference touches."""
+
+    def __init__(self, status_code: int, payload: Dict[str, Any]):
+        self.status_code = status_code
+        self._payload = payload
+
+    def json(self) -> Dict[str, Any]:
+        return self._payload
+
+    def __enter__(self) -> "Response":
+        return self
+
+    def __exit__(self, *exc) -> bool:
+        return False
+
+
+def _b64_point(raw: bytes) -> str:
+    return base64.b64encode(raw).decode()
+
+
+def _b64_fr(raw: bytes) -> str:
+    return base64.b64encode(raw).decode().rstrip("=")
+
+
+def _decode_any(s: str, size: int) -> bytes:
+    raw = base64.b64decode(s + "=" * (-len(s) % 4), validate=True)
+    if len(raw) != size:
+        raise ValueError(f"expected {size} bytes, got {len(raw)}")
+    return raw
+
+
+def decode_poly(poly: Sequence[str]) -> bytes:
+    """List[str] -> n x 32 bytes through the library's batch codec (one C call, no Python loop)."""
+    n = len(poly)
+    if n == 0:
+        return b""
+    if all(len(s) == 43 for s in poly):
+        return native.b64_decode_fr("".join(poly).encode("ascii"), 43, n)
+    if all(len(s) == 44 for s in poly):
+        return native.b64_decode_fr("".join(poly).encode("ascii"), 44, n)
+    return b"".join(_decode_any(s, 32) for s in poly)
+
+
+def encode_poly(raw: bytes) -> List[str]:
+    s = native.b64_encode_fr(raw).decode("ascii")
+    return [s[i:i + 43] for i in range(0, len(s), 43)]
+
+
+class Client:
+    """`Client(port=..., bin=..., uncompressed=..., setup_path=..., precompute_path=...)`.
+
+    `port` and `bin` are accepted for signature compatibility and ignored (there is no prover process).
+    `setup_path` names the SRS file: if it exists it is loaded, otherwise an SRS is generated on the GPU
+    from the public test trapdoor and saved there.  `precompute_path` / `uncompressed` are accepted and
+    ignored: the Lagrange ("precompute") rows live in the same file.
+    """
+
+    def __init__(self, port: int = 1337, bin: Optional[str] = None, uncompressed: bool = False,
+                 setup_path: Optional[str] = None, precompute_path: Optional[str] = None, device: int = 0,
+                 seed: Optional[int] = None):
+        self.port = port
+        self.bin = bin
+        self.uncompressed = uncompressed
+        self.setup_path = setup_path
+        self.precompute_path = precompute_path
+        self.device = device
+        self.scale = None
+        self.machines_scale = None
+        self._ctx: Optional[native.Context] = None
+        self._seed = seed if seed is not None else secrets.randbits(63)
+        self._counter = 0
+
+    # ---- lifecycle (reference base/miner.py:82-84,155,181)
+    def start(self, scale: int = 18, machines_scale: int = 8) -> None:
+        if machines_scale > scale:
+            raise ValueError("machines_scale must not exceed scale")
+        self.scale, self.machines_scale = int(scale), int(machines_scale)
+        log_n = self.scale - self.machines_scale
+        self._ctx = native.Context(self.device)
+        path = self.setup_path
+        if path and os.path.exists(path):
+            self._ctx.srs_load(path)
+            if self._ctx.srs_shape() != (log_n, self.machines_scale):
+                raise native.ZkpError(native.ZKP_ERR_STATE, f"SRS file {path} has shape {self._ctx.srs_shape()}, "
+                                      f"expected {(log_n, self.machines_scale)}")
+        else:
+            self._ctx.srs_generate(TEST_TAU_X, TEST_TAU_Y, log_n, self.machines_scale)
+            if path:
+                self._ctx.srs_save(path)
+
+    def stop(self) -> None:
+        if self._ctx is not None:
+            self._ctx.close()
+            self._ctx = None
+
+    def _need(self) -> native.Context:
+        if self._ctx is None:
+            raise native.ZkpError(native.ZKP_ERR_STATE, "Client.start() has not been called")
+        return self._ctx
+
+    @staticmethod
+    def _fail(e: Exception) -> Response:
+        code = 400 if isinstance(e, (ValueError, native.ZkpError)) and getattr(e, "code", native.ZKP_ERR_ARG) in (
+            native.ZKP_ERR_ARG, native.ZKP_ERR_ENCODING) else 500
+        return Response(code, {"error": str(e)})
+
+    def _next_seed(self) -> int:
+        self._counter += 1
+        return (self._seed + 0x9E3779B97F4A7C15 * self._counter) & 0xFFFFFFFFFFFFFFFF
+
+    # ---- prover calls
+    def worker_commit(self, i: int, poly: Sequence[str]) -> Response:
+        try:
+            com = self._need().worker_commit(int(i), decode_poly(poly))
+            return Response(200, {"commitment": _b64_point(com)})
+        except (ValueError, native.ZkpError) as e:
+            return self._fail(e)
+
+    def worker_open(self, i: int, poly: Sequence[str], x: str) -> Response:
+        try:
+            y, proof = self._need().worker_open(int(i), decode_poly(poly), _decode_any(x, 32))
+            return Response(200, {"eval": _b64_fr(y), "proof": _b64_point(proof)})
+        except (ValueError, TypeError, native.ZkpError) as e:
+            return self._fail(e)
+
+    def worker_commit_and_open(self, i: int, poly: Sequence[str], x: str) -> Response:
+        """Fused form of the reference's rpc_commit_and_open (neurons/miner.py:56-61): one decode, one upload."""
+        try:
+            com, y, proof = self._need().worker_commit_open(int(i), decode_poly(poly), _decode_any(x, 32))
+            return Response(200, {"commitment": _b64_point(com), "eval": _b64_fr(y), "proof": _b64_point(proof)})
+        except (ValueError, TypeError, native.ZkpError) as e:
+            return self._fail(e)
+
+    def worker_verify(self, i: int, proof: str, alpha: str, eval: str, commitment: str) -> Response:
+        # malformed encodings are a failed verification with status 200, never an HTTP-style error
+        # (reference tests/test_validator.py:66,79-86,103-104 expect reward 0.0, not an exception)
+        try:
+            args = (_decode_any(proof, 48), _decode_any(alpha, 32), _decode_any(eval, 32), _decode_any(commitment, 48))
+        except (ValueError, TypeError):
+            return Response(200, {"valid": False})
+        try:
+            return Response(200, {"valid": self._need().worker_verify(int(i), *args)})
+        except native.ZkpError as e:
+            return self._fail(e)
+
+    def fft(self, poly: Sequence[str], left: bool = True, inverse: bool = False) -> Response:
+        try:
+            out = self._need().fft(decode_poly(poly), bool(left), bool(inverse))
+            return Response(200, {"poly": encode_poly(out)})
+        except (ValueError, native.ZkpError) as e:
+            return self._fail(e)
+
+    def eval(self, poly: Sequence[str], x: str) -> Response:
+        try:
+            y = self._need().eval(decode_poly(poly), _decode_any(x, 32))
+            return Response(200, {"y": _b64_fr(y)})
+        except (ValueError, TypeError, native.ZkpError) as e:
+            return self._fail(e)
+
+    def random_poly(self) -> Response:
+        """Random bivariate polynomial as 2^machines_scale rows of 2^(scale-machines_scale) evaluations
+        (reference neurons/validator.py:67-75)."""
+        try:
+            ctx = self._need()
+            rows, n = 1 << self.machines_scale, 1 << (self.scale - self.machines_scale)
+            raw = ctx.random_poly(self._next_seed(), rows * n)
+            flat = encode_poly(raw)
+            return Response(200, {"poly": [flat[r * n:(r + 1) * n] for r in range(rows)]})
+        except native.ZkpError as e:
+            return self._fail(e)
+
+    def random_point(self) -> Response:
+        try:
+            return Response(200, {"point": _b64_fr(self._need().random_point(self._next_seed()))})
+        except native.ZkpError as e:
+            return self._fail(e)

@@ -77,7 +77,7 @@ int open_device(zkp_ctx* ctx, const Fr* d_f, uint32_t n, const Fr64& x) {
     ZKP_CUDA(ctx->partials.ensure((size_t)(blocks > blocks2 ? blocks : blocks2) * 32));
     ZKP_CUDA(cudaMemsetAsync(small_at<uint32_t>(ctx, SM_HIT), 0xff, 4, st));
     k_open_pass1<<<blocks, 128, 0, st>>>(d_f, n, E, to_dev(x), dom->wt.as<Fr>(), to_dev(dom->w_inv), ctx->fr_b.as<Fr>(),
-                                         ctx->partials.as<Fr>(), small_at<uint32_t>(ctx, SM_HIT));
+                                         ctx->partials.as<Fr>(), small_at<uint32_t>(ctx, SM_HIT), 0);
     k_fr_reduce<<<1, 256, 0, st>>>(ctx->partials.as<Fr>(), blocks, small_at<Fr>(ctx, SM_S1));
     k_open_y<<<1, 32, 0, st>>>(d_f, log_n, to_dev(x), to_dev(dom->n_inv), small_at<Fr>(ctx, SM_S1), small_at<uint32_t>(ctx, SM_HIT),
                                small_at<Fr>(ctx, SM_Y));
@@ -122,6 +122,8 @@ int open_checks(zkp_ctx* ctx, uint32_t i, const void* poly, size_t n, const uint
     if (rc) return rc;
     if (!poly || !x_be) return fail(ZKP_ERR_ARG, "null argument");
     if (n != ((size_t)1 << ctx->log_n)) return fail(ZKP_ERR_ARG, "opening needs exactly one SRS row of evaluations");
+    if (ctx->shard_domain_log != ctx->log_n)
+        return fail(ZKP_ERR_STATE, "opening is not available on a point-range shard (commit partials only)");
     if (!Fr64::from_be(*x, x_be)) return fail(ZKP_ERR_ENCODING, "evaluation point is not canonical");
     return ZKP_OK;
 }
@@ -228,10 +230,20 @@ extern "C" {
 // ---------------------------------------------------------------------------------------------- SRS
 int zkp_srs_generate(zkp_ctx* ctx, const uint8_t tau_x_be[32], const uint8_t tau_y_be[32], uint32_t log_n,
                      uint32_t log_machines) {
+    return zkp_srs_generate_shard(ctx, tau_x_be, tau_y_be, log_n, log_machines, 0, 0);
+}
+
+// Point-range shard `shard` of 2^log_shards: every row holds the points j in
+// [shard * n/S, (shard+1) * n/S) of the size-n Lagrange SRS (n = 2^log_n), so an MSM over the row with
+// the matching slice of scalars is this GPU's partial commitment.
+int zkp_srs_generate_shard(zkp_ctx* ctx, const uint8_t tau_x_be[32], const uint8_t tau_y_be[32], uint32_t log_n,
+                           uint32_t log_machines, uint32_t shard, uint32_t log_shards) {
     if (!ctx || !tau_x_be || !tau_y_be) return fail(ZKP_ERR_ARG, "null argument");
+    if (log_shards > log_n || shard >= (1u << log_shards)) return fail(ZKP_ERR_ARG, "bad shard");
     Fr64 tx, ty;
     if (!Fr64::from_be(tx, tau_x_be) || !Fr64::from_be(ty, tau_y_be)) return fail(ZKP_ERR_ENCODING, "trapdoor not canonical");
-    int rc = zkp_srs_set_shape(ctx, log_n, log_machines);
+    const uint32_t log_local = log_n - log_shards;
+    int rc = zkp_srs_set_shape(ctx, log_local, log_machines);
     if (rc) return rc;
     std::lock_guard<std::mutex> lk(ctx->mu);
     DeviceGuard g(ctx->device);
@@ -239,25 +251,26 @@ int zkp_srs_generate(zkp_ctx* ctx, const uint8_t tau_x_be[32], const uint8_t tau
     if (rc) return rc;
     rc = ensure_fixed_base(ctx);
     if (rc) return rc;
-    const uint32_t n = 1u << log_n, M = 1u << log_machines;
+    const uint32_t n = 1u << log_local, M = 1u << log_machines;
+    const uint64_t j0 = (uint64_t)shard << log_local;
     cudaStream_t st = ctx->stream;
     zkp_ctx::Domain* dom;
     rc = get_domain(ctx, log_n, false, &dom);
     if (rc) return rc;
-    // inv_d[j] = 1/(w^j - tau_x) in fr_b
+    // inv_d[j] = 1/(w^(j0+j) - tau_x) in fr_b
     ZKP_CUDA(ctx->fr_b.ensure((size_t)n * 32));
     ZKP_CUDA(ctx->fr_c.ensure((size_t)n * 32));
     uint32_t E = 16, threads = (n + E - 1) / E, blocks = (threads + 127) / 128;
     ZKP_CUDA(ctx->partials.ensure((size_t)blocks * 32));
     ZKP_CUDA(cudaMemsetAsync(small_at<uint32_t>(ctx, SM_HIT), 0xff, 4, st));
     k_open_pass1<<<blocks, 128, 0, st>>>(nullptr, n, E, to_dev(tx), dom->wt.as<Fr>(), to_dev(dom->w_inv), ctx->fr_b.as<Fr>(),
-                                         ctx->partials.as<Fr>(), small_at<uint32_t>(ctx, SM_HIT));
+                                         ctx->partials.as<Fr>(), small_at<uint32_t>(ctx, SM_HIT), j0);
     ctx->launches++;
     uint32_t hit = 0;
     ZKP_CUDA(cudaMemcpyAsync(&hit, small_at<uint32_t>(ctx, SM_HIT), 4, cudaMemcpyDeviceToHost, st));
     ZKP_CUDA(cudaStreamSynchronize(st));
     if (hit != HIT_NONE) return fail(ZKP_ERR_ARG, "tau_x lies in the evaluation domain");
-    // zn = (tau_x^n - 1)/n
+    // zn = (tau_x^n - 1)/n over the FULL domain
     Fr64 zn = tx;
     for (uint32_t k = 0; k < log_n; k++) zn = zn.sqr();
     zn = (zn - Fr64::one()) * dom->n_inv;
@@ -284,12 +297,12 @@ int zkp_srs_generate(zkp_ctx* ctx, const uint8_t tau_x_be[32], const uint8_t tau
     for (uint32_t i = 0; i < M; i++) {
         Fr64 coef = (zn * R[i]).neg();
         k_lagrange_scalars<<<((n + 7) / 8 + 127) / 128, 128, 0, st>>>(ctx->fr_b.as<Fr>(), n, dom->wt.as<Fr>(), to_dev(coef),
-                                                                      ctx->fr_c.as<Fr>());
+                                                                      ctx->fr_c.as<Fr>(), j0);
         k_fixed_base_mul<<<(n + 127) / 128, 128, 0, st>>>(ctx->fr_c.as<Fr>(), n, ctx->fixed_base.as<G1Affine>(),
                                                           ctx->ws.buckets.as<G1Xyzz>());
         uint32_t EA = 16, ta = (n + EA - 1) / EA;
         k_xyzz_to_affine<<<(ta + 127) / 128, 128, 0, st>>>(ctx->ws.buckets.as<G1Xyzz>(), n, EA, ctx->ws.pool.as<Fq>(),
-                                                           ctx->srs.as<G1Affine>() + ((size_t)i << log_n));
+                                                           ctx->srs.as<G1Affine>() + ((size_t)i << log_local));
         ctx->launches += 3;
         Fr64 rc_canon = R[i].from_mont();
         ctx->scale_points[i] = host::g1_generator().mul(rc_canon.v, 4);
@@ -301,6 +314,21 @@ int zkp_srs_generate(zkp_ctx* ctx, const uint8_t tau_x_be[32], const uint8_t tau
     ctx->g2_tau = host::g2_generator().mul(txc.v, 4);
     ctx->have_g2_tau = true;
     set_pairing_lines(ctx);
+    ctx->shard_domain_log = log_n;
+    return ZKP_OK;
+}
+
+// sum of compressed G1 points (the only cross-GPU step of a sharded / Pianist commitment: N partial
+// points, 48 bytes each, combined on the host of rank 0)
+int zkp_g1_sum(const uint8_t* points48, size_t count, uint8_t out48[48]) {
+    if (!points48 || !out48) return fail(ZKP_ERR_ARG, "null argument");
+    host::G1J acc = host::G1J::infinity();
+    for (size_t k = 0; k < count; k++) {
+        host::G1J p;
+        if (!host::g1_decompress(p, points48 + 48 * k, false)) return fail(ZKP_ERR_ENCODING, "bad G1 point");
+        acc = acc.add(p);
+    }
+    host::g1_compress(out48, acc);
     return ZKP_OK;
 }
 

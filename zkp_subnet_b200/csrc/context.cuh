@@ -49,7 +49,7 @@ struct DevBuf {
 };
 
 struct MsmWorkspace {
-    DevBuf keys_a, keys_b, vals_a, vals_b, cub_temp, buckets, next_a, next_b, pool, sums_a, sums_b, bad;
+    DevBuf keys_a, keys_b, vals_a, vals_b, cub_temp, buckets, next_a, next_b, pool, sums_a, sums_b, sums_out, bad;
     std::vector<DevBuf> slot_keys, slot_pts;
     G1Xyzz* h_window = nullptr;  // pinned, W records
     size_t h_window_cap = 0;
@@ -57,7 +57,7 @@ struct MsmWorkspace {
     void release() {
         if (h_bad) cudaFreeHost(h_bad);
         h_bad = nullptr;
-        for (DevBuf* b : {&keys_a, &keys_b, &vals_a, &vals_b, &cub_temp, &buckets, &next_a, &next_b, &pool, &sums_a, &sums_b, &bad})
+        for (DevBuf* b : {&keys_a, &keys_b, &vals_a, &vals_b, &cub_temp, &buckets, &next_a, &next_b, &pool, &sums_a, &sums_b, &sums_out, &bad})
             b->release();
         for (auto& b : slot_keys) b.release();
         for (auto& b : slot_pts) b.release();
@@ -86,6 +86,7 @@ struct zkp_ctx {
     zkp::DevBuf scalars, fr_a, fr_b, fr_c, flush;
     zkp::MsmWorkspace ws;
     uint32_t c_override = 0;
+    uint32_t shard_domain_log = 0;            // log2 of the full domain when the rows are point-range shards
     uint64_t launches = 0;                    // kernels launched by this context (bench accounting)
     // per-size domain tables: wt[k] = w_n^(2^k) (k <= log_n), tw[e] = w_n^e (e < n/2, built on demand)
     struct Domain {

@@ -101,14 +101,14 @@ __global__ void k_fr_reduce(const Fr* __restrict__ partial, uint32_t count, Fr* 
 // Thread t owns elements [t*E, (t+1)*E).  wt[k] = w^(2^k), wt_inv[0] = w^-1.
 __global__ void __launch_bounds__(128)
 k_open_pass1(const Fr* __restrict__ f, uint32_t n, uint32_t E, Fr x, const Fr* __restrict__ wt, Fr w_inv,
-             Fr* __restrict__ inv_d, Fr* __restrict__ partial, uint32_t* __restrict__ hit) {
+             Fr* __restrict__ inv_d, Fr* __restrict__ partial, uint32_t* __restrict__ hit, uint64_t j0) {
     uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
     uint64_t lo = (uint64_t)t * E;
     Fr s1 = Fr::zero();
     if (lo < n) {
         uint32_t cnt = n - lo < E ? (uint32_t)(n - lo) : E;
         const Fr w = load_fr(wt);
-        Fr a = pow_from_table(wt, lo);  // w^lo
+        Fr a = pow_from_table(wt, j0 + lo);  // w^(j0 + lo): element lo of a shard that starts at domain index j0
         Fr run = Fr::one();
         // forward: prefix products of d_j parked in inv_d
         for (uint32_t i = 0; i < cnt; i++) {

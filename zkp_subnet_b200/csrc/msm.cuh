@@ -48,7 +48,11 @@ struct MsmPlan {
     struct RLevel { uint32_t n_in; uint32_t m; uint32_t chunks; };
     std::vector<RLevel> rlevels;
     uint32_t pool_per_window = 0;
+    // tail: P[j] = sum of the inputs whose weight has bit j set (tail_n <= REDUCE_TAIL_MAX inputs)
+    uint32_t tail_n = 0, tail_bits = 0, out_per_window = 0;
+    bool tail_one_based = false;
 };
+constexpr uint32_t REDUCE_TAIL_MAX = 1024;
 
 inline uint32_t msm_window_bits(uint32_t n) {
     uint32_t lg = 0;
@@ -79,22 +83,28 @@ inline MsmPlan msm_make_plan(uint32_t n, int sm_count, uint32_t c_override = 0) 
     size_t items = p.N;
     uint32_t L = L0;
     for (int lvl = 0;; lvl++) {
-        size_t threads = (items + L - 1) / L;
+        size_t shift = lvl ? 1 : 0;  // slot levels slice on odd indices (see k_accumulate)
+        size_t threads = items > shift ? (items - shift + L - 1) / L : 1;
         p.levels.push_back({items, L, threads});
         if (threads <= 1) break;
         items = threads * 2;
         L = lvl == 0 ? 16 : 32;
     }
-    // reduction plan
+    // reduction plan: chunked running sums while the level is large, bit-plane sums for the tail
     uint32_t n_in = p.B;
-    for (;;) {
+    while (n_in > REDUCE_TAIL_MAX) {
         uint32_t m = 8;
         uint32_t chunks = (n_in + m - 1) / m;
         p.rlevels.push_back({n_in, m, chunks});
         p.pool_per_window += chunks;
-        if (chunks <= 1) break;
         n_in = chunks;
     }
+    p.tail_n = n_in;
+    p.tail_one_based = p.rlevels.empty();
+    uint32_t max_weight = p.tail_one_based ? n_in : n_in - 1;
+    p.tail_bits = 0;
+    while ((1u << p.tail_bits) <= max_weight) p.tail_bits++;
+    p.out_per_window = 1 + p.tail_bits;
     return p;
 }
 
@@ -193,15 +203,19 @@ __device__ __forceinline__ G1Affine load_affine(const G1Affine* src) {
 // LEVEL0: items are (key, point index|sign) entries, points gathered from the affine SRS row.
 // else  : items are (key|flags, XYZZ) slots written by the previous level.
 template <bool LEVEL0>
-__global__ void __launch_bounds__(128, 3)
+__global__ void __launch_bounds__(128, LEVEL0 ? 3 : 1)
 k_accumulate(const uint32_t* __restrict__ keys, const uint32_t* __restrict__ vals,
              const G1Affine* __restrict__ points, const G1Xyzz* __restrict__ slots_in, size_t items,
              uint32_t L, uint32_t discard, G1Xyzz* __restrict__ buckets, uint32_t* __restrict__ slot_keys,
              G1Xyzz* __restrict__ slot_pts, int last_level) {
     size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    size_t start = t * L;
+    // Slot lists hold (head_k, tail_k) pairs and the runs worth merging join tail_k with head_{k+1}
+    // (odd index, even index): slices of the slot levels therefore start on ODD indices so that a
+    // slice boundary falls between head_k and tail_k, never inside such a pair.
+    const size_t shift = LEVEL0 ? 0 : 1;
+    size_t start = t * L + (t ? shift : 0);
     if (start >= items) return;
-    size_t end = start + L < items ? start + L : items;
+    size_t end = (t + 1) * L + shift < items ? (t + 1) * L + shift : items;
 
     auto key_at = [&](size_t i) -> uint32_t {
         uint32_t k = keys[i];
@@ -275,7 +289,7 @@ k_accumulate(const uint32_t* __restrict__ keys, const uint32_t* __restrict__ val
 // One thread per (window, chunk of m inputs).  one_based: input j carries weight j+1 (bucket array),
 // else weight j (chunk sums of the previous level).  Writes T = sum_i weight_local(i) * X[i] to the
 // pool and, unless this is the last level, m * S = m * sum_i X[i] (log2 m doublings) as next input.
-__global__ void __launch_bounds__(128, 3)
+__global__ void __launch_bounds__(128, 1)
 k_bucket_reduce(const G1Xyzz* __restrict__ in, uint32_t n_in, uint32_t in_stride, uint32_t m, uint32_t log_m,
                 uint32_t chunks, int one_based, G1Xyzz* __restrict__ next, uint32_t next_stride,
                 G1Xyzz* __restrict__ pool, uint32_t pool_stride, uint32_t pool_off, uint32_t W) {
@@ -295,6 +309,35 @@ k_bucket_reduce(const G1Xyzz* __restrict__ in, uint32_t n_in, uint32_t in_stride
         for (uint32_t d = 0; d < log_m; d++) running = running.dbl();
         store_xyzz(next + (size_t)w * next_stride + k, running);
     }
+}
+
+// Tail of the reduction: block (j, w) computes P[w][j] = sum of in[w][k] over the k whose weight
+// (k + one_based) has bit j set; n_in <= REDUCE_TAIL_MAX.  The host finishes with a Horner pass
+// over the bits (sum_j 2^j P_j).
+constexpr int TAIL_THREADS = 128;
+__global__ void __launch_bounds__(TAIL_THREADS)
+k_bit_sums(const G1Xyzz* __restrict__ in, uint32_t n_in, uint32_t in_stride, int one_based, G1Xyzz* __restrict__ out,
+           uint32_t out_stride, uint32_t out_off) {
+    __shared__ G1Xyzz sh[TAIL_THREADS];
+    uint32_t j = blockIdx.x, w = blockIdx.y;
+    G1Xyzz acc = G1Xyzz::infinity();
+    for (uint32_t k = threadIdx.x; k < n_in; k += TAIL_THREADS) {
+        if (((k + (one_based ? 1u : 0u)) >> j) & 1) {
+            G1Xyzz p = load_xyzz(in + (size_t)w * in_stride + k);
+            acc.add(p);
+        }
+    }
+    sh[threadIdx.x] = acc;
+    __syncthreads();
+    for (int s = TAIL_THREADS / 2; s > 0; s >>= 1) {
+        if ((int)threadIdx.x < s) {
+            G1Xyzz a = sh[threadIdx.x];
+            a.add(sh[threadIdx.x + s]);
+            sh[threadIdx.x] = a;
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) store_xyzz(out + (size_t)w * out_stride + out_off + j, sh[0]);
 }
 
 // Tree-sum: block (part, w) adds in[w*in_stride + part*PART .. +PART) (clipped to count) into

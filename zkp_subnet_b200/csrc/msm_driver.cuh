@@ -31,10 +31,10 @@ inline int msm_run(zkp_ctx* ctx, const MsmPlan& plan, const uint32_t* d_scalars,
         ZKP_CUDA(ws.slot_keys[l].ensure(plan.levels[l].threads * 2 * 4));
         ZKP_CUDA(ws.slot_pts[l].ensure(plan.levels[l].threads * 2 * sizeof(G1Xyzz)));
     }
-    if (ws.h_window_cap < plan.W) {
+    if (ws.h_window_cap < (size_t)plan.W * plan.out_per_window) {
         if (ws.h_window) cudaFreeHost(ws.h_window);
-        ZKP_CUDA(cudaMallocHost(&ws.h_window, sizeof(G1Xyzz) * plan.W));
-        ws.h_window_cap = plan.W;
+        ZKP_CUDA(cudaMallocHost(&ws.h_window, sizeof(G1Xyzz) * plan.W * plan.out_per_window));
+        ws.h_window_cap = (size_t)plan.W * plan.out_per_window;
     }
     if (!ws.h_bad) ZKP_CUDA(cudaMallocHost(&ws.h_bad, 8));
 
@@ -75,48 +75,62 @@ inline int msm_run(zkp_ctx* ctx, const MsmPlan& plan, const uint32_t* d_scalars,
         }
         ctx->launches++;
     }
-    // 4. bucket reduction
-    ZKP_CUDA(ws.pool.ensure((size_t)plan.W * plan.pool_per_window * sizeof(G1Xyzz)));
-    size_t next_cap = (size_t)plan.W * plan.rlevels[0].chunks * sizeof(G1Xyzz);
-    ZKP_CUDA(ws.next_a.ensure(next_cap));
-    ZKP_CUDA(ws.next_b.ensure(next_cap));
+    // 4. bucket reduction: running-sum levels -> pool of plain addends; bit-plane sums for the tail.
+    //    Device output per window: [0] = sum of the pool, [1 + j] = P_j (weight 2^j).
+    const uint32_t opw = plan.out_per_window;
+    ZKP_CUDA(ws.sums_out.ensure((size_t)plan.W * opw * sizeof(G1Xyzz)));
+    G1Xyzz* d_out = ws.sums_out.as<G1Xyzz>();
     const G1Xyzz* in = ws.buckets.as<G1Xyzz>();
-    uint32_t in_stride = plan.B, pool_off = 0;
-    for (size_t l = 0; l < plan.rlevels.size(); l++) {
-        const auto& rl = plan.rlevels[l];
-        bool last = l + 1 == plan.rlevels.size();
-        G1Xyzz* next = last ? nullptr : (l % 2 == 0 ? ws.next_a.as<G1Xyzz>() : ws.next_b.as<G1Xyzz>());
-        uint32_t log_m = 0;
-        while ((1u << log_m) < rl.m) log_m++;
-        uint32_t total = rl.chunks * plan.W;
-        k_bucket_reduce<<<(total + 127) / 128, 128, 0, st>>>(in, rl.n_in, in_stride, rl.m, log_m, rl.chunks, l == 0, next,
-                                                             rl.chunks, ws.pool.as<G1Xyzz>(), plan.pool_per_window,
-                                                             pool_off, plan.W);
-        ctx->launches++;
-        pool_off += rl.chunks;
-        in = next;
-        in_stride = rl.chunks;
+    uint32_t in_stride = plan.B;
+    if (!plan.rlevels.empty()) {
+        ZKP_CUDA(ws.pool.ensure((size_t)plan.W * plan.pool_per_window * sizeof(G1Xyzz)));
+        size_t next_cap = (size_t)plan.W * plan.rlevels[0].chunks * sizeof(G1Xyzz);
+        ZKP_CUDA(ws.next_a.ensure(next_cap));
+        ZKP_CUDA(ws.next_b.ensure(next_cap));
+        uint32_t pool_off = 0;
+        for (size_t l = 0; l < plan.rlevels.size(); l++) {
+            const auto& rl = plan.rlevels[l];
+            G1Xyzz* next = l % 2 == 0 ? ws.next_a.as<G1Xyzz>() : ws.next_b.as<G1Xyzz>();
+            uint32_t log_m = 0;
+            while ((1u << log_m) < rl.m) log_m++;
+            uint32_t total = rl.chunks * plan.W;
+            k_bucket_reduce<<<(total + 127) / 128, 128, 0, st>>>(in, rl.n_in, in_stride, rl.m, log_m, rl.chunks, l == 0, next,
+                                                                 rl.chunks, ws.pool.as<G1Xyzz>(), plan.pool_per_window,
+                                                                 pool_off, plan.W);
+            ctx->launches++;
+            pool_off += rl.chunks;
+            in = next;
+            in_stride = rl.chunks;
+        }
     }
-    // plain sum of the pool -> one point per window
-    uint32_t count = plan.pool_per_window;
-    const G1Xyzz* sin = ws.pool.as<G1Xyzz>();
-    uint32_t sstride = plan.pool_per_window;
-    uint32_t parts0 = (count + SUM_PART - 1) / SUM_PART;
-    ZKP_CUDA(ws.sums_a.ensure((size_t)plan.W * parts0 * sizeof(G1Xyzz)));
-    ZKP_CUDA(ws.sums_b.ensure((size_t)plan.W * parts0 * sizeof(G1Xyzz)));
-    int flip = 0;
-    for (;;) {
-        uint32_t parts = (count + SUM_PART - 1) / SUM_PART;
-        G1Xyzz* sout = flip ? ws.sums_b.as<G1Xyzz>() : ws.sums_a.as<G1Xyzz>();
-        k_sum_segments<<<dim3(parts, plan.W), SUM_THREADS, 0, st>>>(sin, count, sstride, sout, parts);
-        ctx->launches++;
-        sin = sout;
-        sstride = parts;
-        count = parts;
-        flip ^= 1;
-        if (parts == 1) break;
+    k_bit_sums<<<dim3(plan.tail_bits, plan.W), TAIL_THREADS, 0, st>>>(in, plan.tail_n, in_stride, plan.tail_one_based, d_out, opw, 1);
+    ctx->launches++;
+    if (!plan.rlevels.empty()) {
+        // plain sum of the pool -> d_out[w][0]
+        uint32_t count = plan.pool_per_window;
+        const G1Xyzz* sin = ws.pool.as<G1Xyzz>();
+        uint32_t sstride = plan.pool_per_window;
+        uint32_t parts0 = (count + SUM_PART - 1) / SUM_PART;
+        ZKP_CUDA(ws.sums_a.ensure((size_t)plan.W * parts0 * sizeof(G1Xyzz)));
+        ZKP_CUDA(ws.sums_b.ensure((size_t)plan.W * parts0 * sizeof(G1Xyzz)));
+        int flip = 0;
+        for (;;) {
+            uint32_t parts = (count + SUM_PART - 1) / SUM_PART;
+            bool fin = parts == 1;
+            G1Xyzz* sout = fin ? d_out : (flip ? ws.sums_b.as<G1Xyzz>() : ws.sums_a.as<G1Xyzz>());
+            k_sum_segments<<<dim3(parts, plan.W), SUM_THREADS, 0, st>>>(sin, count, sstride, sout, fin ? opw : parts);
+            ctx->launches++;
+            if (fin) break;
+            sin = sout;
+            sstride = parts;
+            count = parts;
+            flip ^= 1;
+        }
+    } else {
+        ZKP_CUDA(cudaMemset2DAsync(d_out, (size_t)opw * sizeof(G1Xyzz), 0, sizeof(G1Xyzz), plan.W, st));
     }
-    ZKP_CUDA(cudaMemcpyAsync(ws.h_window, sin, sizeof(G1Xyzz) * plan.W, cudaMemcpyDeviceToHost, st));
+    const G1Xyzz* sin = d_out;
+    ZKP_CUDA(cudaMemcpyAsync(ws.h_window, sin, sizeof(G1Xyzz) * plan.W * opw, cudaMemcpyDeviceToHost, st));
     ZKP_CUDA(cudaMemcpyAsync(ws.h_bad, ws.bad.p, 4, cudaMemcpyDeviceToHost, st));
     ZKP_CUDA(cudaStreamSynchronize(st));
     ZKP_CUDA(cudaGetLastError());
@@ -131,22 +145,29 @@ inline int msm_run(zkp_ctx* ctx, const MsmPlan& plan, const uint32_t* d_scalars,
     return ZKP_OK;
 }
 
-// 5. host: fold the window sums, result in Jacobian coordinates
+// 5. host: per window  pool + sum_j 2^j P_j  (Horner over the bit planes), then fold the windows
+inline host::G1J xyzz_to_jac(const G1Xyzz& p) {
+    using namespace host;
+    Fq64 x, y, zz, zzz;
+    memcpy(x.v, p.x.v, 48);
+    memcpy(y.v, p.y.v, 48);
+    memcpy(zz.v, p.zz.v, 48);
+    memcpy(zzz.v, p.zzz.v, 48);
+    if (zz.is_zero()) return G1J::infinity();
+    // XYZZ (x = X/ZZ, y = Y/ZZZ, ZZ^3 = ZZZ^2)  ->  Jacobian with Z = ZZ
+    return G1J{x * zz, y * zzz, zz};
+}
 inline host::G1J msm_fold(const MsmPlan& plan, const G1Xyzz* h_window) {
     using namespace host;
     G1J acc = G1J::infinity();
+    const uint32_t opw = plan.out_per_window;
     for (int w = (int)plan.W - 1; w >= 0; w--) {
         for (uint32_t d = 0; d < plan.c; d++) acc = acc.dbl();
-        Fq64 x, y, zz, zzz;
-        memcpy(x.v, h_window[w].x.v, 48);
-        memcpy(y.v, h_window[w].y.v, 48);
-        memcpy(zz.v, h_window[w].zz.v, 48);
-        memcpy(zzz.v, h_window[w].zzz.v, 48);
-        if (!zz.is_zero()) {
-            // XYZZ (x = X/ZZ, y = Y/ZZZ, ZZ^3 = ZZZ^2)  ->  Jacobian with Z = ZZ
-            G1J p = {x * zz, y * zzz, zz};
-            acc = acc.add(p);
-        }
+        const G1Xyzz* rec = h_window + (size_t)w * opw;
+        G1J win = G1J::infinity();
+        for (int j = (int)plan.tail_bits - 1; j >= 0; j--) win = win.dbl().add(xyzz_to_jac(rec[1 + j]));
+        win = win.add(xyzz_to_jac(rec[0]));
+        acc = acc.add(win);
     }
     return acc;
 }

@@ -79,12 +79,12 @@ __global__ void k_points_to_be96(const G1Affine* __restrict__ in, size_t n, uint
 // out[j] = coef * w^j * inv_d[j]   (Lagrange basis values: coef = -(tau^n - 1)/n * R_i(tau_y),
 // inv_d[j] = 1/(w^j - tau))
 __global__ void k_lagrange_scalars(const Fr* __restrict__ inv_d, uint32_t n, const Fr* __restrict__ wt, Fr coef,
-                                   Fr* __restrict__ out) {
+                                   Fr* __restrict__ out, uint64_t j0) {
     constexpr uint32_t E = 8;
     uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
     uint64_t lo = (uint64_t)t * E;
     if (lo >= n) return;
-    Fr a = pow_from_table(wt, lo) * coef;
+    Fr a = pow_from_table(wt, j0 + lo) * coef;
     const Fr w = load_fr(wt);
     for (uint32_t i = 0; i < E && lo + i < n; i++) {
         store_fr(out + lo + i, a * load_fr(inv_d + lo + i));

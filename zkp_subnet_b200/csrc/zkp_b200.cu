@@ -143,6 +143,7 @@ int zkp_srs_set_shape(zkp_ctx* ctx, uint32_t log_n, uint32_t log_machines) {
     ZKP_CUDA(ctx->srs.ensure(total * sizeof(G1Affine)));
     ctx->log_n = log_n;
     ctx->log_m = log_machines;
+    ctx->shard_domain_log = log_n;
     ctx->row_loaded.assign((size_t)1 << log_machines, 0);
     ctx->scale_points.assign((size_t)1 << log_machines, host::G1J::infinity());
     ctx->shaped = true;

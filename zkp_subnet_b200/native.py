@@ -38,6 +38,8 @@ _SIGNATURES = {
     "zkp_last_error": [],
     "zkp_device_count": [],
     "zkp_srs_generate": [_ctxp, _u8p, _u8p, ctypes.c_uint32, ctypes.c_uint32],
+    "zkp_srs_generate_shard": [_ctxp, _u8p, _u8p, ctypes.c_uint32, ctypes.c_uint32, ctypes.c_uint32, ctypes.c_uint32],
+    "zkp_g1_sum": [_u8p, ctypes.c_size_t, _u8p],
     "zkp_srs_set_shape": [_ctxp, ctypes.c_uint32, ctypes.c_uint32],
     "zkp_srs_import_row": [_ctxp, ctypes.c_uint32, _u8p, ctypes.c_size_t, _u8p],
     "zkp_srs_import_g2_tau": [_ctxp, _u8p],
@@ -125,6 +127,10 @@ class Context:
     # ---- SRS
     def srs_generate(self, tau_x: int, tau_y: int, log_n: int, log_machines: int) -> None:
         check(lib().zkp_srs_generate(self._h, tau_x.to_bytes(32, "big"), tau_y.to_bytes(32, "big"), log_n, log_machines))
+
+    def srs_generate_shard(self, tau_x: int, tau_y: int, log_n: int, log_machines: int, shard: int, log_shards: int) -> None:
+        check(lib().zkp_srs_generate_shard(self._h, tau_x.to_bytes(32, "big"), tau_y.to_bytes(32, "big"), log_n,
+                                           log_machines, shard, log_shards))
 
     def srs_set_shape(self, log_n: int, log_machines: int) -> None:
         check(lib().zkp_srs_set_shape(self._h, log_n, log_machines))
@@ -240,6 +246,12 @@ def b64_encode_fr(vals_be: bytes) -> bytes:
     count = len(vals_be) // 32
     out = ctypes.create_string_buffer(43 * count)
     check(lib().zkp_b64_encode_fr(vals_be, count, out))
+    return out.raw
+
+
+def g1_sum(points48: bytes) -> bytes:
+    out = ctypes.create_string_buffer(48)
+    check(lib().zkp_g1_sum(points48, len(points48) // 48, out))
     return out.raw
 
 
