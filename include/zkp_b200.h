@@ -109,6 +109,8 @@ int zkp_bench_commit_open(zkp_ctx* ctx, uint32_t row, const uint8_t* poly_be, si
                           int reps, int flush_l2, float* ms_per_iter, float* ms_msm_kernel, uint32_t* launches,
                           uint8_t commitment48[48], uint8_t eval_be[32], uint8_t proof48[48]);
 int zkp_bench_ntt(zkp_ctx* ctx, size_t n, int reps, int inverse, float* ms_per_ntt);
+/* roofline denominators measured live: chip-wide IMAD.WIDE.U32 issue rate and dependent-chain Fq products/s */
+int zkp_bench_peaks(zkp_ctx* ctx, double* imad_wide_per_s, double* fq_mul_per_s);
 /* MSM tuning knobs: window bits (0 = automatic) */
 int zkp_set_msm_window(zkp_ctx* ctx, uint32_t c);
 int zkp_msm_info(zkp_ctx* ctx, size_t n, uint32_t* c, uint32_t* windows, uint64_t* fq_muls);

@@ -626,6 +626,43 @@ int zkp_bench_commit_open(zkp_ctx* ctx, uint32_t row, const uint8_t* poly_be, si
     return rc;
 }
 
+// measured issue peaks on this device: IMAD.WIDE.U32 per second (whole chip) and dependent-chain Fq
+// products per second at full occupancy
+int zkp_bench_peaks(zkp_ctx* ctx, double* imad_wide_per_s, double* fq_mul_per_s) {
+    if (!ctx || !imad_wide_per_s || !fq_mul_per_s) return fail(ZKP_ERR_ARG, "null argument");
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    DeviceGuard g(ctx->device);
+    const int threads = 256, blocks = ctx->sm_count * 8;  // 64 warps per SM
+    ZKP_CUDA(ctx->flush.ensure((size_t)threads * blocks * sizeof(Fq)));
+    cudaEvent_t e0, e1;
+    ZKP_CUDA(cudaEventCreate(&e0));
+    ZKP_CUDA(cudaEventCreate(&e1));
+    float best_w = 1e30f, best_f = 1e30f;
+    const int fq_iters = 512;
+    for (int r = 0; r < 4; r++) {
+        cudaEventRecord(e0, ctx->stream);
+        k_peak_imad_wide<<<blocks, threads, 0, ctx->stream>>>(ctx->flush.as<uint32_t>(), 0x9e3779b1u);
+        cudaEventRecord(e1, ctx->stream);
+        cudaEventSynchronize(e1);
+        float ms = 0;
+        cudaEventElapsedTime(&ms, e0, e1);
+        if (r && ms < best_w) best_w = ms;
+        cudaEventRecord(e0, ctx->stream);
+        k_peak_fq_mul<<<blocks / 2, threads, 0, ctx->stream>>>(ctx->flush.as<Fq>(), fq_iters);
+        cudaEventRecord(e1, ctx->stream);
+        cudaEventSynchronize(e1);
+        cudaEventElapsedTime(&ms, e0, e1);
+        if (r && ms < best_f) best_f = ms;
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    ZKP_CUDA(cudaGetLastError());
+    ctx->launches += 8;
+    *imad_wide_per_s = (double)threads * blocks * 4.0 * PEAK_ITERS / (best_w * 1e-3);
+    *fq_mul_per_s = (double)threads * (blocks / 2) * fq_iters / (best_f * 1e-3);
+    return ZKP_OK;
+}
+
 int zkp_bench_ntt(zkp_ctx* ctx, size_t n, int reps, int inverse, float* ms_per_ntt) {
     if (!ctx || !ms_per_ntt || !is_pow2(n) || reps < 1) return fail(ZKP_ERR_ARG, "bad argument");
     std::lock_guard<std::mutex> lk(ctx->mu);

@@ -12,6 +12,7 @@
 #include "ntt.cuh"
 #include "host/pairing.hpp"
 #include "srs.cuh"
+#include "bench_kernels.cuh"
 
 using namespace zkp;
 
