@@ -69,6 +69,30 @@ def test_window_override_is_result_invariant(gpu_ctx):
         gpu_ctx.set_msm_window(0)
 
 
+def test_fixed_base_tables_match_classic(gpu_ctx):
+    # the per-row tables [2^(c w)] P_i (shared buckets, no window fold) and the classic per-window
+    # buckets must give identical bytes, for every window width
+    n = 1 << 10
+    gpu_ctx.srs_generate(TAU_X, TAU_Y, 10, 1)
+    try:
+        for row in (0, 1):
+            srs = gpu_ctx.srs_export_row(row, n)
+            for name, sc in adversarial(n).items():
+                exp = ref.msm(srs, sc, 8)
+                for mode in (True, False):
+                    gpu_ctx.set_msm_mode(mode)
+                    for c in (0, 6, 10, 12):
+                        gpu_ctx.set_msm_window(c)
+                        assert gpu_ctx.msm_g1(row, sc) == exp, (row, name, mode, c)
+            gpu_ctx.set_msm_mode(True)
+            gpu_ctx.set_msm_window(0)
+            sc = ref.random_scalars(5, n - 7)  # ragged prefix with tables
+            assert gpu_ctx.msm_g1(row, sc) == ref.msm(srs, sc, 8)
+    finally:
+        gpu_ctx.set_msm_mode(True)
+        gpu_ctx.set_msm_window(0)
+
+
 def test_srs_generate_matches_oracle(gpu_ctx):
     gpu_ctx.srs_generate(TAU_X, TAU_Y, 4, 2)
     Rs = ref.split32(ref.lagrange_scalars(4, TAU_Y))

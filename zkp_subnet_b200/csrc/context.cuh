@@ -86,6 +86,11 @@ struct zkp_ctx {
     zkp::DevBuf scalars, fr_a, fr_b, fr_c, flush;
     zkp::MsmWorkspace ws;
     uint32_t c_override = 0;
+    // fixed-base tables: per SRS row, [2^(c w)] P_i for w < W (slice w at w * 2^log_n); built lazily
+    struct Precomp { zkp::DevBuf table; uint32_t c = 0, W = 0; };
+    std::vector<Precomp> precomp;
+    bool use_precomp = true;
+    zkp::DevBuf scratch_xyzz, scratch_fq;
     uint32_t shard_domain_log = 0;            // log2 of the full domain when the rows are point-range shards
     uint64_t launches = 0;                    // kernels launched by this context (bench accounting)
     // per-size domain tables: wt[k] = w_n^(2^k) (k <= log_n), tw[e] = w_n^e (e < n/2, built on demand)

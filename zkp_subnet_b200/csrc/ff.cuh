@@ -88,6 +88,27 @@ struct Fp {
         uint32_t even[N], odd[N];
         Fp r;
         if constexpr (N == 12) {
+#if defined(__CUDA_ARCH__) && !defined(ZKP_UNROLL_MONT_ROWS)
+            // All 12 rows as a ROLLED loop of row pairs (a generic row on zero accumulators is the first
+            // row): the bucket-accumulation kernel inlines ten of these products and was instruction-fetch
+            // bound when fully unrolled (ncu: stall_no_instruction 1.7 per issue, profiles/).  b's limbs
+            // rotate down two places per trip; the moves issue on slots the 4-cycle IMAD.WIDE pipe leaves idle.
+            // (Measured on B200: rolling ALL rows, first pair included, costs 14% of raw product throughput
+            // -- no overlap across the loop back-edge -- so the first pair stays outside and the loop body is
+            // unrolled by two pairs.)
+            chains::fq_row_first(even, odd, a.v, b.v[0]);
+            chains::fq_row(odd, even, a.v, b.v[1]);
+            uint32_t bb[N - 2];
+#pragma unroll
+            for (int k = 0; k < N - 2; k++) bb[k] = b.v[k + 2];
+#pragma unroll 1
+            for (int i = 2; i < N; i += 2) {
+                chains::fq_row(even, odd, a.v, bb[0]);
+                chains::fq_row(odd, even, a.v, bb[1]);
+#pragma unroll
+                for (int k = 0; k < N - 4; k++) bb[k] = bb[k + 2];
+            }
+#else
             chains::fq_row_first(even, odd, a.v, b.v[0]);
             chains::fq_row(odd, even, a.v, b.v[1]);
 #pragma unroll
@@ -95,6 +116,7 @@ struct Fp {
                 chains::fq_row(even, odd, a.v, b.v[i]);
                 chains::fq_row(odd, even, a.v, b.v[i + 1]);
             }
+#endif
             chains::fq_merge(r.v, odd, even);
             chains::fq_reduce_once(r.v, 0);
         } else {

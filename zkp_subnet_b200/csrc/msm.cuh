@@ -16,10 +16,16 @@
 //                       (key, point) sequence and is reduced by the same kernel (XYZZ + XYZZ
 //                       instead of XYZZ + affine) level by level until one thread sees it all.
 //                       Deterministic: no atomics anywhere.
-//   4. k_bucket_reduce  sum_b b * B[w][b] by chunked running sums, recursively on the chunk sums
-//                       (each level multiplies its chunk sums by the chunk size with doublings, so
-//                       all levels feed one pool of plain addends); k_sum_segments tree-sums the pool.
-//   5. host             fold the W window sums (c doublings each), to affine, compress.
+//   4. reduction        sum_b (b+1) B[b] with b = hi * 2^cl + lo: k_rowcol_sums forms the row sums R_hi and
+//                       column sums C_lo as plain tree sums (2 additions per bucket, depth ~11), k_bit_sums the
+//                       bit planes P_j = sum of the R (resp. C) whose weight has bit j set; the host finishes
+//                       with two Horner passes.  No long sequential chains: a lone warp needs ~17 us per point
+//                       addition on this machine, so depth, not work, is what the tail of an MSM costs.
+//   5. host             Horner over the bit planes, window fold (classic mode only), to affine, compress.
+//
+// Fixed-base mode (plan.precomp): the SRS row is resident, so the context keeps [2^(c w)] P_i for every
+// digit position w (W x the row in HBM).  All digits then feed ONE set of 2^(c-1) buckets: no window fold,
+// a 16x smaller reduction, and room for a wider window (c = log2 n), i.e. ~19% fewer bucket additions.
 #pragma once
 #include <cub/device/device_radix_sort.cuh>
 #include <cuda_runtime.h>
@@ -36,41 +42,49 @@ constexpr uint32_t KEY_EMPTY_FLAG = 0x80000000u;  // slot carries a key but no p
 struct MsmPlan {
     uint32_t n = 0;        // points
     uint32_t c = 0;        // window bits
-    uint32_t W = 0;        // windows
-    uint32_t B = 0;        // buckets per window = 2^(c-1)
+    uint32_t W = 0;        // digit positions per scalar
+    uint32_t Wb = 0;       // bucket windows: W (classic) or 1 (fixed-base tables, shared buckets)
+    uint32_t B = 0;        // buckets per bucket window = 2^(c-1)
     uint32_t key_bits = 0; // radix-sort bits
     uint32_t discard = 0;  // key of zero digits
+    bool precomp = false;  // vals index the table [2^(c w)] P_i at w * win_stride + i
+    uint32_t win_stride = 0;
     size_t N = 0;          // entries = n * W
     // accumulation levels: level 0 consumes entries, level k>0 consumes the slots of level k-1
     struct Level { size_t items; uint32_t L; size_t threads; };
     std::vector<Level> levels;
-    // reduction levels
-    struct RLevel { uint32_t n_in; uint32_t m; uint32_t chunks; };
-    std::vector<RLevel> rlevels;
-    uint32_t pool_per_window = 0;
-    // tail: P[j] = sum of the inputs whose weight has bit j set (tail_n <= REDUCE_TAIL_MAX inputs)
-    uint32_t tail_n = 0, tail_bits = 0, out_per_window = 0;
-    bool tail_one_based = false;
+    // reduction: B > REDUCE_DIRECT_MAX -> rows x cols split, else bit planes straight from the buckets
+    bool rowcol = false;
+    uint32_t log_rows = 0, log_cols = 0;
+    uint32_t bits_c = 0, bits_r = 0;  // bit planes of the column / row weights
+    uint32_t out_per_window = 0;      // bits_c + bits_r records per bucket window
 };
-constexpr uint32_t REDUCE_TAIL_MAX = 1024;
+constexpr uint32_t REDUCE_DIRECT_MAX = 1024;
 
-inline uint32_t msm_window_bits(uint32_t n) {
+inline uint32_t ilog2_floor(uint32_t n) {
     uint32_t lg = 0;
     while ((1ull << (lg + 1)) <= n) lg++;
-    // measured sweet spots: buckets ~ n/32 per window
-    int c = (int)lg - 4;
+    return lg;
+}
+inline uint32_t msm_window_bits(uint32_t n, bool precomp) {
+    int lg = (int)ilog2_floor(n);
+    // classic: buckets ~ n/32 per window.  fixed-base: one shared bucket set of ~n/2, ~2W entries per bucket
+    int c = precomp ? lg : lg - 4;
     if (c < 4) c = 4;
-    if (c > 16) c = 16;
+    if (c > (precomp ? 22 : 16)) c = precomp ? 22 : 16;
     return (uint32_t)c;
 }
 
-inline MsmPlan msm_make_plan(uint32_t n, int sm_count, uint32_t c_override = 0) {
+inline MsmPlan msm_make_plan(uint32_t n, int sm_count, uint32_t c, bool precomp, uint32_t win_stride) {
     MsmPlan p;
     p.n = n;
-    p.c = c_override ? c_override : msm_window_bits(n);
+    p.c = c;
     p.W = 255 / p.c + 1;
+    p.precomp = precomp;
+    p.win_stride = win_stride;
+    p.Wb = precomp ? 1 : p.W;
     p.B = 1u << (p.c - 1);
-    p.discard = p.W * p.B;
+    p.discard = p.Wb * p.B;
     p.key_bits = 1;
     while ((1ull << p.key_bits) <= p.discard) p.key_bits++;
     p.N = (size_t)n * p.W;
@@ -88,23 +102,20 @@ inline MsmPlan msm_make_plan(uint32_t n, int sm_count, uint32_t c_override = 0) 
         p.levels.push_back({items, L, threads});
         if (threads <= 1) break;
         items = threads * 2;
-        L = lvl == 0 ? 16 : 32;
+        L = lvl == 0 ? 16 : 8;  // shallow slot levels: every sequential addition costs ~17 us of latency
     }
-    // reduction plan: chunked running sums while the level is large, bit-plane sums for the tail
-    uint32_t n_in = p.B;
-    while (n_in > REDUCE_TAIL_MAX) {
-        uint32_t m = 8;
-        uint32_t chunks = (n_in + m - 1) / m;
-        p.rlevels.push_back({n_in, m, chunks});
-        p.pool_per_window += chunks;
-        n_in = chunks;
+    // reduction plan
+    if (p.B > REDUCE_DIRECT_MAX) {
+        p.rowcol = true;
+        p.log_cols = (p.c - 1 + 1) / 2;
+        p.log_rows = p.c - 1 - p.log_cols;
+        p.bits_c = p.log_cols + 1;  // column weights lo + 1 in [1, 2^log_cols]
+        p.bits_r = p.log_rows;      // row weights hi in [0, 2^log_rows)
+    } else {
+        p.bits_c = p.c;             // bucket weights b + 1 in [1, 2^(c-1)]
+        p.bits_r = 0;
     }
-    p.tail_n = n_in;
-    p.tail_one_based = p.rlevels.empty();
-    uint32_t max_weight = p.tail_one_based ? n_in : n_in - 1;
-    p.tail_bits = 0;
-    while ((1u << p.tail_bits) <= max_weight) p.tail_bits++;
-    p.out_per_window = 1 + p.tail_bits;
+    p.out_per_window = p.bits_c + p.bits_r;
     return p;
 }
 
@@ -116,9 +127,11 @@ inline MsmPlan msm_make_plan(uint32_t n, int sm_count, uint32_t c_override = 0) 
 // SCALAR_MONT = little-endian Montgomery limbs (output of the opening kernels).  Non-canonical
 // inputs (>= r) set *bad.
 enum { SCALAR_LE = 0, SCALAR_BE = 1, SCALAR_MONT = 2 };
+// precomp: every digit position shares the bucket set (key = |digit| - 1) and val indexes the table
+// [2^(c w)] P_i at w * win_stride + i.
 __global__ void k_decompose(const uint32_t* __restrict__ scalars, uint32_t n, uint32_t c, uint32_t W,
-                            uint32_t B, uint32_t discard, int fmt, uint32_t* __restrict__ keys,
-                            uint32_t* __restrict__ vals, uint32_t* __restrict__ bad) {
+                            uint32_t B, uint32_t discard, int fmt, int precomp, uint32_t win_stride,
+                            uint32_t* __restrict__ keys, uint32_t* __restrict__ vals, uint32_t* __restrict__ bad) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     uint32_t s[9];
@@ -163,8 +176,8 @@ __global__ void k_decompose(const uint32_t* __restrict__ scalars, uint32_t n, ui
         uint32_t mag = neg ? (1u << c) - raw : raw;
         carry = neg;
         size_t o = (size_t)w * n + i;
-        keys[o] = mag ? w * B + mag - 1 : discard;
-        vals[o] = i | (neg << 31);
+        keys[o] = mag ? (precomp ? 0u : w * B) + mag - 1 : discard;
+        vals[o] = (precomp ? w * win_stride + i : i) | (neg << 31);
     }
 }
 
@@ -286,28 +299,44 @@ k_accumulate(const uint32_t* __restrict__ keys, const uint32_t* __restrict__ val
 // ------------------------------------------------------------------------------------------------
 // 4. bucket reduction
 // ------------------------------------------------------------------------------------------------
-// One thread per (window, chunk of m inputs).  one_based: input j carries weight j+1 (bucket array),
-// else weight j (chunk sums of the previous level).  Writes T = sum_i weight_local(i) * X[i] to the
-// pool and, unless this is the last level, m * S = m * sum_i X[i] (log2 m doublings) as next input.
-__global__ void __launch_bounds__(128, 1)
-k_bucket_reduce(const G1Xyzz* __restrict__ in, uint32_t n_in, uint32_t in_stride, uint32_t m, uint32_t log_m,
-                uint32_t chunks, int one_based, G1Xyzz* __restrict__ next, uint32_t next_stride,
-                G1Xyzz* __restrict__ pool, uint32_t pool_stride, uint32_t pool_off, uint32_t W) {
-    uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= chunks * W) return;
-    uint32_t w = t / chunks, k = t % chunks;
-    const G1Xyzz* x = in + (size_t)w * in_stride + (size_t)k * m;
-    uint32_t cnt = n_in - k * m < m ? n_in - k * m : m;
-    G1Xyzz running = G1Xyzz::infinity(), sum = G1Xyzz::infinity();
-    for (int i = (int)cnt - 1; i >= 0; i--) {
-        G1Xyzz p = load_xyzz(x + i);
-        running.add(p);
-        if (one_based || i > 0) sum.add(running);
+constexpr int RC_THREADS = 128;
+__device__ __forceinline__ void block_tree_sum(G1Xyzz* sh, G1Xyzz acc, G1Xyzz* out) {
+    sh[threadIdx.x] = acc;
+    __syncthreads();
+    for (int s = RC_THREADS / 2; s > 0; s >>= 1) {
+        if ((int)threadIdx.x < s) {
+            G1Xyzz a = sh[threadIdx.x];
+            a.add(sh[threadIdx.x + s]);
+            sh[threadIdx.x] = a;
+        }
+        __syncthreads();
     }
-    store_xyzz(pool + (size_t)w * pool_stride + pool_off + k, sum);
-    if (next) {
-        for (uint32_t d = 0; d < log_m; d++) running = running.dbl();
-        store_xyzz(next + (size_t)w * next_stride + k, running);
+    if (threadIdx.x == 0) store_xyzz(out, sh[0]);
+}
+// Bucket array of one window viewed as 2^log_rows x 2^log_cols (bucket b = hi * cols + lo).
+// Blocks [0, cols) of grid.x form the column sums C_lo = sum_hi X[hi][lo] (strided reads), blocks
+// [cols, cols + rows) the row sums R_hi = sum_lo X[hi][lo] (contiguous reads).  grid.y = bucket window.
+__global__ void __launch_bounds__(RC_THREADS)
+k_rowcol_sums(const G1Xyzz* __restrict__ in, uint32_t log_rows, uint32_t log_cols, G1Xyzz* __restrict__ out_c,
+              G1Xyzz* __restrict__ out_r) {
+    __shared__ G1Xyzz sh[RC_THREADS];
+    const uint32_t rows = 1u << log_rows, cols = 1u << log_cols, w = blockIdx.y;
+    const G1Xyzz* x = in + ((size_t)w << (log_rows + log_cols));
+    G1Xyzz acc = G1Xyzz::infinity();
+    if (blockIdx.x < cols) {
+        uint32_t lo = blockIdx.x;
+        for (uint32_t hi = threadIdx.x; hi < rows; hi += RC_THREADS) {
+            G1Xyzz p = load_xyzz(x + ((size_t)hi << log_cols) + lo);
+            acc.add(p);
+        }
+        block_tree_sum(sh, acc, out_c + (size_t)w * cols + lo);
+    } else {
+        uint32_t hi = blockIdx.x - cols;
+        for (uint32_t lo = threadIdx.x; lo < cols; lo += RC_THREADS) {
+            G1Xyzz p = load_xyzz(x + ((size_t)hi << log_cols) + lo);
+            acc.add(p);
+        }
+        block_tree_sum(sh, acc, out_r + (size_t)w * rows + hi);
     }
 }
 
@@ -338,35 +367,6 @@ k_bit_sums(const G1Xyzz* __restrict__ in, uint32_t n_in, uint32_t in_stride, int
         __syncthreads();
     }
     if (threadIdx.x == 0) store_xyzz(out + (size_t)w * out_stride + out_off + j, sh[0]);
-}
-
-// Tree-sum: block (part, w) adds in[w*in_stride + part*PART .. +PART) (clipped to count) into
-// out[w*out_stride + part].
-constexpr int SUM_THREADS = 128;
-constexpr int SUM_PART = 512;
-__global__ void __launch_bounds__(SUM_THREADS)
-k_sum_segments(const G1Xyzz* __restrict__ in, uint32_t count, uint32_t in_stride, G1Xyzz* __restrict__ out,
-               uint32_t out_stride) {
-    __shared__ G1Xyzz sh[SUM_THREADS];
-    uint32_t part = blockIdx.x, w = blockIdx.y;
-    uint32_t lo = part * SUM_PART;
-    uint32_t hi = lo + SUM_PART < count ? lo + SUM_PART : count;
-    G1Xyzz acc = G1Xyzz::infinity();
-    for (uint32_t i = lo + threadIdx.x; i < hi; i += SUM_THREADS) {
-        G1Xyzz p = load_xyzz(in + (size_t)w * in_stride + i);
-        acc.add(p);
-    }
-    sh[threadIdx.x] = acc;
-    __syncthreads();
-    for (int s = SUM_THREADS / 2; s > 0; s >>= 1) {
-        if ((int)threadIdx.x < s) {
-            G1Xyzz a = sh[threadIdx.x];
-            a.add(sh[threadIdx.x + s]);
-            sh[threadIdx.x] = a;
-        }
-        __syncthreads();
-    }
-    if (threadIdx.x == 0) store_xyzz(out + (size_t)w * out_stride + part, sh[0]);
 }
 
 }  // namespace zkp

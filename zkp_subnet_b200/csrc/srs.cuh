@@ -109,6 +109,20 @@ k_fixed_base_mul(const Fr* __restrict__ scalars, size_t n, const G1Affine* __res
     out[i] = acc;
 }
 
+// fixed-base table step: out[i] = [2^c] in[i]
+__global__ void __launch_bounds__(128)
+k_table_next(const G1Affine* __restrict__ in, size_t n, uint32_t c, G1Xyzz* __restrict__ out) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    G1Affine p = in[i];
+    G1Xyzz acc = G1Xyzz::infinity();
+    if (!p.is_inf()) {
+        acc = G1Xyzz::dbl_affine(p.x, p.y);
+        for (uint32_t d = 1; d < c; d++) acc = acc.dbl();
+    }
+    out[i] = acc;
+}
+
 // XYZZ -> affine with one inversion per run of E points (prefix products parked in scratch)
 __global__ void __launch_bounds__(128)
 k_xyzz_to_affine(const G1Xyzz* __restrict__ in, size_t n, uint32_t E, Fq* __restrict__ scratch, G1Affine* __restrict__ out) {

@@ -60,10 +60,65 @@ int finish_point(const MsmPlan& plan, zkp_ctx* ctx, uint8_t out48[48]) {
     return ZKP_OK;
 }
 
+// Build (once per row and window size) the fixed-base table [2^(c w)] P_i, w < W.  Returns false in
+// *ok if the table would not fit comfortably in free HBM (the caller then uses the classic path).
+int ensure_precomp(zkp_ctx* ctx, uint32_t row, uint32_t c, bool* ok) {
+    *ok = false;
+    if (ctx->precomp.size() != ctx->row_loaded.size()) ctx->precomp.assign(ctx->row_loaded.size(), zkp_ctx::Precomp());
+    zkp_ctx::Precomp& pc = ctx->precomp[row];
+    const uint32_t W = 255 / c + 1;
+    if (pc.table.p && pc.c == c && pc.W == W) { *ok = true; return ZKP_OK; }
+    const size_t n_row = (size_t)1 << ctx->log_n;
+    const size_t bytes = (size_t)W * n_row * sizeof(G1Affine);
+    pc.table.release();
+    pc.c = 0;
+    size_t free_b = 0, total_b = 0;
+    ZKP_CUDA(cudaMemGetInfo(&free_b, &total_b));
+    if (bytes > free_b / 2) return ZKP_OK;  // keep at least half of the free HBM for workspaces
+    ZKP_CUDA(pc.table.ensure(bytes));
+    ZKP_CUDA(ctx->scratch_xyzz.ensure(n_row * sizeof(G1Xyzz)));
+    ZKP_CUDA(ctx->scratch_fq.ensure(n_row * sizeof(Fq)));
+    cudaStream_t st = ctx->stream;
+    G1Affine* tab = pc.table.as<G1Affine>();
+    ZKP_CUDA(cudaMemcpyAsync(tab, row_ptr(ctx, row), n_row * sizeof(G1Affine), cudaMemcpyDeviceToDevice, st));
+    const uint32_t EA = 16;
+    const unsigned ta = (unsigned)((n_row + EA - 1) / EA);
+    for (uint32_t w = 1; w < W; w++) {
+        k_table_next<<<(unsigned)((n_row + 127) / 128), 128, 0, st>>>(tab + (size_t)(w - 1) * n_row, n_row, c, ctx->scratch_xyzz.as<G1Xyzz>());
+        k_xyzz_to_affine<<<(ta + 127) / 128, 128, 0, st>>>(ctx->scratch_xyzz.as<G1Xyzz>(), n_row, EA, ctx->scratch_fq.as<Fq>(),
+                                                           tab + (size_t)w * n_row);
+        ctx->launches += 2;
+    }
+    ZKP_CUDA(cudaStreamSynchronize(st));
+    ZKP_CUDA(cudaGetLastError());
+    pc.c = c;
+    pc.W = W;
+    *ok = true;
+    return ZKP_OK;
+}
+
+void drop_precomp(zkp_ctx* ctx, int row /* -1 = all */) {
+    for (size_t r = 0; r < ctx->precomp.size(); r++)
+        if (row < 0 || (size_t)row == r) { ctx->precomp[r].table.release(); ctx->precomp[r].c = 0; }
+}
+
+MsmPlan plan_for(zkp_ctx* ctx, size_t n, bool precomp) {
+    uint32_t c = ctx->c_override ? ctx->c_override : msm_window_bits((uint32_t)n, precomp);
+    return msm_make_plan((uint32_t)n, ctx->sm_count, c, precomp, 1u << ctx->log_n);
+}
+
 // MSM over row `row` with device-resident scalars
 int msm_device(zkp_ctx* ctx, uint32_t row, const uint32_t* d_scalars, int fmt, size_t n, uint8_t out48[48]) {
-    MsmPlan plan = msm_make_plan((uint32_t)n, ctx->sm_count, ctx->c_override);
-    int rc = msm_run(ctx, plan, d_scalars, fmt, row_ptr(ctx, row));
+    bool precomp = false;
+    MsmPlan plan;
+    if (ctx->use_precomp && n >= 256) {
+        plan = plan_for(ctx, n, true);
+        int rc = ensure_precomp(ctx, row, plan.c, &precomp);
+        if (rc) return rc;
+    }
+    if (!precomp) plan = plan_for(ctx, n, false);
+    const G1Affine* pts = precomp ? ctx->precomp[row].table.as<G1Affine>() : row_ptr(ctx, row);
+    int rc = msm_run(ctx, plan, d_scalars, fmt, pts);
     if (rc) return rc;
     return finish_point(plan, ctx, out48);
 }
@@ -108,6 +163,9 @@ void zkp_ctx_destroy(zkp_ctx* ctx) {
         DeviceGuard g(ctx->device);
         cudaStreamSynchronize(ctx->stream);
         ctx->ws.release();
+        drop_precomp(ctx, -1);
+        ctx->scratch_xyzz.release();
+        ctx->scratch_fq.release();
         for (DevBuf* b : {&ctx->srs, &ctx->scalars, &ctx->fr_a, &ctx->fr_b, &ctx->fr_c, &ctx->flush, &ctx->small, &ctx->partials,
                           &ctx->ntt_tmp, &ctx->fixed_base})
             b->release();
@@ -126,9 +184,17 @@ int zkp_set_msm_window(zkp_ctx* ctx, uint32_t c) {
     return ZKP_OK;
 }
 
+int zkp_set_msm_mode(zkp_ctx* ctx, int fixed_base_tables) {
+    if (!ctx) return fail(ZKP_ERR_ARG, "null context");
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    ctx->use_precomp = fixed_base_tables != 0;
+    return ZKP_OK;
+}
+
 int zkp_msm_info(zkp_ctx* ctx, size_t n, uint32_t* c, uint32_t* windows, uint64_t* fq_muls) {
     if (!ctx || !n) return fail(ZKP_ERR_ARG, "bad argument");
-    MsmPlan plan = msm_make_plan((uint32_t)n, ctx->sm_count, ctx->c_override);
+    bool pre = ctx->use_precomp && n >= 256;
+    MsmPlan plan = plan_for(ctx, n, pre);
     if (c) *c = plan.c;
     if (windows) *windows = plan.W;
     if (fq_muls) *fq_muls = msm_fq_muls(plan);
@@ -145,6 +211,8 @@ int zkp_srs_set_shape(zkp_ctx* ctx, uint32_t log_n, uint32_t log_machines) {
     ctx->log_n = log_n;
     ctx->log_m = log_machines;
     ctx->shard_domain_log = log_n;
+    drop_precomp(ctx, -1);
+    ctx->precomp.clear();
     ctx->row_loaded.assign((size_t)1 << log_machines, 0);
     ctx->scale_points.assign((size_t)1 << log_machines, host::G1J::infinity());
     ctx->shaped = true;
@@ -182,6 +250,7 @@ int zkp_srs_import_row(zkp_ctx* ctx, uint32_t row, const uint8_t* points96, size
     ZKP_CUDA(cudaMemcpyAsync(&bad, ctx->fr_b.p, 4, cudaMemcpyDeviceToHost, ctx->stream));
     ZKP_CUDA(cudaStreamSynchronize(ctx->stream));
     if (bad) return fail(ZKP_ERR_ENCODING, "SRS row holds a malformed or off-curve point");
+    drop_precomp(ctx, (int)row);
     ctx->row_loaded[row] = 1;
     return ZKP_OK;
 }

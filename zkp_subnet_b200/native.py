@@ -65,6 +65,7 @@ _SIGNATURES = {
                               ctypes.POINTER(ctypes.c_uint32), _u8p, _u8p, _u8p],
     "zkp_bench_ntt": [_ctxp, ctypes.c_size_t, ctypes.c_int, ctypes.c_int, ctypes.POINTER(ctypes.c_float)],
     "zkp_bench_peaks": [_ctxp, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_double)],
+    "zkp_set_msm_mode": [_ctxp, ctypes.c_int],
     "zkp_set_msm_window": [_ctxp, ctypes.c_uint32],
     "zkp_msm_info": [_ctxp, ctypes.c_size_t, ctypes.POINTER(ctypes.c_uint32), ctypes.POINTER(ctypes.c_uint32),
                      ctypes.POINTER(ctypes.c_uint64)],
@@ -210,6 +211,9 @@ class Context:
     # ---- bench / tuning
     def set_msm_window(self, c: int) -> None:
         check(lib().zkp_set_msm_window(self._h, c))
+
+    def set_msm_mode(self, fixed_base_tables: bool) -> None:
+        check(lib().zkp_set_msm_mode(self._h, int(fixed_base_tables)))
 
     def msm_info(self, n: int) -> Tuple[int, int, int]:
         c, w, m = ctypes.c_uint32(), ctypes.c_uint32(), ctypes.c_uint64()
