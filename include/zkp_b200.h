@@ -108,6 +108,7 @@ int zkp_bench_msm(zkp_ctx* ctx, uint32_t row, const uint8_t* scalars_be, size_t 
 int zkp_bench_commit_open(zkp_ctx* ctx, uint32_t row, const uint8_t* poly_be, size_t n, const uint8_t x_be[32],
                           int reps, int flush_l2, float* ms_per_iter, float* ms_msm_kernel, uint32_t* launches,
                           uint8_t commitment48[48], uint8_t eval_be[32], uint8_t proof48[48]);
+int zkp_bench_last_kernel_ms(zkp_ctx* ctx, float* ms);
 int zkp_bench_ntt(zkp_ctx* ctx, size_t n, int reps, int inverse, float* ms_per_ntt);
 /* roofline denominators measured live: chip-wide IMAD.WIDE.U32 issue rate and dependent-chain Fq products/s */
 int zkp_bench_peaks(zkp_ctx* ctx, double* imad_wide_per_s, double* fq_mul_per_s);

@@ -61,12 +61,11 @@ int ensure_small(zkp_ctx* ctx) {
 template <class T> T* small_at(zkp_ctx* ctx, size_t off) { return reinterpret_cast<T*>(ctx->small.as<uint8_t>() + off); }
 
 // ---- opening on device: f (Montgomery, n elements) -> y (device, SM_Y) and q (Montgomery, fr_c)
-int open_device(zkp_ctx* ctx, const Fr* d_f, uint32_t n, const Fr64& x) {
+int open_device(zkp_ctx* ctx, cudaStream_t st, const Fr* d_f, uint32_t n, const Fr64& x) {
     uint32_t log_n = ilog2(n);
     zkp_ctx::Domain* dom;
     int rc = get_domain(ctx, log_n, false, &dom);
     if (rc) return rc;
-    cudaStream_t st = ctx->stream;
     ZKP_CUDA(ctx->fr_b.ensure((size_t)n * 32));
     ZKP_CUDA(ctx->fr_c.ensure((size_t)n * 32));
     uint32_t E = n >> 14;
@@ -105,16 +104,24 @@ int upload_poly(zkp_ctx* ctx, const uint8_t* poly_be, size_t n) {
     return ZKP_OK;
 }
 
-// read back y (big-endian) and the bad-encoding flag; synchronises
-int fetch_y(zkp_ctx* ctx, uint8_t eval_be[32]) {
-    k_fr_to_be<<<1, 32, 0, ctx->stream>>>(small_at<Fr>(ctx, SM_Y), 1, small_at<uint32_t>(ctx, SM_EVAL));
+// read back y (big-endian) and the bad-encoding flag
+int fetch_y_enqueue(zkp_ctx* ctx, cudaStream_t st) {
+    k_fr_to_be<<<1, 32, 0, st>>>(small_at<Fr>(ctx, SM_Y), 1, small_at<uint32_t>(ctx, SM_EVAL));
     ctx->launches++;
-    ZKP_CUDA(cudaMemcpyAsync(ctx->h_small, small_at<uint8_t>(ctx, SM_EVAL), 32, cudaMemcpyDeviceToHost, ctx->stream));
-    ZKP_CUDA(cudaMemcpyAsync(ctx->h_small + 64, small_at<uint8_t>(ctx, SM_BAD), 4, cudaMemcpyDeviceToHost, ctx->stream));
-    ZKP_CUDA(cudaStreamSynchronize(ctx->stream));
+    ZKP_CUDA(cudaMemcpyAsync(ctx->h_small, small_at<uint8_t>(ctx, SM_EVAL), 32, cudaMemcpyDeviceToHost, st));
+    ZKP_CUDA(cudaMemcpyAsync(ctx->h_small + 64, small_at<uint8_t>(ctx, SM_BAD), 4, cudaMemcpyDeviceToHost, st));
+    return ZKP_OK;
+}
+int fetch_y_finish(zkp_ctx* ctx, uint8_t eval_be[32]) {  // the stream has been synchronised by the caller
     if (*reinterpret_cast<uint32_t*>(ctx->h_small + 64)) return fail(ZKP_ERR_ENCODING, "polynomial holds a non-canonical field element");
     memcpy(eval_be, ctx->h_small, 32);
     return ZKP_OK;
+}
+int fetch_y(zkp_ctx* ctx, uint8_t eval_be[32]) {
+    int rc = fetch_y_enqueue(ctx, ctx->stream);
+    if (rc) return rc;
+    ZKP_CUDA(cudaStreamSynchronize(ctx->stream));
+    return fetch_y_finish(ctx, eval_be);
 }
 
 int open_checks(zkp_ctx* ctx, uint32_t i, const void* poly, size_t n, const uint8_t* x_be, Fr64* x) {
@@ -128,19 +135,33 @@ int open_checks(zkp_ctx* ctx, uint32_t i, const void* poly, size_t n, const uint
     return ZKP_OK;
 }
 
-// the full device part of commit (optional) + open with the polynomial already resident
+// The full device part of commit (optional) + open with the polynomial already resident (raw bytes in
+// ctx->scalars, Montgomery form in fr_a, both produced on lane 0).  The commitment MSM runs on lane 0, the
+// opening (field kernels + its MSM) on lane 1; the host folds the commitment while lane 1 is still busy.
 int commit_open_resident(zkp_ctx* ctx, uint32_t i, size_t n, const Fr64& x, uint8_t* commitment48, uint8_t eval_be[32],
                          uint8_t proof48[48]) {
     int rc;
+    MsmPlan plan_c, plan_o;
+    cudaStream_t s0 = ctx->stream, s1 = ctx->stream2;
+    ZKP_CUDA(cudaEventRecord(ctx->ev_ready, s0));
+    ZKP_CUDA(cudaStreamWaitEvent(s1, ctx->ev_ready, 0));
     if (commitment48) {
-        rc = msm_device(ctx, i, ctx->scalars.as<uint32_t>(), SCALAR_BE, n, commitment48);
+        rc = msm_device_enqueue(ctx, 0, i, ctx->scalars.as<uint32_t>(), SCALAR_BE, n, &plan_c);
         if (rc) return rc;
     }
-    rc = open_device(ctx, ctx->fr_a.as<Fr>(), (uint32_t)n, x);
+    rc = open_device(ctx, s1, ctx->fr_a.as<Fr>(), (uint32_t)n, x);
     if (rc) return rc;
-    rc = msm_device(ctx, i, ctx->fr_c.as<uint32_t>(), SCALAR_MONT, n, proof48);
+    rc = msm_device_enqueue(ctx, 1, i, ctx->fr_c.as<uint32_t>(), SCALAR_MONT, n, &plan_o);
     if (rc) return rc;
-    return fetch_y(ctx, eval_be);
+    rc = fetch_y_enqueue(ctx, s1);
+    if (rc) return rc;
+    if (commitment48) {
+        rc = msm_device_finish(ctx, 0, plan_c, commitment48);
+        if (rc) { cudaStreamSynchronize(s1); return rc; }
+    }
+    rc = msm_device_finish(ctx, 1, plan_o, proof48);
+    if (rc) return rc;
+    return fetch_y_finish(ctx, eval_be);
 }
 
 void flush_l2(zkp_ctx* ctx) {
@@ -571,6 +592,9 @@ int zkp_bench_msm(zkp_ctx* ctx, uint32_t row, const uint8_t* scalars_be, size_t 
     ZKP_CUDA(cudaEventCreate(&e0));
     ZKP_CUDA(cudaEventCreate(&e1));
     double total = 0;
+    ctx->time_acc = true;
+    ctx->acc_ms_total = 0;
+    ctx->acc_count = 0;
     for (int r = 0; r < reps && !rc; r++) {
         if (do_flush) flush_l2(ctx);
         cudaEventRecord(e0, ctx->stream);
@@ -583,6 +607,8 @@ int zkp_bench_msm(zkp_ctx* ctx, uint32_t row, const uint8_t* scalars_be, size_t 
     }
     cudaEventDestroy(e0);
     cudaEventDestroy(e1);
+    ctx->time_acc = false;
+    ctx->last_acc_ms = ctx->acc_count ? (float)(ctx->acc_ms_total / ctx->acc_count) : 0.f;
     *ms_per_msm = (float)(total / reps);
     return rc;
 }
@@ -660,6 +686,14 @@ int zkp_bench_peaks(zkp_ctx* ctx, double* imad_wide_per_s, double* fq_mul_per_s)
     ctx->launches += 8;
     *imad_wide_per_s = (double)threads * blocks * 4.0 * PEAK_ITERS / (best_w * 1e-3);
     *fq_mul_per_s = (double)threads * (blocks / 2) * fq_iters / (best_f * 1e-3);
+    return ZKP_OK;
+}
+
+// mean duration of the dominant kernel (level-0 bucket accumulation) over the last zkp_bench_msm call,
+// i.e. measured with nothing else running on the device
+int zkp_bench_last_kernel_ms(zkp_ctx* ctx, float* ms) {
+    if (!ctx || !ms) return fail(ZKP_ERR_ARG, "null argument");
+    *ms = ctx->last_acc_ms;
     return ZKP_OK;
 }
 

@@ -84,7 +84,13 @@ struct zkp_ctx {
     zkp::host::G2J g2_tau;                    // [tau_x]_2
     // scratch
     zkp::DevBuf scalars, fr_a, fr_b, fr_c, flush;
-    zkp::MsmWorkspace ws;
+    zkp::MsmWorkspace ws;                     // lane 0 workspace (runs on `stream`)
+    // lane 1: second stream + workspace so that the two MSMs of a commit+open (and their
+    // latency-bound reduction tails) overlap on the device
+    cudaStream_t stream2 = nullptr;
+    zkp::MsmWorkspace ws2;
+    cudaEvent_t ev_ready = nullptr;           // polynomial uploaded + converted (lane 0 -> lane 1)
+    cudaEvent_t ev_acc2_0 = nullptr, ev_acc2_1 = nullptr;
     uint32_t c_override = 0;
     // fixed-base tables: per SRS row, [2^(c w)] P_i for w < W (slice w at w * 2^log_n); built lazily
     struct Precomp { zkp::DevBuf table; uint32_t c = 0, W = 0; };
@@ -110,4 +116,5 @@ struct zkp_ctx {
     cudaEvent_t ev_acc0 = nullptr, ev_acc1 = nullptr;
     double acc_ms_total = 0;
     uint64_t acc_count = 0;
+    float last_acc_ms = 0;
 };

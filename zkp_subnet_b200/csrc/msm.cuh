@@ -90,7 +90,9 @@ inline MsmPlan msm_make_plan(uint32_t n, int sm_count, uint32_t c, bool precomp,
     p.N = (size_t)n * p.W;
     // level 0: slice length chosen so that the grid is a whole number of waves of resident threads
     const size_t resident = (size_t)sm_count * 384;
-    size_t waves = (p.N + resident * 32 - 1) / (resident * 32);
+    // ~6 waves: long slices mean few slice-boundary partials for the slot levels, and because every
+    // thread does the same work the last wave is as full as the first
+    size_t waves = (p.N + resident * 48 - 1) / (resident * 48);
     if (waves < 1) waves = 1;
     uint32_t L0 = (uint32_t)((p.N + waves * resident - 1) / (waves * resident));
     if (L0 < 8) L0 = 8;
@@ -102,7 +104,7 @@ inline MsmPlan msm_make_plan(uint32_t n, int sm_count, uint32_t c, bool precomp,
         p.levels.push_back({items, L, threads});
         if (threads <= 1) break;
         items = threads * 2;
-        L = lvl == 0 ? 16 : 8;  // shallow slot levels: every sequential addition costs ~17 us of latency
+        L = 8;  // shallow slot levels: every sequential addition costs ~17 us of latency
     }
     // reduction plan
     if (p.B > REDUCE_DIRECT_MAX) {
@@ -300,59 +302,64 @@ k_accumulate(const uint32_t* __restrict__ keys, const uint32_t* __restrict__ val
 // 4. bucket reduction
 // ------------------------------------------------------------------------------------------------
 constexpr int RC_THREADS = 128;
-__device__ __forceinline__ void block_tree_sum(G1Xyzz* sh, G1Xyzz acc, G1Xyzz* out) {
-    sh[threadIdx.x] = acc;
-    __syncthreads();
-    for (int s = RC_THREADS / 2; s > 0; s >>= 1) {
-        if ((int)threadIdx.x < s) {
-            G1Xyzz a = sh[threadIdx.x];
-            a.add(sh[threadIdx.x + s]);
-            sh[threadIdx.x] = a;
-        }
-        __syncthreads();
-    }
-    if (threadIdx.x == 0) store_xyzz(out, sh[0]);
-}
+constexpr int RC_LANES = 32;                       // threads cooperating on one sum
+constexpr int RC_SUMS = RC_THREADS / RC_LANES;     // sums per block
 // Bucket array of one window viewed as 2^log_rows x 2^log_cols (bucket b = hi * cols + lo).
-// Blocks [0, cols) of grid.x form the column sums C_lo = sum_hi X[hi][lo] (strided reads), blocks
-// [cols, cols + rows) the row sums R_hi = sum_lo X[hi][lo] (contiguous reads).  grid.y = bucket window.
+// Sum s < cols is the column sum C_s = sum_hi X[hi][s] (strided reads), sum s >= cols the row sum
+// R_(s-cols) = sum_lo X[s-cols][lo] (contiguous reads).  One warp per sum: every lane adds a strided
+// share sequentially (all lanes busy), then 5 shared-memory tree steps.  grid.y = bucket window.
 __global__ void __launch_bounds__(RC_THREADS)
 k_rowcol_sums(const G1Xyzz* __restrict__ in, uint32_t log_rows, uint32_t log_cols, G1Xyzz* __restrict__ out_c,
               G1Xyzz* __restrict__ out_r) {
     __shared__ G1Xyzz sh[RC_THREADS];
     const uint32_t rows = 1u << log_rows, cols = 1u << log_cols, w = blockIdx.y;
+    const uint32_t lane = threadIdx.x % RC_LANES;
+    const uint32_t s = blockIdx.x * RC_SUMS + threadIdx.x / RC_LANES;
     const G1Xyzz* x = in + ((size_t)w << (log_rows + log_cols));
     G1Xyzz acc = G1Xyzz::infinity();
-    if (blockIdx.x < cols) {
-        uint32_t lo = blockIdx.x;
-        for (uint32_t hi = threadIdx.x; hi < rows; hi += RC_THREADS) {
+    if (s < cols) {
+        for (uint32_t hi = lane; hi < rows; hi += RC_LANES) {
+            G1Xyzz p = load_xyzz(x + ((size_t)hi << log_cols) + s);
+            acc.add(p);
+        }
+    } else if (s < cols + rows) {
+        const uint32_t hi = s - cols;
+        for (uint32_t lo = lane; lo < cols; lo += RC_LANES) {
             G1Xyzz p = load_xyzz(x + ((size_t)hi << log_cols) + lo);
             acc.add(p);
         }
-        block_tree_sum(sh, acc, out_c + (size_t)w * cols + lo);
-    } else {
-        uint32_t hi = blockIdx.x - cols;
-        for (uint32_t lo = threadIdx.x; lo < cols; lo += RC_THREADS) {
-            G1Xyzz p = load_xyzz(x + ((size_t)hi << log_cols) + lo);
-            acc.add(p);
-        }
-        block_tree_sum(sh, acc, out_r + (size_t)w * rows + hi);
     }
+    sh[threadIdx.x] = acc;
+    __syncthreads();
+    for (int st = RC_LANES / 2; st > 0; st >>= 1) {
+        if ((int)lane < st) {
+            G1Xyzz a = sh[threadIdx.x];
+            a.add(sh[threadIdx.x + st]);
+            sh[threadIdx.x] = a;
+        }
+        __syncthreads();
+    }
+    if (lane == 0 && s < cols + rows)
+        store_xyzz(s < cols ? out_c + (size_t)w * cols + s : out_r + (size_t)w * rows + (s - cols), sh[threadIdx.x]);
 }
 
-// Tail of the reduction: block (j, w) computes P[w][j] = sum of in[w][k] over the k whose weight
-// (k + one_based) has bit j set; n_in <= REDUCE_TAIL_MAX.  The host finishes with a Horner pass
-// over the bits (sum_j 2^j P_j).
+// Bit planes: block (j, w) computes P[w][j] = sum of the inputs whose weight has bit j set.  Planes
+// j < bits_a come from array a (n_a inputs per window, weight k + 1), planes j >= bits_a from array b
+// (n_b inputs per window, weight k).  The host finishes with Horner passes (sum_j 2^j P_j).
 constexpr int TAIL_THREADS = 128;
 __global__ void __launch_bounds__(TAIL_THREADS)
-k_bit_sums(const G1Xyzz* __restrict__ in, uint32_t n_in, uint32_t in_stride, int one_based, G1Xyzz* __restrict__ out,
-           uint32_t out_stride, uint32_t out_off) {
+k_bit_sums(const G1Xyzz* __restrict__ a, uint32_t n_a, uint32_t bits_a, const G1Xyzz* __restrict__ b, uint32_t n_b,
+           G1Xyzz* __restrict__ out, uint32_t out_stride) {
     __shared__ G1Xyzz sh[TAIL_THREADS];
-    uint32_t j = blockIdx.x, w = blockIdx.y;
+    const uint32_t w = blockIdx.y;
+    const bool first = blockIdx.x < bits_a;
+    const uint32_t j = first ? blockIdx.x : blockIdx.x - bits_a;
+    const uint32_t n_in = first ? n_a : n_b, one = first ? 1u : 0u;
+    const G1Xyzz* in = (first ? a : b) + (size_t)w * n_in;
     G1Xyzz acc = G1Xyzz::infinity();
     for (uint32_t k = threadIdx.x; k < n_in; k += TAIL_THREADS) {
-        if (((k + (one_based ? 1u : 0u)) >> j) & 1) {
-            G1Xyzz p = load_xyzz(in + (size_t)w * in_stride + k);
+        if (((k + one) >> j) & 1) {
+            G1Xyzz p = load_xyzz(in + k);
             acc.add(p);
         }
     }
@@ -360,13 +367,13 @@ k_bit_sums(const G1Xyzz* __restrict__ in, uint32_t n_in, uint32_t in_stride, int
     __syncthreads();
     for (int s = TAIL_THREADS / 2; s > 0; s >>= 1) {
         if ((int)threadIdx.x < s) {
-            G1Xyzz a = sh[threadIdx.x];
-            a.add(sh[threadIdx.x + s]);
-            sh[threadIdx.x] = a;
+            G1Xyzz t = sh[threadIdx.x];
+            t.add(sh[threadIdx.x + s]);
+            sh[threadIdx.x] = t;
         }
         __syncthreads();
     }
-    if (threadIdx.x == 0) store_xyzz(out + (size_t)w * out_stride + out_off + j, sh[0]);
+    if (threadIdx.x == 0) store_xyzz(out + (size_t)w * out_stride + blockIdx.x, sh[0]);
 }
 
 }  // namespace zkp

@@ -13,9 +13,11 @@ inline uint64_t msm_fq_muls(const MsmPlan& p) {
 // Launches the whole device pipeline on ctx->stream and copies the bit-plane sums to pinned host
 // memory; synchronises the stream before returning.  d_points: the SRS row (classic) or the fixed-base
 // table of the row (plan.precomp).
-inline int msm_run(zkp_ctx* ctx, const MsmPlan& plan, const uint32_t* d_scalars, int fmt, const G1Affine* d_points) {
-    MsmWorkspace& ws = ctx->ws;
-    cudaStream_t st = ctx->stream;
+inline int msm_enqueue(zkp_ctx* ctx, int lane, const MsmPlan& plan, const uint32_t* d_scalars, int fmt,
+                       const G1Affine* d_points) {
+    MsmWorkspace& ws = lane ? ctx->ws2 : ctx->ws;
+    cudaStream_t st = lane ? ctx->stream2 : ctx->stream;
+    cudaEvent_t ev0 = lane ? ctx->ev_acc2_0 : ctx->ev_acc0, ev1 = lane ? ctx->ev_acc2_1 : ctx->ev_acc1;
     const size_t N = plan.N;
     ZKP_CUDA(ws.keys_a.ensure(N * 4));
     ZKP_CUDA(ws.keys_b.ensure(N * 4));
@@ -62,12 +64,12 @@ inline int msm_run(zkp_ctx* ctx, const MsmPlan& plan, const uint32_t* d_scalars,
         int last = l + 1 == plan.levels.size();
         unsigned blocks = (unsigned)((lv.threads + 127) / 128);
         if (l == 0) {
-            if (ctx->time_acc) cudaEventRecord(ctx->ev_acc0, st);
+            if (ctx->time_acc) cudaEventRecord(ev0, st);
             k_accumulate<true><<<blocks, 128, 0, st>>>(ws.keys_b.as<uint32_t>(), ws.vals_b.as<uint32_t>(), d_points, nullptr,
                                                        lv.items, lv.L, plan.discard, ws.buckets.as<G1Xyzz>(),
                                                        last ? nullptr : ws.slot_keys[0].as<uint32_t>(),
                                                        last ? nullptr : ws.slot_pts[0].as<G1Xyzz>(), last);
-            if (ctx->time_acc) cudaEventRecord(ctx->ev_acc1, st);
+            if (ctx->time_acc) cudaEventRecord(ev1, st);
         } else {
             k_accumulate<false><<<blocks, 128, 0, st>>>(ws.slot_keys[l - 1].as<uint32_t>(), nullptr, nullptr,
                                                         ws.slot_pts[l - 1].as<G1Xyzz>(), lv.items, lv.L, plan.discard,
@@ -85,23 +87,31 @@ inline int msm_run(zkp_ctx* ctx, const MsmPlan& plan, const uint32_t* d_scalars,
         const uint32_t rows = 1u << plan.log_rows, cols = 1u << plan.log_cols;
         ZKP_CUDA(ws.sums_a.ensure((size_t)plan.Wb * cols * sizeof(G1Xyzz)));
         ZKP_CUDA(ws.sums_b.ensure((size_t)plan.Wb * rows * sizeof(G1Xyzz)));
-        k_rowcol_sums<<<dim3(cols + rows, plan.Wb), RC_THREADS, 0, st>>>(ws.buckets.as<G1Xyzz>(), plan.log_rows, plan.log_cols,
-                                                                          ws.sums_a.as<G1Xyzz>(), ws.sums_b.as<G1Xyzz>());
-        k_bit_sums<<<dim3(plan.bits_c, plan.Wb), TAIL_THREADS, 0, st>>>(ws.sums_a.as<G1Xyzz>(), cols, cols, 1, d_out, opw, 0);
-        k_bit_sums<<<dim3(plan.bits_r, plan.Wb), TAIL_THREADS, 0, st>>>(ws.sums_b.as<G1Xyzz>(), rows, rows, 0, d_out, opw,
-                                                                        plan.bits_c);
-        ctx->launches += 3;
+        k_rowcol_sums<<<dim3((cols + rows + RC_SUMS - 1) / RC_SUMS, plan.Wb), RC_THREADS, 0, st>>>(
+            ws.buckets.as<G1Xyzz>(), plan.log_rows, plan.log_cols, ws.sums_a.as<G1Xyzz>(), ws.sums_b.as<G1Xyzz>());
+        k_bit_sums<<<dim3(plan.bits_c + plan.bits_r, plan.Wb), TAIL_THREADS, 0, st>>>(
+            ws.sums_a.as<G1Xyzz>(), cols, plan.bits_c, ws.sums_b.as<G1Xyzz>(), rows, d_out, opw);
+        ctx->launches += 2;
     } else {
-        k_bit_sums<<<dim3(plan.bits_c, plan.Wb), TAIL_THREADS, 0, st>>>(ws.buckets.as<G1Xyzz>(), plan.B, plan.B, 1, d_out, opw, 0);
+        k_bit_sums<<<dim3(plan.bits_c, plan.Wb), TAIL_THREADS, 0, st>>>(ws.buckets.as<G1Xyzz>(), plan.B, plan.bits_c, nullptr, 0,
+                                                                        d_out, opw);
         ctx->launches++;
     }
     ZKP_CUDA(cudaMemcpyAsync(ws.h_window, d_out, sizeof(G1Xyzz) * out_records, cudaMemcpyDeviceToHost, st));
     ZKP_CUDA(cudaMemcpyAsync(ws.h_bad, ws.bad.p, 4, cudaMemcpyDeviceToHost, st));
+    return ZKP_OK;
+}
+
+// waits for the lane's pipeline; afterwards ws.h_window holds the bit-plane sums
+inline int msm_wait(zkp_ctx* ctx, int lane) {
+    MsmWorkspace& ws = lane ? ctx->ws2 : ctx->ws;
+    cudaStream_t st = lane ? ctx->stream2 : ctx->stream;
+    cudaEvent_t ev0 = lane ? ctx->ev_acc2_0 : ctx->ev_acc0, ev1 = lane ? ctx->ev_acc2_1 : ctx->ev_acc1;
     ZKP_CUDA(cudaStreamSynchronize(st));
     ZKP_CUDA(cudaGetLastError());
     if (ctx->time_acc) {
         float ms = 0;
-        if (cudaEventElapsedTime(&ms, ctx->ev_acc0, ctx->ev_acc1) == cudaSuccess) {
+        if (cudaEventElapsedTime(&ms, ev0, ev1) == cudaSuccess) {
             ctx->acc_ms_total += ms;
             ctx->acc_count++;
         }

@@ -54,8 +54,8 @@ int upload_scalars(zkp_ctx* ctx, const uint8_t* be, size_t n, DevBuf& dst) {
     return ZKP_OK;
 }
 
-int finish_point(const MsmPlan& plan, zkp_ctx* ctx, uint8_t out48[48]) {
-    host::G1J r = msm_fold(plan, ctx->ws.h_window);
+int finish_point(const MsmPlan& plan, zkp_ctx* ctx, int lane, uint8_t out48[48]) {
+    host::G1J r = msm_fold(plan, (lane ? ctx->ws2 : ctx->ws).h_window);
     host::g1_compress(out48, r);
     return ZKP_OK;
 }
@@ -107,8 +107,8 @@ MsmPlan plan_for(zkp_ctx* ctx, size_t n, bool precomp) {
     return msm_make_plan((uint32_t)n, ctx->sm_count, c, precomp, 1u << ctx->log_n);
 }
 
-// MSM over row `row` with device-resident scalars
-int msm_device(zkp_ctx* ctx, uint32_t row, const uint32_t* d_scalars, int fmt, size_t n, uint8_t out48[48]) {
+// Enqueue an MSM over row `row` with device-resident scalars on a lane (no host sync).
+int msm_device_enqueue(zkp_ctx* ctx, int lane, uint32_t row, const uint32_t* d_scalars, int fmt, size_t n, MsmPlan* plan_out) {
     bool precomp = false;
     MsmPlan plan;
     if (ctx->use_precomp && n >= 256) {
@@ -118,9 +118,20 @@ int msm_device(zkp_ctx* ctx, uint32_t row, const uint32_t* d_scalars, int fmt, s
     }
     if (!precomp) plan = plan_for(ctx, n, false);
     const G1Affine* pts = precomp ? ctx->precomp[row].table.as<G1Affine>() : row_ptr(ctx, row);
-    int rc = msm_run(ctx, plan, d_scalars, fmt, pts);
+    *plan_out = plan;
+    return msm_enqueue(ctx, lane, plan, d_scalars, fmt, pts);
+}
+int msm_device_finish(zkp_ctx* ctx, int lane, const MsmPlan& plan, uint8_t out48[48]) {
+    int rc = msm_wait(ctx, lane);
     if (rc) return rc;
-    return finish_point(plan, ctx, out48);
+    return finish_point(plan, ctx, lane, out48);
+}
+// MSM over row `row` with device-resident scalars (lane 0, synchronous)
+int msm_device(zkp_ctx* ctx, uint32_t row, const uint32_t* d_scalars, int fmt, size_t n, uint8_t out48[48]) {
+    MsmPlan plan;
+    int rc = msm_device_enqueue(ctx, 0, row, d_scalars, fmt, n, &plan);
+    if (rc) return rc;
+    return msm_device_finish(ctx, 0, plan, out48);
 }
 
 }  // namespace
@@ -152,6 +163,10 @@ int zkp_ctx_create(int device, zkp_ctx** out) {
     ZKP_CUDA(cudaMallocHost(&ctx->h_small, 4096));
     ZKP_CUDA(cudaEventCreate(&ctx->ev_acc0));
     ZKP_CUDA(cudaEventCreate(&ctx->ev_acc1));
+    ZKP_CUDA(cudaStreamCreateWithFlags(&ctx->stream2, cudaStreamNonBlocking));
+    ZKP_CUDA(cudaEventCreate(&ctx->ev_acc2_0));
+    ZKP_CUDA(cudaEventCreate(&ctx->ev_acc2_1));
+    ZKP_CUDA(cudaEventCreateWithFlags(&ctx->ev_ready, cudaEventDisableTiming));
     ZKP_CUDA(cudaFuncSetAttribute(k_ntt_pass, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * 16 * (1 << NTT_MAX_TILE_LOG)));
     *out = ctx.release();
     return ZKP_OK;
@@ -162,7 +177,13 @@ void zkp_ctx_destroy(zkp_ctx* ctx) {
     {
         DeviceGuard g(ctx->device);
         cudaStreamSynchronize(ctx->stream);
+        cudaStreamSynchronize(ctx->stream2);
         ctx->ws.release();
+        ctx->ws2.release();
+        cudaEventDestroy(ctx->ev_acc2_0);
+        cudaEventDestroy(ctx->ev_acc2_1);
+        cudaEventDestroy(ctx->ev_ready);
+        cudaStreamDestroy(ctx->stream2);
         drop_precomp(ctx, -1);
         ctx->scratch_xyzz.release();
         ctx->scratch_fq.release();

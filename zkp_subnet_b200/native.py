@@ -64,6 +64,7 @@ _SIGNATURES = {
                               ctypes.POINTER(ctypes.c_float), ctypes.POINTER(ctypes.c_float),
                               ctypes.POINTER(ctypes.c_uint32), _u8p, _u8p, _u8p],
     "zkp_bench_ntt": [_ctxp, ctypes.c_size_t, ctypes.c_int, ctypes.c_int, ctypes.POINTER(ctypes.c_float)],
+    "zkp_bench_last_kernel_ms": [_ctxp, ctypes.POINTER(ctypes.c_float)],
     "zkp_bench_peaks": [_ctxp, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_double)],
     "zkp_set_msm_mode": [_ctxp, ctypes.c_int],
     "zkp_set_msm_window": [_ctxp, ctypes.c_uint32],
@@ -234,6 +235,11 @@ class Context:
         check(lib().zkp_bench_commit_open(self._h, row, poly_be, len(poly_be) // 32, x_be, reps, int(flush_l2),
                                           ctypes.byref(ms), ctypes.byref(ms_k), ctypes.byref(launches), com, y, proof))
         return ms.value, ms_k.value, launches.value, com.raw, y.raw, proof.raw
+
+    def bench_last_kernel_ms(self) -> float:
+        ms = ctypes.c_float()
+        check(lib().zkp_bench_last_kernel_ms(self._h, ctypes.byref(ms)))
+        return ms.value
 
     def bench_peaks(self) -> Tuple[float, float]:
         a, b = ctypes.c_double(), ctypes.c_double()
