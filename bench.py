@@ -208,21 +208,19 @@ def main():
     agg = None
     if dist is not None:
         import torch
-        mine = torch.tensor(list(com + proof), dtype=torch.uint8, device=f"cuda:{local}")
-        gathered = [torch.empty_like(mine) for _ in range(world)]
-        dist.all_gather(gathered, mine)
+        from zkp_subnet_b200 import sharding
+        dev = f"cuda:{local}"
+        sharding.gather_bytes(dist, com + proof, dev)  # warm-up (NCCL communicator setup)
         torch.cuda.synchronize()
         t0 = time.perf_counter()
         reps = 20
         for _ in range(reps):
-            dist.all_gather(gathered, mine)
-            torch.cuda.synchronize()
+            parts = sharding.gather_bytes(dist, com + proof, dev)
             if rank == 0:
-                allb = [bytes(g.cpu().tolist()) for g in gathered]
-                agg = (native.g1_sum(b"".join(b[:48] for b in allb)), native.g1_sum(b"".join(b[48:] for b in allb)))
+                agg = sharding.combine_partials(parts)  # aggregated commitment and proof (Pianist)
         combine_ms = (time.perf_counter() - t0) * 1e3 / reps
         t = torch.tensor([t_rank + combine_ms * args.steps, e2e_rank + combine_ms * args.steps, ms_kernel],
-                         dtype=torch.float64, device=f"cuda:{local}")
+                         dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         t_job, e2e_job, ms_kernel_max = t.tolist()
     else:
