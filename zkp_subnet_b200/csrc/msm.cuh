@@ -282,6 +282,13 @@ k_accumulate(const uint32_t* __restrict__ keys, const uint32_t* __restrict__ val
         last_key = k;
         if (LEVEL0) {
             uint32_t v = vals[i];
+            if (i + 1 < end) {
+                // the gather is a 96-byte random read of a table far larger than L2: pull the NEXT point
+                // towards L2 while this one is being added (no registers held, unlike a software pipeline)
+                const char* nx = reinterpret_cast<const char*>(points + (vals[i + 1] & 0x7fffffffu));
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(nx));
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(nx + 64));
+            }
             G1Affine p = load_affine(points + (v & 0x7fffffffu));
             acc.madd(p, v >> 31);
         } else if (!(raw & KEY_EMPTY_FLAG)) {
