@@ -181,25 +181,49 @@ int ntt_device(zkp_ctx* ctx, const Fr* in, Fr* out, uint32_t log_n, int inverse)
     if (rc) return rc;
     const Fr n_inv = to_dev(dom->n_inv);
     const size_t smem_per_elt = 32;
+    auto sub_table = [&](uint32_t log_m, const Fr** out_tw) -> int {
+        if (log_m == 0) { *out_tw = dom->tw.as<Fr>(); return ZKP_OK; }
+        zkp_ctx::Domain* d;
+        int r = get_domain(ctx, log_m, true, &d);
+        if (r) return r;
+        *out_tw = d->tw.as<Fr>();
+        return ZKP_OK;
+    };
+    auto threads_for = [](uint32_t log_tile) -> unsigned {
+        unsigned t = log_tile > 3 ? 1u << (log_tile - 3) : 1u;
+        if (t < 32) t = 32;
+        if (t > (unsigned)NTT_MAX_THREADS) t = NTT_MAX_THREADS;
+        return t;
+    };
+    // columns per CTA: aim at 1024-element tiles (32 KB: 7-8 CTAs per SM) but keep >= 512 CTAs in flight
+    auto cols_for = [](uint32_t log_m, uint32_t log_ncols) -> uint32_t {
+        uint32_t lc = log_m < 10 ? 10 - log_m : 0;
+        if (lc > log_ncols) lc = log_ncols;
+        while (lc > 0 && log_ncols - lc < 9) lc--;
+        return lc;
+    };
     if (log_n <= NTT_MAX_TILE_LOG) {
         NttPass p = {log_n, 0, 1, 1, 0, 1, 0, 1, log_n, 0, (uint32_t)inverse, (uint32_t)inverse};
-        k_ntt_pass<<<1, NTT_THREADS, smem_per_elt << log_n, ctx->stream>>>(in, out, dom->tw.as<Fr>(), p, n_inv);
+        k_ntt_pass<<<1, threads_for(log_n), smem_per_elt << log_n, ctx->stream>>>(in, out, dom->tw.as<Fr>(), dom->tw.as<Fr>(), p, n_inv);
         ctx->launches++;
         return ZKP_OK;
     }
     uint32_t l1 = log_n / 2, l2 = log_n - l1;
     uint64_t n1 = 1ull << l1, n2 = 1ull << l2;
+    const Fr *tw1, *tw2;
+    rc = sub_table(l1, &tw1);
+    if (rc) return rc;
+    rc = sub_table(l2, &tw2);
+    if (rc) return rc;
     ZKP_CUDA(ctx->ntt_tmp.ensure(32ull << log_n));
     Fr* tmp = ctx->ntt_tmp.as<Fr>();
-    uint32_t lc1 = NTT_MAX_TILE_LOG - l1, lc2 = NTT_MAX_TILE_LOG - l2;
-    if (lc1 > 3) lc1 = 3;  // 8 columns = 256-byte runs; more columns only lengthen the tile
-    if (lc2 > 3) lc2 = 3;
+    uint32_t lc1 = cols_for(l1, l2), lc2 = cols_for(l2, l1);
     // pass 1: columns i2 (n2 of them), rows i1; element (r, c) at r*n2 + c; twiddle w^(c*k)
     NttPass p1 = {l1, lc1, (uint32_t)n2, n2, 1, n2, 1, 0, log_n, 1, (uint32_t)inverse, 0};
-    k_ntt_pass<<<(unsigned)(n2 >> lc1), NTT_THREADS, smem_per_elt << (l1 + lc1), ctx->stream>>>(in, tmp, dom->tw.as<Fr>(), p1, n_inv);
+    k_ntt_pass<<<(unsigned)(n2 >> lc1), threads_for(l1 + lc1), smem_per_elt << (l1 + lc1), ctx->stream>>>(in, tmp, dom->tw.as<Fr>(), tw1, p1, n_inv);
     // pass 2: columns k1 (n1 of them), rows i2; element (r, c) at c*n2 + r; output (k2, c) at k2*n1 + c
     NttPass p2 = {l2, lc2, (uint32_t)n1, 1, n2, n1, 1, 1, log_n, 0, (uint32_t)inverse, (uint32_t)inverse};
-    k_ntt_pass<<<(unsigned)(n1 >> lc2), NTT_THREADS, smem_per_elt << (l2 + lc2), ctx->stream>>>(tmp, out, dom->tw.as<Fr>(), p2, n_inv);
+    k_ntt_pass<<<(unsigned)(n1 >> lc2), threads_for(l2 + lc2), smem_per_elt << (l2 + lc2), ctx->stream>>>(tmp, out, dom->tw.as<Fr>(), tw2, p2, n_inv);
     ctx->launches += 2;
     return ZKP_OK;
 }
