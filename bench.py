@@ -193,15 +193,39 @@ def main():
     clocks = sampler.stop(t_begin, time.perf_counter())
     t_rank = ms_iter * args.steps
 
-    # ---- e2e: the C-ABI call with host buffers (H2D of the polynomial + D2H of the results inside)
+    # ---- e2e: the C-ABI call with host buffers (H2D of the polynomial from page-locked host memory + D2H of the
+    #      results inside the timed region, every step)
+    pinned = native.PinnedBuffer(len(poly)).write(poly)
     for _ in range(2):
-        ctx.worker_commit_open(row, poly, x)
+        ctx.worker_commit_open(row, pinned, x)
     barrier()
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        e_com, e_y, e_proof = ctx.worker_commit_open(row, poly, x)
+        e_com, e_y, e_proof = ctx.worker_commit_open(row, pinned, x)
     e2e_rank = (time.perf_counter() - t0) * 1e3
     assert (e_com, e_y, e_proof) == (com, y, proof), "e2e and device-resident paths disagree"
+    # the same call from ordinary pageable memory (what a caller gets without zkp_host_alloc)
+    t0 = time.perf_counter()
+    for _ in range(3):
+        ctx.worker_commit_open(row, poly, x)
+    e2e_pageable_ms = (time.perf_counter() - t0) * 1e3 / 3
+    # ---- and through the reference-facing shim: fourier.Client.worker_commit_and_open(i, List[str], str) -- base64
+    #      decode of 2^20 strings on the host + the call above + base64 of the results
+    client_ms = None
+    if rank == 0:
+        import base64
+        from zkp_subnet_b200.client import Client, encode_poly
+        cl = Client().attach(ctx, log_n + log_m, log_m)
+        strs = encode_poly(poly)
+        xs = base64.b64encode(x).decode().rstrip("=")
+        cl.worker_commit_and_open(row, strs, xs)
+        t0 = time.perf_counter()
+        for _ in range(3):
+            resp = cl.worker_commit_and_open(row, strs, xs)
+        client_ms = (time.perf_counter() - t0) * 1e3 / 3
+        assert resp.status_code == 200 and base64.b64decode(resp.json()["commitment"]) == com
+        cl.stop()
+        del strs
 
     # ---- cross-GPU combine: gather 2 x 48 bytes per rank, sum on rank 0 (timed separately, added per step)
     combine_ms = 0.0
@@ -238,6 +262,10 @@ def main():
     ms_kernel_alone = ctx.bench_last_kernel_ms()  # the dominant kernel with nothing else on the device
     ms_ntt = ctx.bench_ntt(n, 3, False)
     value = world * args.steps / (t_job * 1e-3)
+    # device -> host per step: the bit-plane partial sums of both MSMs (192-byte XYZZ records, folded by ~40 host
+    # point operations), the evaluation y and two status words
+    planes = c if (1 << (c - 1)) <= 1024 else c  # (log_cols + 1) + log_rows = c records per bucket window
+    d2h_bytes = 2 * (planes * 192 + 4) + 32 + 4
     e2e_value = world * args.steps / (e2e_job * 1e-3)
     # dominant kernel: level-0 bucket accumulation, 10 Fq products per mixed addition, n*W additions
     acc_fq_muls = 10.0 * n * W
@@ -270,8 +298,10 @@ def main():
         "gpu_launches": int(launches) * args.steps,
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": n * 32 + 32,
-                "d2h_bytes_per_step": 48 + 48 + 32 + 2 * W * 192 * 11, "ms_per_step": e2e_job / args.steps,
-                "api": "zkp_worker_commit_open (C ABI, pageable host buffers -> results on host)"},
+                "d2h_bytes_per_step": d2h_bytes, "ms_per_step": e2e_job / args.steps,
+                "api": "zkp_worker_commit_open (C ABI; polynomial in page-locked host memory from zkp_host_alloc -> results on host)",
+                "ms_per_step_pageable_input": e2e_pageable_ms,
+                "ms_per_call_via_fourier_Client_list_of_base64_str": client_ms},
         "roofline": {"bound": "imad", "kernel": "k_accumulate<level0>", "achieved": achieved, "peak": peak,
                      "unit": "G Fq-mul/s", "frac": achieved / peak, "traffic": traffic,
                      "note": "bound is INT32 multiply issue (IMAD.WIDE.U32, fmaheavy pipe), neither HBM nor tensor: "

@@ -46,6 +46,14 @@ void zkp_ctx_destroy(zkp_ctx* ctx);
 const char* zkp_last_error(void);
 int zkp_device_count(void);
 
+/* ---- pinned host staging.  A polynomial crosses the boundary as n x 32 bytes; when those bytes sit in a
+ *      buffer from zkp_host_alloc (page-locked) the host->device copy inside zkp_worker_* runs as one
+ *      asynchronous DMA at PCIe rate instead of being staged through the driver's bounce buffer.  Any
+ *      ordinary (pageable) pointer is accepted too -- the result is identical, only the copy is slower.
+ *      The Python client decodes the base64 `poly` list straight into such a buffer. */
+int zkp_host_alloc(size_t bytes, void** out);
+int zkp_host_free(void* p);
+
 /* ---- SRS: replaces `prover setup --generate-setup --generate-precompute` and the
  *      setup_path / precompute_path files (reference tests/conftest.py:50-65, Makefile:30-48).
  *      Layout: 2^log_machines rows of 2^log_n points, U[i][j] = [R_i(tau_y) L_j(tau_x)]_1

@@ -27,6 +27,35 @@ def test_b64_codec(golden):
         assert native.b64_encode_fr(b).decode() == base64.b64encode(b).decode().rstrip("=")
 
 
+def test_wire_list_codec(golden):
+    """csrc/wire_py.cpp: List[str] <-> bytes through the CPython API, against Python's own base64."""
+    import os
+    import random
+    rng = random.Random(0xB200)
+    vals = [rng.randrange(o.R) for _ in range(20000)] + [0, 1, o.R - 1]
+    raw = b"".join(v.to_bytes(32, "big") for v in vals)
+    strs = native.wire_encode_list(raw)
+    assert isinstance(strs, list) and len(strs) == len(vals)
+    assert strs[:50] == [base64.b64encode(v.to_bytes(32, "big")).decode().rstrip("=") for v in vals[:50]]
+    assert native.wire_decode_list(strs) == raw
+    assert native.wire_decode_list(tuple(strs)) == raw
+    assert native.wire_decode_list([s.encode() for s in strs[:100]]) == raw[:3200]      # bytes items
+    assert native.wire_decode_list([s + "=" for s in strs[:100]]) == raw[:3200]         # padded form
+    assert native.wire_decode_list(iter(strs[:10])) == raw[:320]                        # any iterable
+    for bad in ("*" + strs[7][1:], strs[7][:42], strs[7] + "A", strs[7][:42] + "B", "é" * 43, 5, None):
+        lst = list(strs[:64])
+        lst[7] = bad
+        with pytest.raises(ValueError, match="element 7"):
+            native.wire_decode_list(lst)
+    # a bad element far into a long list is reported with its own index (threads race for the minimum)
+    lst = list(strs)
+    lst[15001] = "!" * 43
+    lst[19000] = "!" * 43
+    with pytest.raises(ValueError, match="element 15001"):
+        native.wire_decode_list(lst)
+    assert decode_poly(golden["test_poly"]) == b"".join(o.b64_decode(s) for s in golden["test_poly"])
+
+
 def test_g1_sum(golden):
     pts = [bytes.fromhex(r["commitment"]) for r in golden["pianist_4x16"]]
     assert native.g1_sum(b"".join(pts)).hex() == golden["B_eval_form"]["commitment"]

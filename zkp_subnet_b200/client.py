@@ -16,6 +16,7 @@ from __future__ import annotations
 import base64
 import os
 import secrets
+import threading
 from typing import Any, Dict, List, Optional, Sequence
 
 from . import native
@@ -58,21 +59,17 @@ def _decode_any(s: str, size: int) -> bytes:
     return raw
 
 
-def decode_poly(poly: Sequence[str]) -> bytes:
-    """List[str] -> n x 32 bytes through the library's batch codec (one C call, no Python loop)."""
-    n = len(poly)
-    if n == 0:
+def decode_poly(poly: Sequence[str], staging: Optional[native.PinnedBuffer] = None):
+    """List[str] -> n x 32 bytes in one native call (csrc/wire_py.cpp walks the list through the C API and
+    decodes on host threads; no Python-level join).  With a `staging` buffer the bytes land in page-locked
+    memory, ready for an asynchronous upload.  Raises ValueError on a malformed element."""
+    if len(poly) == 0:
         return b""
-    if all(len(s) == 43 for s in poly):
-        return native.b64_decode_fr("".join(poly).encode("ascii"), 43, n)
-    if all(len(s) == 44 for s in poly):
-        return native.b64_decode_fr("".join(poly).encode("ascii"), 44, n)
-    return b"".join(_decode_any(s, 32) for s in poly)
+    return native.wire_decode_list(poly, staging)
 
 
 def encode_poly(raw: bytes) -> List[str]:
-    s = native.b64_encode_fr(raw).decode("ascii")
-    return [s[i:i + 43] for i in range(0, len(s), 43)]
+    return native.wire_encode_list(raw)
 
 
 class Client:
@@ -96,6 +93,8 @@ class Client:
         self.scale = None
         self.machines_scale = None
         self._ctx: Optional[native.Context] = None
+        self._staging: Optional[native.PinnedBuffer] = None
+        self._lock = threading.Lock()  # the staging buffer is shared: one prover call at a time, as in the library
         self._seed = seed if seed is not None else secrets.randbits(63)
         self._counter = 0
 
@@ -117,10 +116,33 @@ class Client:
             if path:
                 self._ctx.srs_save(path)
 
+    def attach(self, ctx: native.Context, scale: int, machines_scale: int) -> "Client":
+        """Use an existing context (its SRS already resident) instead of start(); for benchmarks and tests that
+        share one GPU context between the raw C-ABI calls and this wire-level shim."""
+        self._ctx, self.scale, self.machines_scale = ctx, int(scale), int(machines_scale)
+        self._attached = True
+        return self
+
     def stop(self) -> None:
+        if getattr(self, "_attached", False):
+            self._ctx = None
+        if self._staging is not None:
+            self._staging.close()
+            self._staging = None
         if self._ctx is not None:
             self._ctx.close()
             self._ctx = None
+
+    def _decode(self, poly: Sequence[str]):
+        """Decode a wire polynomial into the client's page-locked staging buffer (grown on demand)."""
+        need = 32 * len(poly)
+        if need == 0:
+            return b""
+        if self._staging is None or self._staging.capacity < need:
+            if self._staging is not None:
+                self._staging.close()
+            self._staging = native.PinnedBuffer(max(need, 32 << (self.scale - self.machines_scale)))
+        return decode_poly(poly, self._staging)
 
     def _need(self) -> native.Context:
         if self._ctx is None:
@@ -140,14 +162,16 @@ class Client:
     # ---- prover calls
     def worker_commit(self, i: int, poly: Sequence[str]) -> Response:
         try:
-            com = self._need().worker_commit(int(i), decode_poly(poly))
+            with self._lock:
+                com = self._need().worker_commit(int(i), self._decode(poly))
             return Response(200, {"commitment": _b64_point(com)})
         except (ValueError, native.ZkpError) as e:
             return self._fail(e)
 
     def worker_open(self, i: int, poly: Sequence[str], x: str) -> Response:
         try:
-            y, proof = self._need().worker_open(int(i), decode_poly(poly), _decode_any(x, 32))
+            with self._lock:
+                y, proof = self._need().worker_open(int(i), self._decode(poly), _decode_any(x, 32))
             return Response(200, {"eval": _b64_fr(y), "proof": _b64_point(proof)})
         except (ValueError, TypeError, native.ZkpError) as e:
             return self._fail(e)
@@ -155,7 +179,8 @@ class Client:
     def worker_commit_and_open(self, i: int, poly: Sequence[str], x: str) -> Response:
         """Fused form of the reference's rpc_commit_and_open (neurons/miner.py:56-61): one decode, one upload."""
         try:
-            com, y, proof = self._need().worker_commit_open(int(i), decode_poly(poly), _decode_any(x, 32))
+            with self._lock:
+                com, y, proof = self._need().worker_commit_open(int(i), self._decode(poly), _decode_any(x, 32))
             return Response(200, {"commitment": _b64_point(com), "eval": _b64_fr(y), "proof": _b64_point(proof)})
         except (ValueError, TypeError, native.ZkpError) as e:
             return self._fail(e)
@@ -174,14 +199,16 @@ class Client:
 
     def fft(self, poly: Sequence[str], left: bool = True, inverse: bool = False) -> Response:
         try:
-            out = self._need().fft(decode_poly(poly), bool(left), bool(inverse))
+            with self._lock:
+                out = self._need().fft(self._decode(poly), bool(left), bool(inverse))
             return Response(200, {"poly": encode_poly(out)})
         except (ValueError, native.ZkpError) as e:
             return self._fail(e)
 
     def eval(self, poly: Sequence[str], x: str) -> Response:
         try:
-            y = self._need().eval(decode_poly(poly), _decode_any(x, 32))
+            with self._lock:
+                y = self._need().eval(self._decode(poly), _decode_any(x, 32))
             return Response(200, {"y": _b64_fr(y)})
         except (ValueError, TypeError, native.ZkpError) as e:
             return self._fail(e)

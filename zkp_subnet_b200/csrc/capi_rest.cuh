@@ -592,13 +592,13 @@ int zkp_random_point(zkp_ctx* ctx, uint64_t seed, uint8_t out_be[32]) { return z
 // ---------------------------------------------------------------------------------------------- codec
 int zkp_b64_decode_fr(const char* strs, size_t stride, size_t count, uint8_t* out_be) {
     if (!strs || !out_be || stride < 43) return fail(ZKP_ERR_ARG, "bad argument");
-    for (size_t i = 0; i < count; i++)
-        if (!codec::b64_decode32(strs + i * stride, out_be + 32 * i)) return fail(ZKP_ERR_ENCODING, "invalid base64 field element");
+    size_t bad = codec::b64_decode_batch(strs, stride, count, out_be);
+    if (bad != count) return fail(ZKP_ERR_ENCODING, "invalid base64 field element at index " + std::to_string(bad));
     return ZKP_OK;
 }
 int zkp_b64_encode_fr(const uint8_t* in_be, size_t count, char* out_strs) {
     if (!in_be || !out_strs) return fail(ZKP_ERR_ARG, "null argument");
-    for (size_t i = 0; i < count; i++) codec::b64_encode32(in_be + 32 * i, out_strs + 43 * i);
+    codec::b64_encode_batch(in_be, count, out_strs);
     return ZKP_OK;
 }
 

@@ -146,6 +146,18 @@ int zkp_device_count(void) {
     return n;
 }
 
+int zkp_host_alloc(size_t bytes, void** out) {
+    if (!out || !bytes) return fail(ZKP_ERR_ARG, "bad argument");
+    *out = nullptr;
+    ZKP_CUDA(cudaHostAlloc(out, bytes, cudaHostAllocPortable));
+    return ZKP_OK;
+}
+int zkp_host_free(void* p) {
+    if (!p) return ZKP_OK;
+    ZKP_CUDA(cudaFreeHost(p));
+    return ZKP_OK;
+}
+
 int zkp_ctx_create(int device, zkp_ctx** out) {
     if (!out) return fail(ZKP_ERR_ARG, "null out pointer");
     int count = 0;

@@ -37,6 +37,8 @@ _SIGNATURES = {
     "zkp_ctx_destroy": [_ctxp],
     "zkp_last_error": [],
     "zkp_device_count": [],
+    "zkp_host_alloc": [ctypes.c_size_t, ctypes.POINTER(ctypes.c_void_p)],
+    "zkp_host_free": [ctypes.c_void_p],
     "zkp_srs_generate": [_ctxp, _u8p, _u8p, ctypes.c_uint32, ctypes.c_uint32],
     "zkp_srs_generate_shard": [_ctxp, _u8p, _u8p, ctypes.c_uint32, ctypes.c_uint32, ctypes.c_uint32, ctypes.c_uint32],
     "zkp_g1_sum": [_u8p, ctypes.c_size_t, _u8p],
@@ -102,6 +104,48 @@ def check(rc: int) -> None:
         raise ZkpError(rc, last_error())
 
 
+class PinnedBuffer:
+    """Page-locked host staging buffer (zkp_host_alloc).  Pass it wherever a Context method takes polynomial
+    bytes: the host->device copy then runs as one asynchronous DMA.  `len()` is the number of bytes in use."""
+
+    def __init__(self, nbytes: int):
+        self._p = ctypes.c_void_p()
+        check(lib().zkp_host_alloc(nbytes, ctypes.byref(self._p)))
+        self.capacity = nbytes
+        self.used = nbytes
+        self.buf = (ctypes.c_char * nbytes).from_address(self._p.value)
+
+    def __len__(self) -> int:
+        return self.used
+
+    def write(self, data: bytes, offset: int = 0) -> "PinnedBuffer":
+        if offset + len(data) > self.capacity:
+            raise ValueError("PinnedBuffer overflow")
+        ctypes.memmove(self._p.value + offset, data, len(data))
+        self.used = offset + len(data)
+        return self
+
+    def tobytes(self) -> bytes:
+        return ctypes.string_at(self._p.value, self.used)
+
+    def close(self) -> None:
+        if self._p:
+            self.buf = None
+            lib().zkp_host_free(self._p)
+            self._p = ctypes.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def _arg(b):
+    """bytes or PinnedBuffer -> what ctypes passes as const uint8_t*"""
+    return b.buf if isinstance(b, PinnedBuffer) else b
+
+
 class Context:
     """Owns one zkp_ctx (one GPU, one resident SRS).  Mirrors the lifetime of the reference's prover
     process started by Client.start() and killed by Client.stop() (reference base/miner.py:73-84,155)."""
@@ -163,20 +207,20 @@ class Context:
     # ---- hot path (bytes in, bytes out)
     def worker_commit(self, i: int, poly_be: bytes) -> bytes:
         out = ctypes.create_string_buffer(48)
-        check(lib().zkp_worker_commit(self._h, i, poly_be, len(poly_be) // 32, out))
+        check(lib().zkp_worker_commit(self._h, i, _arg(poly_be), len(poly_be) // 32, out))
         return out.raw
 
     def worker_open(self, i: int, poly_be: bytes, x_be: bytes) -> Tuple[bytes, bytes]:
         y = ctypes.create_string_buffer(32)
         proof = ctypes.create_string_buffer(48)
-        check(lib().zkp_worker_open(self._h, i, poly_be, len(poly_be) // 32, x_be, y, proof))
+        check(lib().zkp_worker_open(self._h, i, _arg(poly_be), len(poly_be) // 32, x_be, y, proof))
         return y.raw, proof.raw
 
     def worker_commit_open(self, i: int, poly_be: bytes, x_be: bytes) -> Tuple[bytes, bytes, bytes]:
         com = ctypes.create_string_buffer(48)
         y = ctypes.create_string_buffer(32)
         proof = ctypes.create_string_buffer(48)
-        check(lib().zkp_worker_commit_open(self._h, i, poly_be, len(poly_be) // 32, x_be, com, y, proof))
+        check(lib().zkp_worker_commit_open(self._h, i, _arg(poly_be), len(poly_be) // 32, x_be, com, y, proof))
         return com.raw, y.raw, proof.raw
 
     def worker_verify(self, i: int, proof48: bytes, alpha_be: bytes, eval_be: bytes, commitment48: bytes) -> bool:
@@ -186,12 +230,12 @@ class Context:
 
     def fft(self, vals_be: bytes, left: bool = True, inverse: bool = False) -> bytes:
         out = ctypes.create_string_buffer(len(vals_be))
-        check(lib().zkp_fft(self._h, vals_be, len(vals_be) // 32, int(left), int(inverse), out))
+        check(lib().zkp_fft(self._h, _arg(vals_be), len(vals_be) // 32, int(left), int(inverse), out))
         return out.raw
 
     def eval(self, coeffs_be: bytes, x_be: bytes) -> bytes:
         out = ctypes.create_string_buffer(32)
-        check(lib().zkp_eval(self._h, coeffs_be, len(coeffs_be) // 32, x_be, out))
+        check(lib().zkp_eval(self._h, _arg(coeffs_be), len(coeffs_be) // 32, x_be, out))
         return out.raw
 
     def random_poly(self, seed: int, count: int) -> bytes:
@@ -206,7 +250,7 @@ class Context:
 
     def msm_g1(self, row: int, scalars_be: bytes) -> bytes:
         out = ctypes.create_string_buffer(48)
-        check(lib().zkp_msm_g1(self._h, row, scalars_be, len(scalars_be) // 32, out))
+        check(lib().zkp_msm_g1(self._h, row, _arg(scalars_be), len(scalars_be) // 32, out))
         return out.raw
 
     # ---- bench / tuning
@@ -224,7 +268,7 @@ class Context:
     def bench_msm(self, row: int, scalars_be: bytes, reps: int, flush_l2: bool = True) -> Tuple[float, bytes]:
         ms = ctypes.c_float()
         out = ctypes.create_string_buffer(48)
-        check(lib().zkp_bench_msm(self._h, row, scalars_be, len(scalars_be) // 32, reps, int(flush_l2), ctypes.byref(ms), out))
+        check(lib().zkp_bench_msm(self._h, row, _arg(scalars_be), len(scalars_be) // 32, reps, int(flush_l2), ctypes.byref(ms), out))
         return ms.value, out.raw
 
     def bench_commit_open(self, row: int, poly_be: bytes, x_be: bytes, reps: int, flush_l2: bool = True):
@@ -232,7 +276,7 @@ class Context:
         com = ctypes.create_string_buffer(48)
         y = ctypes.create_string_buffer(32)
         proof = ctypes.create_string_buffer(48)
-        check(lib().zkp_bench_commit_open(self._h, row, poly_be, len(poly_be) // 32, x_be, reps, int(flush_l2),
+        check(lib().zkp_bench_commit_open(self._h, row, _arg(poly_be), len(poly_be) // 32, x_be, reps, int(flush_l2),
                                           ctypes.byref(ms), ctypes.byref(ms_k), ctypes.byref(launches), com, y, proof))
         return ms.value, ms_k.value, launches.value, com.raw, y.raw, proof.raw
 
@@ -252,10 +296,17 @@ class Context:
         return ms.value
 
 
-def b64_decode_fr(strs: bytes, stride: int, count: int) -> bytes:
-    out = ctypes.create_string_buffer(32 * count)
-    check(lib().zkp_b64_decode_fr(strs, stride, count, out))
-    return out.raw
+def b64_decode_fr(strs: bytes, stride: int, count: int, out: Optional[PinnedBuffer] = None):
+    """Batch-decode `count` base64 field elements; into `out` (a PinnedBuffer, returned) when given."""
+    if out is not None:
+        if out.capacity < 32 * count:
+            raise ValueError("PinnedBuffer too small")
+        check(lib().zkp_b64_decode_fr(strs, stride, count, out.buf))
+        out.used = 32 * count
+        return out
+    buf = ctypes.create_string_buffer(32 * count)
+    check(lib().zkp_b64_decode_fr(strs, stride, count, buf))
+    return buf.raw
 
 
 def b64_encode_fr(vals_be: bytes) -> bytes:
@@ -263,6 +314,53 @@ def b64_encode_fr(vals_be: bytes) -> bytes:
     out = ctypes.create_string_buffer(43 * count)
     check(lib().zkp_b64_encode_fr(vals_be, count, out))
     return out.raw
+
+
+# ---- CPython-side wire codec (zkp_subnet_b200/_zkp_wire.so, csrc/wire_py.cpp): List[str] <-> bytes without a
+#      Python-level join/split; PyDLL keeps the GIL for the call, the decode itself runs on host threads
+WIRE_PATH = os.path.join(_HERE, "_zkp_wire.so")
+_wire = None
+
+
+def wire() -> ctypes.PyDLL:
+    global _wire
+    if _wire is None:
+        if not os.path.exists(WIRE_PATH):
+            raise ZkpError(ZKP_ERR_STATE, f"{WIRE_PATH} not built; run `make`")
+        h = ctypes.PyDLL(WIRE_PATH)
+        h.zkp_wire_decode_list.argtypes = [ctypes.py_object, ctypes.c_void_p, ctypes.c_size_t]
+        h.zkp_wire_decode_list.restype = ctypes.c_longlong
+        h.zkp_wire_encode_list.argtypes = [ctypes.c_char_p, ctypes.c_size_t]
+        h.zkp_wire_encode_list.restype = ctypes.py_object
+        _wire = h
+    return _wire
+
+
+def wire_decode_list(strs, out: Optional[PinnedBuffer] = None):
+    """List[str] (43/44-char base64 field elements) -> n x 32 bytes, into `out` (returned) when given."""
+    if not isinstance(strs, (list, tuple)):
+        strs = list(strs)
+    n = len(strs)
+    if out is not None:
+        if out.capacity < 32 * n:
+            raise ValueError("PinnedBuffer too small")
+        rc = wire().zkp_wire_decode_list(strs, ctypes.addressof(out.buf), out.capacity)
+    else:
+        buf = ctypes.create_string_buffer(32 * n)
+        rc = wire().zkp_wire_decode_list(strs, ctypes.addressof(buf), 32 * n)
+    if rc != n:
+        if rc <= -(1 << 40):
+            raise ValueError("wire decode: bad argument")
+        raise ValueError(f"element {-1 - rc} is not a base64 field element of 43/44 characters")
+    if out is not None:
+        out.used = 32 * n
+        return out
+    return buf.raw
+
+
+def wire_encode_list(vals_be: bytes):
+    """n x 32 bytes -> list of n unpadded base64 strings (43 chars each)."""
+    return wire().zkp_wire_encode_list(vals_be, len(vals_be) // 32)
 
 
 def g1_sum(points48: bytes) -> bytes:
