@@ -65,6 +65,20 @@ int zkp_srs_generate(zkp_ctx* ctx, const uint8_t tau_x_be[32], const uint8_t tau
  * commitment (MSM sharding by point range) */
 int zkp_srs_generate_shard(zkp_ctx* ctx, const uint8_t tau_x_be[32], const uint8_t tau_y_be[32],
                            uint32_t log_n, uint32_t log_machines, uint32_t shard, uint32_t log_shards);
+/* Opening of a polynomial split by point range over G GPUs, each holding the shard made by
+ * zkp_srs_generate_shard and the matching slice of evaluations.  The barycentric sum for y = f(x) splits by
+ * point range exactly like the MSM: (1) every rank computes its partial sum (32 bytes) with
+ * zkp_shard_eval_partial, (2) the G partials are gathered and turned into y on the host by
+ * zkp_shard_eval_combine (log_n = the FULL domain), (3) every rank computes the partial proof of its slice
+ * with zkp_shard_open_partial; proof = zkp_g1_sum of the G partial proofs.  One 32-byte and one 48-byte
+ * exchange per opening, no collective inside any kernel.  x inside the evaluation domain is refused
+ * (ZKP_ERR_ARG) in this mode -- it needs a second global sum and has probability 2^-235 for a random x. */
+int zkp_shard_eval_partial(zkp_ctx* ctx, uint32_t i, const uint8_t* slice_be, size_t n_local, const uint8_t x_be[32],
+                           uint8_t partial_be[32]);
+int zkp_shard_eval_combine(const uint8_t* partials_be, size_t count, uint32_t log_n, const uint8_t x_be[32],
+                           uint8_t y_be[32]);
+int zkp_shard_open_partial(zkp_ctx* ctx, uint32_t i, const uint8_t* slice_be, size_t n_local, const uint8_t x_be[32],
+                           const uint8_t y_be[32], uint8_t proof_partial48[48]);
 /* sum of `count` compressed G1 points: the cross-GPU combine of partial commitments / Pianist
  * aggregation com = sum_i com_i, pi = sum_i pi_i (host arithmetic, 48 bytes per GPU) */
 int zkp_g1_sum(const uint8_t* points48, size_t count, uint8_t out48[48]);
@@ -73,6 +87,7 @@ int zkp_srs_set_shape(zkp_ctx* ctx, uint32_t log_n, uint32_t log_machines);
 int zkp_srs_import_row(zkp_ctx* ctx, uint32_t row, const uint8_t* points96, size_t n,
                        const uint8_t scale_point48[48]);
 int zkp_srs_import_g2_tau(zkp_ctx* ctx, const uint8_t tau_x_be[32]);
+int zkp_srs_import_g2_tau_y(zkp_ctx* ctx, const uint8_t tau_y_be[32]); /* [tau_y]_2, master verification only */
 int zkp_srs_export_row(zkp_ctx* ctx, uint32_t row, uint8_t* points96, size_t n);
 int zkp_srs_save(zkp_ctx* ctx, const char* path);
 int zkp_srs_load(zkp_ctx* ctx, const char* path);
@@ -100,6 +115,20 @@ int zkp_eval(zkp_ctx* ctx, const uint8_t* coeffs_be, size_t n, const uint8_t x_b
 /* Client.random_poly() / random_point()  (reference neurons/validator.py:68-75,88-95) */
 int zkp_random_poly(zkp_ctx* ctx, uint64_t seed, uint8_t* out_be, size_t count);
 int zkp_random_point(zkp_ctx* ctx, uint64_t seed, uint8_t out_be[32]);
+
+/* ---- Pianist master node (eprint 2023/1271 section 3): what the validator does with the M = 2^log_machines
+ *      worker responses once "multi-miner proofs" land (reference neurons/validator.py:198 "not yet
+ *      implemented", README.md:38).  f(X,Y) = sum_i R_i(Y) f_i(X);  com = sum_i com_i and pi_X = sum_i pi_i are
+ *      zkp_g1_sum over the workers' 48-byte answers.  zkp_master_open_y opens g(Y) = f(alpha, Y), given by its
+ *      evaluations y_i = f_i(alpha) (the workers' `eval`s, M x 32 bytes, worker order), at beta:
+ *      z = g(beta), pi_Y = [(g(tau_y) - z)/(tau_y - beta)]_1 over the row scale points [R_i(tau_y)]_1.
+ *      zkp_master_verify checks e(com - [z]_1, g2) == e(pi_X, [tau_x - alpha]_2) e(pi_Y, [tau_y - beta]_2);
+ *      malformed points give *valid = 0 with ZKP_OK, as for zkp_worker_verify.  Host arithmetic (M <= 2^16). */
+int zkp_master_open_y(zkp_ctx* ctx, const uint8_t* worker_evals_be, size_t m, const uint8_t beta_be[32],
+                      uint8_t z_be[32], uint8_t proof_y48[48]);
+int zkp_master_verify(zkp_ctx* ctx, const uint8_t commitment48[48], const uint8_t proof_x48[48],
+                      const uint8_t proof_y48[48], const uint8_t alpha_be[32], const uint8_t beta_be[32],
+                      const uint8_t z_be[32], int* valid);
 
 /* ---- wire codec for the List[str] format of the Prove synapse (reference base/protocol.py:35-40):
  *      `strs` holds `count` base64 strings of 43 (unpadded) or 44 (padded) characters each,

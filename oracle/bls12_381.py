@@ -514,3 +514,34 @@ def kzg_verify(commitment: G1Point, proof: G1Point, x: int, y: int,
     lhs = g1_add(commitment, g1_neg(g1_mul(scale_g1, y)))
     rhs_g2 = g2_add(tau_g2, g2_neg(g2_mul(G2_GEN, x)))
     return pairing_product_is_one([(lhs, g2_neg(G2_GEN)), (proof, rhs_g2)])
+
+
+# ------------------------------------------------------------------------------------------------
+# Pianist master node (eprint 2023/1271 section 3; the reference's roadmap item, README.md:38 and the
+# "not yet implemented" note at neurons/validator.py:198).  f(X, Y) = sum_i R_i(Y) f_i(X):
+#   com = sum_i com_i,  pi_X = sum_i pi_i,  g(Y) = f(alpha, Y) has evaluations y_i = f_i(alpha) on the
+#   size-M domain,  z = g(beta),  pi_Y = [(g(tau_Y) - z)/(tau_Y - beta)]_1,
+#   check  e(com - [z]_1, g2) == e(pi_X, [tau_X - alpha]_2) * e(pi_Y, [tau_Y - beta]_2).
+# The Y-direction opening is restated here in COEFFICIENT form (interpolate, Horner, synthetic division,
+# monomial SRS in tau_Y) -- deliberately not the evaluation-form route the product takes.
+# ------------------------------------------------------------------------------------------------
+def master_aggregate(points: Sequence[G1Point]) -> G1Point:
+    acc = None
+    for p in points:
+        acc = g1_add(acc, p)
+    return acc
+
+
+def master_open_y(worker_evals: Sequence[int], beta: int, tau_y: int):
+    coeffs = ntt(list(worker_evals), inverse=True) if len(worker_evals) > 1 else list(worker_evals)
+    q, z = quotient_coeffs(coeffs, beta)
+    mono_y = srs_monomial(max(len(q), 1), tau_y)
+    return z, (g1_msm_naive(mono_y[: len(q)], q) if q else None)
+
+
+def master_verify(com: G1Point, pi_x: G1Point, pi_y: G1Point, alpha: int, beta: int, z: int,
+                  tau_x_g2: G2Point, tau_y_g2: G2Point) -> bool:
+    lhs = g1_add(com, g1_neg(g1_mul(G1_GEN, z)))
+    qx = g2_add(tau_x_g2, g2_neg(g2_mul(G2_GEN, alpha)))
+    qy = g2_add(tau_y_g2, g2_neg(g2_mul(G2_GEN, beta)))
+    return pairing_product_is_one([(lhs, g2_neg(G2_GEN)), (pi_x, qx), (pi_y, qy)])

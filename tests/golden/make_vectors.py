@@ -48,6 +48,32 @@ for i in range(4):
     pianist.append({"row": i, "scale_point": o.g1_compress(o.g1_mul(o.G1_GEN, Rs[i])).hex(),
                     "commitment": o.g1_compress(com).hex(), "eval": o.fr_to_b64(y), "proof": o.g1_compress(proof).hex()})
 
+# Pianist master (config 5 in miniature): 4 different sub-polynomials (rotations of TEST_POLY), one per row;
+# aggregated commitment, X-opening at alpha = TEST_POINT, Y-opening at beta = TEST_EVAL (and at a domain point)
+beta = o.fr_from_b64(TEST_EVAL)
+m_rows = []
+for i in range(4):
+    row = o.srs_lagrange(16, TAU_X, scale=Rs[i])
+    fi = poly[i:] + poly[:i]
+    yi, pi_i = o.kzg_open_evals(fi, x, row)
+    m_rows.append((o.kzg_commit(fi, row), yi, pi_i))
+m_com = o.master_aggregate([r[0] for r in m_rows])
+m_pix = o.master_aggregate([r[2] for r in m_rows])
+m_z, m_piy = o.master_open_y([r[1] for r in m_rows], beta, TAU_Y)
+g2x, g2y = o.g2_mul(o.G2_GEN, TAU_X), o.g2_mul(o.G2_GEN, TAU_Y)
+assert o.master_verify(m_com, m_pix, m_piy, x, beta, m_z, g2x, g2y)
+assert not o.master_verify(m_com, m_pix, m_piy, x, beta, (m_z + 1) % o.R, g2x, g2y)
+beta_d = pow(o.root_of_unity(4), 3, o.R)
+m_zd, m_piyd = o.master_open_y([r[1] for r in m_rows], beta_d, TAU_Y)
+assert m_zd == m_rows[3][1] and o.master_verify(m_com, m_pix, m_piyd, x, beta_d, m_zd, g2x, g2y)
+master = {
+    "rows": [{"commitment": o.g1_compress(c).hex(), "eval": o.fr_to_b64(yy), "proof": o.g1_compress(pp).hex()}
+             for c, yy, pp in m_rows],
+    "commitment": o.g1_compress(m_com).hex(), "proof_x": o.g1_compress(m_pix).hex(),
+    "beta": o.fr_to_b64(beta), "z": o.fr_to_b64(m_z), "proof_y": o.g1_compress(m_piy).hex(),
+    "beta_in_domain": o.fr_to_b64(beta_d), "z_in_domain": o.fr_to_b64(m_zd), "proof_y_in_domain": o.g1_compress(m_piyd).hex(),
+}
+
 vec = {
     "source": "oracle/bls12_381.py (big-int); TEST_* copied from reference tests/test_miner.py:33-55",
     "tau_x": str(TAU_X), "tau_y": str(TAU_Y),
@@ -65,6 +91,8 @@ vec = {
     "ntt16": [o.fr_to_b64(v) for v in o.ntt(poly)],
     "intt16": [o.fr_to_b64(v) for v in o.ntt(poly, inverse=True)],
     "pianist_4x16": pianist,
+    "pianist_master_4x16": master,
+    "g2_tau_y": [hex(c) for c in (lambda p: (p[0][0], p[0][1], p[1][0], p[1][1]))(g2y)],
     "g2_tau_x": [hex(c) for c in (lambda p: (p[0][0], p[0][1], p[1][0], p[1][1]))(o.g2_mul(o.G2_GEN, TAU_X))],
 }
 out = os.path.join(os.path.dirname(__file__), "vectors.json")

@@ -135,6 +135,42 @@ def test_golden_vectors(gpu_ctx, golden):
         assert not gpu_ctx.worker_verify(i, tampered, x, y, com)
 
 
+def test_pianist_master_golden(gpu_ctx, golden):
+    """Config 5 in miniature: 4 sub-polynomials on 4 SRS rows, aggregated commitment, X-opening at alpha and the
+    master's Y-direction opening at beta -- bytes against the oracle's coefficient-form restatement, and the
+    bivariate pairing check."""
+    M = golden["pianist_master_4x16"]
+    poly = [o.b64_decode(s) for s in golden["test_poly"]]
+    x = o.b64_decode(golden["test_point"])
+    gpu_ctx.srs_generate(TAU_X, TAU_Y, 4, 2)
+    coms, ys, proofs = [], [], []
+    for i, rec in enumerate(M["rows"]):
+        fi = b"".join(poly[i:] + poly[:i])
+        com, y, proof = gpu_ctx.worker_commit_open(i, fi, x)
+        assert (com.hex(), o.fr_to_b64(int.from_bytes(y, "big")), proof.hex()) == (rec["commitment"], rec["eval"], rec["proof"])
+        coms.append(com); ys.append(y); proofs.append(proof)
+    com, pix = native.g1_sum(b"".join(coms)), native.g1_sum(b"".join(proofs))
+    assert (com.hex(), pix.hex()) == (M["commitment"], M["proof_x"])
+    for bk, zk, pk in (("beta", "z", "proof_y"), ("beta_in_domain", "z_in_domain", "proof_y_in_domain")):
+        beta = o.b64_decode(M[bk])
+        z, piy = gpu_ctx.master_open_y(b"".join(ys), beta)
+        assert (o.fr_to_b64(int.from_bytes(z, "big")), piy.hex()) == (M[zk], M[pk])
+        assert gpu_ctx.master_verify(com, pix, piy, x, beta, z)
+        bad_z = ((int.from_bytes(z, "big") + 1) % o.R).to_bytes(32, "big")
+        assert not gpu_ctx.master_verify(com, pix, piy, x, beta, bad_z)
+        assert not gpu_ctx.master_verify(com, piy, pix, x, beta, z)          # proofs swapped
+        assert not gpu_ctx.master_verify(coms[0], pix, piy, x, beta, z)      # a worker's commitment, not the aggregate
+        assert not gpu_ctx.master_verify(com, pix, b"\xff" * 48, x, beta, z)  # malformed point: invalid, not an error
+    with pytest.raises(native.ZkpError):
+        gpu_ctx.master_open_y(b"".join(ys[:3]), x)  # one evaluation per worker
+    # M = 1: g is constant, the Y-proof is the point at infinity
+    gpu_ctx.srs_generate(TAU_X, TAU_Y, 4, 0)
+    com, y, proof = gpu_ctx.worker_commit_open(0, b"".join(poly), x)
+    z, piy = gpu_ctx.master_open_y(y, o.b64_decode(M["beta"]))
+    assert z == y and piy.hex() == golden["g1_encodings"]["inf"]
+    assert gpu_ctx.master_verify(com, proof, piy, x, o.b64_decode(M["beta"]), z)
+
+
 @pytest.mark.parametrize("log_n", [0, 1, 3, 9, 12, 13, 15, 17])
 def test_ntt_vs_oracle(gpu_ctx, log_n):
     n = 1 << log_n
@@ -229,6 +265,37 @@ def test_sharded_commit_combines_to_full(gpu_ctx):
     assert native.g1_sum(parts) == full
 
 
+@pytest.mark.parametrize("log_n,log_shards", [(6, 2), (12, 3), (16, 1)])
+def test_sharded_open_combines_to_full(gpu_ctx, log_n, log_shards):
+    """Point-range shards (generated one after the other on this GPU): partial barycentric sums -> y, partial
+    proofs -> proof; both equal the unsharded opening, bit for bit."""
+    n, G = 1 << log_n, 1 << log_shards
+    f = ref.random_scalars(0x5A + log_n, n)
+    x = ref.random_scalars(0x5B, 1)
+    gpu_ctx.srs_generate(TAU_X, TAU_Y, log_n, 0)
+    com, y, proof = gpu_ctx.worker_commit_open(0, f, x)
+    per = n // G * 32
+    partial_sums, coms = [], []
+    for g in range(G):
+        gpu_ctx.srs_generate_shard(TAU_X, TAU_Y, log_n, 0, g, log_shards)
+        partial_sums.append(gpu_ctx.shard_eval_partial(0, f[g * per:(g + 1) * per], x))
+        coms.append(gpu_ctx.worker_commit(0, f[g * per:(g + 1) * per]))
+    assert native.shard_eval_combine(b"".join(partial_sums), log_n, x) == y
+    assert native.g1_sum(b"".join(coms)) == com
+    proofs = []
+    for g in range(G):
+        gpu_ctx.srs_generate_shard(TAU_X, TAU_Y, log_n, 0, g, log_shards)
+        proofs.append(gpu_ctx.shard_open_partial(0, f[g * per:(g + 1) * per], x, y))
+        with pytest.raises(native.ZkpError):  # the single-device opening is refused on a shard
+            gpu_ctx.worker_open(0, f[g * per:(g + 1) * per], x)
+    assert native.g1_sum(b"".join(proofs)) == proof
+    # x inside this shard's part of the domain is refused explicitly
+    w = o.root_of_unity(n)
+    xin = pow(w, n - 1, o.R).to_bytes(32, "big")  # last shard holds index n - 1
+    with pytest.raises(native.ZkpError, match="inside the domain"):
+        gpu_ctx.shard_eval_partial(0, f[(G - 1) * per:], xin)
+
+
 def test_errors_and_edge_inputs(gpu_ctx):
     gpu_ctx.srs_generate(TAU_X, TAU_Y, 4, 0)
     with pytest.raises(native.ZkpError) as e:
@@ -266,5 +333,9 @@ def test_srs_file_roundtrip(gpu_ctx, tmp_path, golden):
         com, y, proof = other.worker_commit_open(3, poly, x)
         assert com.hex() == rec["commitment"] and proof.hex() == rec["proof"]
         assert other.worker_verify(3, proof, x, y, com) and gpu_ctx.worker_verify(3, proof, x, y, com)
+        # [tau_y]_2 travels in the file (format version 2): the master check works on the loaded SRS
+        M = golden["pianist_master_4x16"]
+        assert other.master_verify(bytes.fromhex(M["commitment"]), bytes.fromhex(M["proof_x"]), bytes.fromhex(M["proof_y"]), x,
+                                   o.b64_decode(M["beta"]), o.b64_decode(M["z"]))
     finally:
         other.close()

@@ -99,6 +99,27 @@ def test_pianist_rows(golden, poly):
     assert o.g1_compress(agg).hex() == golden["B_eval_form"]["commitment"]
 
 
+def test_pianist_master_vectors(golden):
+    """The committed master vectors (coefficient-form Y-opening over a monomial tau_Y SRS) equal the
+    evaluation-form route over the row scale points [R_i(tau_Y)]_1 -- two formulations, one group element --
+    and the trapdoor identity pi_Y = [(g(tau_Y) - z)/(tau_Y - beta)]_1."""
+    M = golden["pianist_master_4x16"]
+    tau_y = int(golden["tau_y"])
+    ys = [o.fr_from_b64(r["eval"]) for r in M["rows"]]
+    Rs = o.lagrange_at(4, tau_y)
+    scale_pts = [o.g1_mul(o.G1_GEN, r) for r in Rs]
+    for bk, zk, pk in (("beta", "z", "proof_y"), ("beta_in_domain", "z_in_domain", "proof_y_in_domain")):
+        beta = o.fr_from_b64(M[bk])
+        z, piy = o.master_open_y(ys, beta, tau_y)
+        assert (o.fr_to_b64(z), o.g1_compress(piy).hex()) == (M[zk], M[pk])
+        q, z2 = o.quotient_evals(ys, beta)
+        assert z2 == z and o.g1_compress(o.g1_msm_naive(scale_pts, q)).hex() == M[pk]
+        g_tau = sum(y * r for y, r in zip(ys, Rs)) % R
+        assert o.g1_compress(o.g1_mul(o.G1_GEN, (g_tau - z) * o.fr_inv((tau_y - beta) % R) % R)).hex() == M[pk]
+    assert o.g1_compress(o.master_aggregate([o.g1_decompress(bytes.fromhex(r["commitment"])) for r in M["rows"]])).hex() == M["commitment"]
+    assert o.g1_compress(o.master_aggregate([o.g1_decompress(bytes.fromhex(r["proof"])) for r in M["rows"]])).hex() == M["proof_x"]
+
+
 def test_msm_trapdoor_and_threads():
     n = 1 << 10
     srs = ref.srs(n, o.TEST_SECRET, "lagrange")

@@ -197,6 +197,37 @@ class Client:
         except native.ZkpError as e:
             return self._fail(e)
 
+    # ---- Pianist master node.  Not part of the reference's Client yet ("multi-miner proofs ... not yet
+    #      implemented", reference neurons/validator.py:198; roadmap README.md:38); named after the worker_* calls.
+    def master_commit(self, commitments: Sequence[str]) -> Response:
+        """com = sum_i com_i over the workers' commitments."""
+        try:
+            raw = b"".join(_decode_any(c, 48) for c in commitments)
+            return Response(200, {"commitment": _b64_point(native.g1_sum(raw))})
+        except (ValueError, TypeError, native.ZkpError) as e:
+            return self._fail(e)
+
+    def master_open(self, evals: Sequence[str], proofs: Sequence[str], beta: str) -> Response:
+        """From the workers' (eval, proof) answers at a common alpha: pi_X = sum_i pi_i, z = f(alpha, beta) and the
+        Y-direction proof pi_Y."""
+        try:
+            pix = native.g1_sum(b"".join(_decode_any(p, 48) for p in proofs))
+            z, piy = self._need().master_open_y(b"".join(_decode_any(e, 32) for e in evals), _decode_any(beta, 32))
+            return Response(200, {"eval": _b64_fr(z), "proof_x": _b64_point(pix), "proof_y": _b64_point(piy)})
+        except (ValueError, TypeError, native.ZkpError) as e:
+            return self._fail(e)
+
+    def master_verify(self, proof_x: str, proof_y: str, alpha: str, beta: str, eval: str, commitment: str) -> Response:
+        try:
+            args = (_decode_any(commitment, 48), _decode_any(proof_x, 48), _decode_any(proof_y, 48), _decode_any(alpha, 32),
+                    _decode_any(beta, 32), _decode_any(eval, 32))
+        except (ValueError, TypeError):
+            return Response(200, {"valid": False})
+        try:
+            return Response(200, {"valid": self._need().master_verify(*args)})
+        except native.ZkpError as e:
+            return self._fail(e)
+
     def fft(self, poly: Sequence[str], left: bool = True, inverse: bool = False) -> Response:
         try:
             with self._lock:

@@ -265,6 +265,7 @@ int ensure_fixed_base(zkp_ctx* ctx) {
 void set_pairing_lines(zkp_ctx* ctx) {
     ctx->lines_g2 = host::g2_precompute(host::g2_generator());
     ctx->lines_tau = host::g2_precompute(ctx->g2_tau);
+    if (ctx->have_g2_tau_y) ctx->lines_tau_y = host::g2_precompute(ctx->g2_tau_y);
     ctx->have_lines = true;
 }
 
@@ -358,8 +359,12 @@ int zkp_srs_generate_shard(zkp_ctx* ctx, const uint8_t tau_x_be[32], const uint8
     Fr64 txc = tx.from_mont();
     ctx->g2_tau = host::g2_generator().mul(txc.v, 4);
     ctx->have_g2_tau = true;
+    Fr64 tyc = ty.from_mont();
+    ctx->g2_tau_y = host::g2_generator().mul(tyc.v, 4);
+    ctx->have_g2_tau_y = true;
     set_pairing_lines(ctx);
     ctx->shard_domain_log = log_n;
+    ctx->shard_index = shard;
     return ZKP_OK;
 }
 
@@ -389,20 +394,35 @@ int zkp_srs_import_g2_tau(zkp_ctx* ctx, const uint8_t tau_x_be[32]) {
     return ZKP_OK;
 }
 
-// file: "ZKPB200S" | u32 version | u32 log_n | u32 log_m | G2 tau affine (4 x 48 B BE) |
+int zkp_srs_import_g2_tau_y(zkp_ctx* ctx, const uint8_t tau_y_be[32]) {
+    if (!ctx || !tau_y_be) return fail(ZKP_ERR_ARG, "null argument");
+    Fr64 t;
+    if (!Fr64::from_be(t, tau_y_be)) return fail(ZKP_ERR_ENCODING, "tau not canonical");
+    Fr64 c = t.from_mont();
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    ctx->g2_tau_y = host::g2_generator().mul(c.v, 4);
+    ctx->have_g2_tau_y = true;
+    if (ctx->have_g2_tau) set_pairing_lines(ctx);
+    return ZKP_OK;
+}
+
+// file: "ZKPB200S" | u32 version | u32 log_n | u32 log_m | [tau_x]_2 affine (4 x 48 B BE) |
+//       version 2 only: [tau_y]_2 affine (4 x 48 B BE) |
 //       M x 48 B compressed scale points | M*n x 96 B uncompressed points
 int zkp_srs_save(zkp_ctx* ctx, const char* path) {
     if (!ctx || !path) return fail(ZKP_ERR_ARG, "null argument");
     if (!ctx->shaped || !ctx->have_g2_tau) return fail(ZKP_ERR_STATE, "SRS incomplete");
     FILE* f = fopen(path, "wb");
     if (!f) return fail(ZKP_ERR_IO, std::string("cannot open ") + path);
-    uint32_t hdr[3] = {1, ctx->log_n, ctx->log_m};
+    uint32_t hdr[3] = {ctx->have_g2_tau_y ? 2u : 1u, ctx->log_n, ctx->log_m};
     bool ok = fwrite("ZKPB200S", 1, 8, f) == 8 && fwrite(hdr, 4, 3, f) == 3;
-    host::Fq2 gx, gy;
-    ctx->g2_tau.to_affine(gx, gy);
-    uint8_t g2[192];
-    gx.c0.to_be(g2); gx.c1.to_be(g2 + 48); gy.c0.to_be(g2 + 96); gy.c1.to_be(g2 + 144);
-    ok = ok && fwrite(g2, 1, 192, f) == 192;
+    for (int which = 0; which < (ctx->have_g2_tau_y ? 2 : 1); which++) {
+        host::Fq2 gx, gy;
+        (which ? ctx->g2_tau_y : ctx->g2_tau).to_affine(gx, gy);
+        uint8_t g2[192];
+        gx.c0.to_be(g2); gx.c1.to_be(g2 + 48); gy.c0.to_be(g2 + 96); gy.c1.to_be(g2 + 144);
+        ok = ok && fwrite(g2, 1, 192, f) == 192;
+    }
     size_t M = (size_t)1 << ctx->log_m, n = (size_t)1 << ctx->log_n;
     for (size_t i = 0; i < M && ok; i++) {
         uint8_t sp[48];
@@ -425,17 +445,20 @@ int zkp_srs_load(zkp_ctx* ctx, const char* path) {
     if (!f) return fail(ZKP_ERR_IO, std::string("cannot open ") + path);
     char magic[8];
     uint32_t hdr[3];
-    uint8_t g2[192];
-    if (fread(magic, 1, 8, f) != 8 || memcmp(magic, "ZKPB200S", 8) || fread(hdr, 4, 3, f) != 3 || hdr[0] != 1 ||
-        fread(g2, 1, 192, f) != 192) {
+    uint8_t g2[192], g2y[192];
+    if (fread(magic, 1, 8, f) != 8 || memcmp(magic, "ZKPB200S", 8) || fread(hdr, 4, 3, f) != 3 || (hdr[0] != 1 && hdr[0] != 2) ||
+        fread(g2, 1, 192, f) != 192 || (hdr[0] == 2 && fread(g2y, 1, 192, f) != 192)) {
         fclose(f);
         return fail(ZKP_ERR_IO, "not a zkp_b200 SRS file");
     }
     int rc = zkp_srs_set_shape(ctx, hdr[1], hdr[2]);
     if (rc) { fclose(f); return rc; }
-    host::Fq2 gx, gy;
-    if (!Fq64::from_be(gx.c0, g2) || !Fq64::from_be(gx.c1, g2 + 48) || !Fq64::from_be(gy.c0, g2 + 96) ||
-        !Fq64::from_be(gy.c1, g2 + 144) || !host::g2_on_curve(gx, gy)) {
+    auto parse_g2 = [](const uint8_t* b, host::Fq2& x, host::Fq2& y) {
+        return Fq64::from_be(x.c0, b) && Fq64::from_be(x.c1, b + 48) && Fq64::from_be(y.c0, b + 96) && Fq64::from_be(y.c1, b + 144) &&
+               host::g2_on_curve(x, y);
+    };
+    host::Fq2 gx, gy, hx, hy;
+    if (!parse_g2(g2, gx, gy) || (hdr[0] == 2 && !parse_g2(g2y, hx, hy))) {
         fclose(f);
         return fail(ZKP_ERR_ENCODING, "bad G2 point in SRS file");
     }
@@ -451,6 +474,8 @@ int zkp_srs_load(zkp_ctx* ctx, const char* path) {
     std::lock_guard<std::mutex> lk(ctx->mu);
     ctx->g2_tau = host::G2J::from_affine(gx, gy);
     ctx->have_g2_tau = true;
+    ctx->have_g2_tau_y = hdr[0] == 2;
+    if (ctx->have_g2_tau_y) ctx->g2_tau_y = host::G2J::from_affine(hx, hy);
     set_pairing_lines(ctx);
     return ZKP_OK;
 }
@@ -482,6 +507,108 @@ int zkp_worker_commit_open(zkp_ctx* ctx, uint32_t i, const uint8_t* poly_be, siz
     return commit_open_resident(ctx, i, n, x, commitment48, eval_be, proof48);
 }
 
+// ---------------------------------------------------------------------------------------------- sharded open
+// Opening of a polynomial whose evaluations (and SRS row) are split by point range over G GPUs
+// (zkp_srs_generate_shard).  The barycentric sum splits by point range like the MSM does:
+//   f(x) = -(x^n - 1)/n * sum_g S_g,   S_g = sum_{j in shard g} f_j w^j / (w^j - x)
+// so the ranks exchange ONE 32-byte partial sum (all-gather), form y on the host, and then each computes the
+// quotient evaluations of its own slice and the MSM over its own points; pi = sum_g pi_g (zkp_g1_sum).
+namespace {
+int shard_checks(zkp_ctx* ctx, uint32_t i, const void* slice, size_t n_local, const uint8_t* x_be, Fr64* x) {
+    int rc = check_row(ctx, i, n_local);
+    if (rc) return rc;
+    if (!slice || !x_be) return fail(ZKP_ERR_ARG, "null argument");
+    if (n_local != ((size_t)1 << ctx->log_n)) return fail(ZKP_ERR_ARG, "need exactly this shard's slice of evaluations");
+    if (!Fr64::from_be(*x, x_be)) return fail(ZKP_ERR_ENCODING, "evaluation point is not canonical");
+    return ZKP_OK;
+}
+// f slice -> fr_a (Montgomery), 1/(w^j - x) -> fr_b, S_g -> small[SM_S1]; fails if x lies in this shard's slice
+int shard_pass1(zkp_ctx* ctx, const uint8_t* slice_be, size_t n_local, const Fr64& x) {
+    int rc = upload_poly(ctx, slice_be, n_local);
+    if (rc) return rc;
+    zkp_ctx::Domain* dom;
+    rc = get_domain(ctx, ctx->shard_domain_log, false, &dom);
+    if (rc) return rc;
+    cudaStream_t st = ctx->stream;
+    const uint32_t n = (uint32_t)n_local;
+    ZKP_CUDA(ctx->fr_b.ensure((size_t)n * 32));
+    uint32_t E = n >> 14;
+    if (E < 8) E = 8;
+    if (E > 64) E = 64;
+    uint32_t threads = (n + E - 1) / E, blocks = (threads + 127) / 128;
+    ZKP_CUDA(ctx->partials.ensure((size_t)blocks * 32));
+    ZKP_CUDA(cudaMemsetAsync(small_at<uint32_t>(ctx, SM_HIT), 0xff, 4, st));
+    k_open_pass1<<<blocks, 128, 0, st>>>(ctx->fr_a.as<Fr>(), n, E, to_dev(x), dom->wt.as<Fr>(), to_dev(dom->w_inv), ctx->fr_b.as<Fr>(),
+                                         ctx->partials.as<Fr>(), small_at<uint32_t>(ctx, SM_HIT), (uint64_t)ctx->shard_index << ctx->log_n);
+    k_fr_reduce<<<1, 256, 0, st>>>(ctx->partials.as<Fr>(), blocks, small_at<Fr>(ctx, SM_S1));
+    ctx->launches += 2;
+    ZKP_CUDA(cudaMemcpyAsync(ctx->h_small + 96, small_at<uint8_t>(ctx, SM_HIT), 4, cudaMemcpyDeviceToHost, st));
+    ZKP_CUDA(cudaMemcpyAsync(ctx->h_small + 64, small_at<uint8_t>(ctx, SM_BAD), 4, cudaMemcpyDeviceToHost, st));
+    ZKP_CUDA(cudaStreamSynchronize(st));
+    if (*reinterpret_cast<uint32_t*>(ctx->h_small + 64)) return fail(ZKP_ERR_ENCODING, "polynomial holds a non-canonical field element");
+    if (*reinterpret_cast<uint32_t*>(ctx->h_small + 96) != HIT_NONE)
+        return fail(ZKP_ERR_ARG, "evaluation point lies inside the domain: not supported on point-range shards "
+                                 "(use zkp_worker_open on an unsharded row)");
+    return ZKP_OK;
+}
+}  // namespace
+
+int zkp_shard_eval_partial(zkp_ctx* ctx, uint32_t i, const uint8_t* slice_be, size_t n_local, const uint8_t x_be[32],
+                           uint8_t partial_be[32]) {
+    Fr64 x;
+    int rc = shard_checks(ctx, i, slice_be, n_local, x_be, &x);
+    if (rc) return rc;
+    if (!partial_be) return fail(ZKP_ERR_ARG, "null output");
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    DeviceGuard g(ctx->device);
+    rc = shard_pass1(ctx, slice_be, n_local, x);
+    if (rc) return rc;
+    k_fr_to_be<<<1, 32, 0, ctx->stream>>>(small_at<Fr>(ctx, SM_S1), 1, small_at<uint32_t>(ctx, SM_EVAL));
+    ctx->launches++;
+    ZKP_CUDA(cudaMemcpyAsync(ctx->h_small, small_at<uint8_t>(ctx, SM_EVAL), 32, cudaMemcpyDeviceToHost, ctx->stream));
+    ZKP_CUDA(cudaStreamSynchronize(ctx->stream));
+    memcpy(partial_be, ctx->h_small, 32);
+    return ZKP_OK;
+}
+
+// y = -(x^n - 1)/n * sum_g S_g   (host; n = 2^log_n is the FULL domain size)
+int zkp_shard_eval_combine(const uint8_t* partials_be, size_t count, uint32_t log_n, const uint8_t x_be[32], uint8_t y_be[32]) {
+    if (!partials_be || !x_be || !y_be || !count || log_n > 32) return fail(ZKP_ERR_ARG, "bad argument");
+    Fr64 x, acc = Fr64::zero();
+    if (!Fr64::from_be(x, x_be)) return fail(ZKP_ERR_ENCODING, "evaluation point is not canonical");
+    for (size_t g = 0; g < count; g++) {
+        Fr64 s;
+        if (!Fr64::from_be(s, partials_be + 32 * g)) return fail(ZKP_ERR_ENCODING, "partial sum is not canonical");
+        acc = acc + s;
+    }
+    Fr64 xn = x;
+    for (uint32_t k = 0; k < log_n; k++) xn = xn.sqr();
+    Fr64 y = ((xn - Fr64::one()) * Fr64::from_u64(1ull << log_n).inverse() * acc).neg();
+    y.to_be(y_be);
+    return ZKP_OK;
+}
+
+int zkp_shard_open_partial(zkp_ctx* ctx, uint32_t i, const uint8_t* slice_be, size_t n_local, const uint8_t x_be[32],
+                           const uint8_t y_be[32], uint8_t proof_partial48[48]) {
+    Fr64 x, y;
+    int rc = shard_checks(ctx, i, slice_be, n_local, x_be, &x);
+    if (rc) return rc;
+    if (!y_be || !proof_partial48) return fail(ZKP_ERR_ARG, "null argument");
+    if (!Fr64::from_be(y, y_be)) return fail(ZKP_ERR_ENCODING, "evaluation is not canonical");
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    DeviceGuard g(ctx->device);
+    rc = shard_pass1(ctx, slice_be, n_local, x);
+    if (rc) return rc;
+    cudaStream_t st = ctx->stream;
+    const uint32_t n = (uint32_t)n_local;
+    ZKP_CUDA(ctx->fr_c.ensure((size_t)n * 32));
+    memcpy(ctx->h_small + 128, y.v, 32);
+    ZKP_CUDA(cudaMemcpyAsync(small_at<uint8_t>(ctx, SM_Y), ctx->h_small + 128, 32, cudaMemcpyHostToDevice, st));
+    k_open_pass2<<<(n + 255) / 256, 256, 0, st>>>(ctx->fr_a.as<Fr>(), ctx->fr_b.as<Fr>(), n, small_at<Fr>(ctx, SM_Y), ctx->fr_c.as<Fr>());
+    ctx->launches++;
+    return msm_device(ctx, i, ctx->fr_c.as<uint32_t>(), SCALAR_MONT, n, proof_partial48);
+}
+
 // ---------------------------------------------------------------------------------------------- verify
 int zkp_worker_verify(zkp_ctx* ctx, uint32_t i, const uint8_t proof48[48], const uint8_t alpha_be[32], const uint8_t eval_be[32],
                       const uint8_t commitment48[48], int* valid) {
@@ -505,6 +632,102 @@ int zkp_worker_verify(zkp_ctx* ctx, uint32_t i, const uint8_t proof48[48], const
     G1J a = com.add(scale.mul(yc.v, 4).neg()).add(proof.mul(ac.v, 4));
     std::vector<G1AffineHost> ps = {g1_affine_host(a), g1_affine_host(proof.neg())};
     std::vector<const G2Lines*> qs = {&ctx->lines_g2, &ctx->lines_tau};
+    *valid = pairing_product_is_one(ps, qs) ? 1 : 0;
+    return ZKP_OK;
+}
+
+// ---------------------------------------------------------------------------------------------- Pianist master
+int zkp_master_open_y(zkp_ctx* ctx, const uint8_t* worker_evals_be, size_t m, const uint8_t beta_be[32], uint8_t z_be[32],
+                      uint8_t proof_y48[48]) {
+    if (!ctx || !worker_evals_be || !beta_be || !z_be || !proof_y48) return fail(ZKP_ERR_ARG, "null argument");
+    if (!ctx->shaped) return fail(ZKP_ERR_STATE, "SRS not loaded");
+    const uint32_t log_m = ctx->log_m;
+    if (m != ((size_t)1 << log_m)) return fail(ZKP_ERR_ARG, "need exactly one evaluation per worker (2^log_machines)");
+    std::vector<Fr64> y(m);
+    Fr64 beta;
+    if (!Fr64::from_be(beta, beta_be)) return fail(ZKP_ERR_ENCODING, "beta is not canonical");
+    for (size_t i = 0; i < m; i++)
+        if (!Fr64::from_be(y[i], worker_evals_be + 32 * i)) return fail(ZKP_ERR_ENCODING, "worker evaluation is not canonical");
+    std::vector<host::G1J> scale;
+    {
+        std::lock_guard<std::mutex> lk(ctx->mu);
+        for (size_t i = 0; i < m; i++)
+            if (!ctx->row_loaded[i]) return fail(ZKP_ERR_STATE, "SRS row not loaded");
+        scale = ctx->scale_points;
+    }
+    // d_i = w^i - beta over the size-m domain; beta inside the domain is handled exactly
+    const Fr64 w = fr_root_of_unity(log_m);
+    std::vector<Fr64> wi(m), d(m);
+    size_t hit = m;
+    Fr64 cur = Fr64::one();
+    for (size_t i = 0; i < m; i++) {
+        wi[i] = cur;
+        d[i] = cur - beta;
+        if (d[i].is_zero()) hit = i;
+        cur = cur * w;
+    }
+    // one batch inversion of the non-zero d_i
+    std::vector<Fr64> pre(m);
+    Fr64 run = Fr64::one();
+    for (size_t i = 0; i < m; i++) {
+        pre[i] = run;
+        if (i != hit) run = run * d[i];
+    }
+    Fr64 inv = run.inverse();
+    std::vector<Fr64> dinv(m, Fr64::zero());
+    for (size_t i = m; i-- > 0;) {
+        if (i == hit) continue;
+        dinv[i] = inv * pre[i];
+        inv = inv * d[i];
+    }
+    Fr64 z;
+    if (hit < m) {
+        z = y[hit];
+    } else {
+        // barycentric: g(beta) = (beta^m - 1)/m * sum_i y_i w^i / (beta - w^i)
+        Fr64 acc = Fr64::zero();
+        for (size_t i = 0; i < m; i++) acc = acc - y[i] * wi[i] * dinv[i];
+        Fr64 bm = beta;
+        for (uint32_t k = 0; k < log_m; k++) bm = bm.sqr();
+        z = acc * (bm - Fr64::one()) * Fr64::from_u64(m).inverse();
+    }
+    std::vector<Fr64> q(m, Fr64::zero());
+    for (size_t i = 0; i < m; i++)
+        if (i != hit) q[i] = (y[i] - z) * dinv[i];
+    if (hit < m) {
+        // q_hit = g'(w^hit) = -sum_{i != hit} q_i w^(i - hit)
+        Fr64 acc = Fr64::zero(), whi = wi[hit].inverse();
+        for (size_t i = 0; i < m; i++)
+            if (i != hit) acc = acc + q[i] * wi[i] * whi;
+        q[hit] = acc.neg();
+    }
+    host::G1J pi = host::G1J::infinity();
+    for (size_t i = 0; i < m; i++) {
+        if (q[i].is_zero()) continue;
+        Fr64 qc = q[i].from_mont();
+        pi = pi.add(scale[i].mul(qc.v, 4));
+    }
+    z.to_be(z_be);
+    host::g1_compress(proof_y48, pi);
+    return ZKP_OK;
+}
+
+int zkp_master_verify(zkp_ctx* ctx, const uint8_t commitment48[48], const uint8_t proof_x48[48], const uint8_t proof_y48[48],
+                      const uint8_t alpha_be[32], const uint8_t beta_be[32], const uint8_t z_be[32], int* valid) {
+    if (!ctx || !commitment48 || !proof_x48 || !proof_y48 || !alpha_be || !beta_be || !z_be || !valid)
+        return fail(ZKP_ERR_ARG, "null argument");
+    *valid = 0;
+    if (!ctx->shaped || !ctx->have_lines || !ctx->have_g2_tau_y) return fail(ZKP_ERR_STATE, "SRS (G2 part, tau_x and tau_y) not loaded");
+    using namespace host;
+    G1J com, px, py;
+    Fr64 alpha, beta, z;
+    if (!g1_decompress(com, commitment48) || !g1_decompress(px, proof_x48) || !g1_decompress(py, proof_y48)) return ZKP_OK;
+    if (!Fr64::from_be(alpha, alpha_be) || !Fr64::from_be(beta, beta_be) || !Fr64::from_be(z, z_be)) return ZKP_OK;
+    Fr64 ac = alpha.from_mont(), bc = beta.from_mont(), zc = z.from_mont();
+    // A = com - z G + alpha pi_X + beta pi_Y ;  e(A, g2) e(-pi_X, [tau_x]_2) e(-pi_Y, [tau_y]_2) == 1
+    G1J a = com.add(g1_generator().mul(zc.v, 4).neg()).add(px.mul(ac.v, 4)).add(py.mul(bc.v, 4));
+    std::vector<G1AffineHost> ps = {g1_affine_host(a), g1_affine_host(px.neg()), g1_affine_host(py.neg())};
+    std::vector<const G2Lines*> qs = {&ctx->lines_g2, &ctx->lines_tau, &ctx->lines_tau_y};
     *valid = pairing_product_is_one(ps, qs) ? 1 : 0;
     return ZKP_OK;
 }

@@ -82,6 +82,8 @@ struct zkp_ctx {
     std::vector<zkp::host::G1J> scale_points; // [R_i(tau_y)]_1
     bool have_g2_tau = false;
     zkp::host::G2J g2_tau;                    // [tau_x]_2
+    bool have_g2_tau_y = false;
+    zkp::host::G2J g2_tau_y;                  // [tau_y]_2 (Pianist master verification only)
     // scratch
     zkp::DevBuf scalars, fr_a, fr_b, fr_c, flush;
     zkp::MsmWorkspace ws;                     // lane 0 workspace (runs on `stream`)
@@ -98,6 +100,7 @@ struct zkp_ctx {
     bool use_precomp = true;
     zkp::DevBuf scratch_xyzz, scratch_fq;
     uint32_t shard_domain_log = 0;            // log2 of the full domain when the rows are point-range shards
+    uint32_t shard_index = 0;                 // which slice [shard * 2^log_n, (shard+1) * 2^log_n) of that domain
     uint64_t launches = 0;                    // kernels launched by this context (bench accounting)
     // per-size domain tables: wt[k] = w_n^(2^k) (k <= log_n), tw[e] = w_n^e (e < n/2, built on demand)
     struct Domain {
@@ -109,7 +112,7 @@ struct zkp_ctx {
     zkp::DevBuf small, partials, ntt_tmp, fixed_base;  // device scalars / block partial sums / NTT scratch / [d*256^w]G table
     uint8_t* h_small = nullptr;               // pinned scratch (>= 256 B)
     // pairing data fixed per SRS
-    zkp::host::G2Lines lines_g2, lines_tau;
+    zkp::host::G2Lines lines_g2, lines_tau, lines_tau_y;
     bool have_lines = false;
     // kernel timing of the dominant kernel (k_accumulate level 0), enabled by the bench entries
     bool time_acc = false;

@@ -244,6 +244,7 @@ int zkp_srs_set_shape(zkp_ctx* ctx, uint32_t log_n, uint32_t log_machines) {
     ctx->log_n = log_n;
     ctx->log_m = log_machines;
     ctx->shard_domain_log = log_n;
+    ctx->shard_index = 0;
     drop_precomp(ctx, -1);
     ctx->precomp.clear();
     ctx->row_loaded.assign((size_t)1 << log_machines, 0);

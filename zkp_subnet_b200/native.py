@@ -42,9 +42,15 @@ _SIGNATURES = {
     "zkp_srs_generate": [_ctxp, _u8p, _u8p, ctypes.c_uint32, ctypes.c_uint32],
     "zkp_srs_generate_shard": [_ctxp, _u8p, _u8p, ctypes.c_uint32, ctypes.c_uint32, ctypes.c_uint32, ctypes.c_uint32],
     "zkp_g1_sum": [_u8p, ctypes.c_size_t, _u8p],
+    "zkp_shard_eval_partial": [_ctxp, ctypes.c_uint32, _u8p, ctypes.c_size_t, _u8p, _u8p],
+    "zkp_shard_eval_combine": [_u8p, ctypes.c_size_t, ctypes.c_uint32, _u8p, _u8p],
+    "zkp_shard_open_partial": [_ctxp, ctypes.c_uint32, _u8p, ctypes.c_size_t, _u8p, _u8p, _u8p],
     "zkp_srs_set_shape": [_ctxp, ctypes.c_uint32, ctypes.c_uint32],
     "zkp_srs_import_row": [_ctxp, ctypes.c_uint32, _u8p, ctypes.c_size_t, _u8p],
     "zkp_srs_import_g2_tau": [_ctxp, _u8p],
+    "zkp_srs_import_g2_tau_y": [_ctxp, _u8p],
+    "zkp_master_open_y": [_ctxp, _u8p, ctypes.c_size_t, _u8p, _u8p, _u8p],
+    "zkp_master_verify": [_ctxp, _u8p, _u8p, _u8p, _u8p, _u8p, _u8p, ctypes.POINTER(ctypes.c_int)],
     "zkp_srs_export_row": [_ctxp, ctypes.c_uint32, _u8p, ctypes.c_size_t],
     "zkp_srs_save": [_ctxp, ctypes.c_char_p],
     "zkp_srs_load": [_ctxp, ctypes.c_char_p],
@@ -188,6 +194,9 @@ class Context:
     def srs_import_g2_tau(self, tau_x: int) -> None:
         check(lib().zkp_srs_import_g2_tau(self._h, tau_x.to_bytes(32, "big")))
 
+    def srs_import_g2_tau_y(self, tau_y: int) -> None:
+        check(lib().zkp_srs_import_g2_tau_y(self._h, tau_y.to_bytes(32, "big")))
+
     def srs_export_row(self, row: int, n: int) -> bytes:
         out = ctypes.create_string_buffer(96 * n)
         check(lib().zkp_srs_export_row(self._h, row, out, n))
@@ -226,6 +235,30 @@ class Context:
     def worker_verify(self, i: int, proof48: bytes, alpha_be: bytes, eval_be: bytes, commitment48: bytes) -> bool:
         valid = ctypes.c_int(0)
         check(lib().zkp_worker_verify(self._h, i, proof48, alpha_be, eval_be, commitment48, ctypes.byref(valid)))
+        return bool(valid.value)
+
+    # ---- opening split by point range over several GPUs (see include/zkp_b200.h)
+    def shard_eval_partial(self, i: int, slice_be: bytes, x_be: bytes) -> bytes:
+        out = ctypes.create_string_buffer(32)
+        check(lib().zkp_shard_eval_partial(self._h, i, _arg(slice_be), len(slice_be) // 32, x_be, out))
+        return out.raw
+
+    def shard_open_partial(self, i: int, slice_be: bytes, x_be: bytes, y_be: bytes) -> bytes:
+        out = ctypes.create_string_buffer(48)
+        check(lib().zkp_shard_open_partial(self._h, i, _arg(slice_be), len(slice_be) // 32, x_be, y_be, out))
+        return out.raw
+
+    # ---- Pianist master node (aggregation is g1_sum; the Y-direction opening and the bivariate check are here)
+    def master_open_y(self, worker_evals_be: bytes, beta_be: bytes) -> Tuple[bytes, bytes]:
+        z = ctypes.create_string_buffer(32)
+        proof = ctypes.create_string_buffer(48)
+        check(lib().zkp_master_open_y(self._h, worker_evals_be, len(worker_evals_be) // 32, beta_be, z, proof))
+        return z.raw, proof.raw
+
+    def master_verify(self, commitment48: bytes, proof_x48: bytes, proof_y48: bytes, alpha_be: bytes, beta_be: bytes,
+                      z_be: bytes) -> bool:
+        valid = ctypes.c_int(0)
+        check(lib().zkp_master_verify(self._h, commitment48, proof_x48, proof_y48, alpha_be, beta_be, z_be, ctypes.byref(valid)))
         return bool(valid.value)
 
     def fft(self, vals_be: bytes, left: bool = True, inverse: bool = False) -> bytes:
@@ -361,6 +394,12 @@ def wire_decode_list(strs, out: Optional[PinnedBuffer] = None):
 def wire_encode_list(vals_be: bytes):
     """n x 32 bytes -> list of n unpadded base64 strings (43 chars each)."""
     return wire().zkp_wire_encode_list(vals_be, len(vals_be) // 32)
+
+
+def shard_eval_combine(partials_be: bytes, log_n: int, x_be: bytes) -> bytes:
+    out = ctypes.create_string_buffer(32)
+    check(lib().zkp_shard_eval_combine(partials_be, len(partials_be) // 32, log_n, x_be, out))
+    return out.raw
 
 
 def g1_sum(points48: bytes) -> bytes:

@@ -33,3 +33,18 @@ def combine_partials(parts: Sequence[bytes]) -> Tuple[bytes, ...]:
         raise ValueError("nothing to combine")
     k = len(parts[0]) // 48
     return tuple(native.g1_sum(b"".join(p[48 * j:48 * (j + 1)] for p in parts)) for j in range(k))
+
+
+def sharded_commit_open(dist, ctx, row: int, slice_be: bytes, x_be: bytes, log_n: int, device: str = "cpu") -> Tuple[bytes, bytes, bytes]:
+    """Commit + open of ONE polynomial of 2^log_n evaluations split by point range over the ranks of `dist`
+    (rank g holds the shard made by srs_generate_shard(..., g, log2(world)) and `slice_be`, its slice of the
+    evaluations).  Two small all-gathers (80 and 48 bytes per rank), no collective inside a kernel; every rank
+    returns the same (commitment, y, proof).  `ctx` needs worker_commit / shard_eval_partial / shard_open_partial."""
+    com_g = ctx.worker_commit(row, slice_be)
+    s_g = ctx.shard_eval_partial(row, slice_be, x_be)
+    parts = gather_bytes(dist, com_g + s_g, device)
+    com = native.g1_sum(b"".join(p[:48] for p in parts))
+    y = native.shard_eval_combine(b"".join(p[48:80] for p in parts), log_n, x_be)
+    pi_g = ctx.shard_open_partial(row, slice_be, x_be, y)
+    proof = native.g1_sum(b"".join(gather_bytes(dist, pi_g, device)))
+    return com, y, proof
