@@ -146,6 +146,10 @@ int zkp_bench_commit_open(zkp_ctx* ctx, uint32_t row, const uint8_t* poly_be, si
                           int reps, int flush_l2, float* ms_per_iter, float* ms_msm_kernel, uint32_t* launches,
                           uint8_t commitment48[48], uint8_t eval_be[32], uint8_t proof48[48]);
 int zkp_bench_last_kernel_ms(zkp_ctx* ctx, float* ms);
+/* stage timeline of one commit+open (CUDA events between the pipeline stages of both lanes): text lines
+ * "<lane> <stage> <ms since request start>" and a final "host total <ms>" */
+int zkp_bench_trace(zkp_ctx* ctx, uint32_t row, const uint8_t* poly_be, size_t n, const uint8_t x_be[32], int warm,
+                    char* out, size_t out_cap);
 int zkp_bench_ntt(zkp_ctx* ctx, size_t n, int reps, int inverse, float* ms_per_ntt);
 /* roofline denominators measured live: chip-wide IMAD.WIDE.U32 issue rate and dependent-chain Fq products/s */
 int zkp_bench_peaks(zkp_ctx* ctx, double* imad_wide_per_s, double* fq_mul_per_s);

@@ -77,10 +77,13 @@ int open_device(zkp_ctx* ctx, cudaStream_t st, const Fr* d_f, uint32_t n, const 
     ZKP_CUDA(cudaMemsetAsync(small_at<uint32_t>(ctx, SM_HIT), 0xff, 4, st));
     k_open_pass1<<<blocks, 128, 0, st>>>(d_f, n, E, to_dev(x), dom->wt.as<Fr>(), to_dev(dom->w_inv), ctx->fr_b.as<Fr>(),
                                          ctx->partials.as<Fr>(), small_at<uint32_t>(ctx, SM_HIT), 0);
+    trace_mark(ctx, 1, st, "open_pass1");
     k_fr_reduce<<<1, 256, 0, st>>>(ctx->partials.as<Fr>(), blocks, small_at<Fr>(ctx, SM_S1));
     k_open_y<<<1, 32, 0, st>>>(d_f, log_n, to_dev(x), to_dev(dom->n_inv), small_at<Fr>(ctx, SM_S1), small_at<uint32_t>(ctx, SM_HIT),
                                small_at<Fr>(ctx, SM_Y));
+    trace_mark(ctx, 1, st, "open_y");
     k_open_pass2<<<blocks2, 256, 0, st>>>(d_f, ctx->fr_b.as<Fr>(), n, small_at<Fr>(ctx, SM_Y), ctx->fr_c.as<Fr>());
+    trace_mark(ctx, 1, st, "open_pass2");
     // x in the domain (rare): q_m = -sum_{j != m} q_j w^(j-m); the kernels are no-ops otherwise
     k_open_fix_partial<<<blocks2, 256, 0, st>>>(ctx->fr_c.as<Fr>(), n, dom->wt.as<Fr>(), small_at<uint32_t>(ctx, SM_HIT),
                                                 ctx->partials.as<Fr>());
@@ -149,8 +152,10 @@ int commit_open_resident(zkp_ctx* ctx, uint32_t i, size_t n, const Fr64& x, uint
         rc = msm_device_enqueue(ctx, 0, i, ctx->scalars.as<uint32_t>(), SCALAR_BE, n, &plan_c);
         if (rc) return rc;
     }
+    trace_mark(ctx, 1, s1, "open_begin");
     rc = open_device(ctx, s1, ctx->fr_a.as<Fr>(), (uint32_t)n, x);
     if (rc) return rc;
+    trace_mark(ctx, 1, s1, "open_field_kernels");
     rc = msm_device_enqueue(ctx, 1, i, ctx->fr_c.as<uint32_t>(), SCALAR_MONT, n, &plan_o);
     if (rc) return rc;
     rc = fetch_y_enqueue(ctx, s1);
@@ -896,6 +901,54 @@ int zkp_bench_commit_open(zkp_ctx* ctx, uint32_t row, const uint8_t* poly_be, si
     *ms_per_iter = (float)(total / reps);
     if (ms_msm_kernel) *ms_msm_kernel = ctx->acc_count ? (float)(ctx->acc_ms_total / ctx->acc_count) : 0.f;
     if (launches) *launches = (uint32_t)((ctx->launches - launches0) / reps);
+    return rc;
+}
+
+// One traced commit+open (polynomial resident, after `warm` untraced runs): writes "lane stage t_ms" lines, t
+// relative to the start of the request, where each line says when everything up to and including that stage
+// had finished on that lane's stream; last line "host total <ms>" is the host wall time of the request.
+int zkp_bench_trace(zkp_ctx* ctx, uint32_t row, const uint8_t* poly_be, size_t n, const uint8_t x_be[32], int warm, char* out,
+                    size_t out_cap) {
+    Fr64 x;
+    int rc = open_checks(ctx, row, poly_be, n, x_be, &x);
+    if (rc) return rc;
+    if (!out || out_cap < 64) return fail(ZKP_ERR_ARG, "bad argument");
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    DeviceGuard g(ctx->device);
+    rc = upload_poly(ctx, poly_be, n);
+    if (rc) return rc;
+    uint8_t c48[48], y32[32], p48[48];
+    for (int r = 0; r < warm && !rc; r++) rc = commit_open_resident(ctx, row, n, x, c48, y32, p48);
+    if (rc) return rc;
+    flush_l2(ctx);
+    ZKP_CUDA(cudaStreamSynchronize(ctx->stream));
+    ZKP_CUDA(cudaStreamSynchronize(ctx->stream2));
+    cudaEvent_t base;
+    ZKP_CUDA(cudaEventCreate(&base));
+    ctx->trace.clear();
+    ctx->trace_on = true;
+    auto t0 = std::chrono::steady_clock::now();
+    cudaEventRecord(base, ctx->stream);
+    rc = commit_open_resident(ctx, row, n, x, c48, y32, p48);
+    double host_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    ctx->trace_on = false;
+    std::string text;
+    for (auto& tp : ctx->trace) {
+        float ms = 0;
+        cudaEventSynchronize(tp.ev);
+        cudaEventElapsedTime(&ms, base, tp.ev);
+        char line[128];
+        snprintf(line, sizeof(line), "%d %s %.4f\n", tp.lane, tp.name, ms);
+        text += line;
+        cudaEventDestroy(tp.ev);
+    }
+    ctx->trace.clear();
+    cudaEventDestroy(base);
+    char line[64];
+    snprintf(line, sizeof(line), "host total %.4f\n", host_ms);
+    text += line;
+    if (text.size() + 1 > out_cap) return fail(ZKP_ERR_ARG, "trace buffer too small");
+    memcpy(out, text.c_str(), text.size() + 1);
     return rc;
 }
 

@@ -120,4 +120,19 @@ struct zkp_ctx {
     double acc_ms_total = 0;
     uint64_t acc_count = 0;
     float last_acc_ms = 0;
+    // stage timeline (zkp_bench_trace): events recorded on the lanes' streams between pipeline stages
+    struct TracePoint { cudaEvent_t ev; int lane; const char* name; };
+    bool trace_on = false;
+    std::vector<TracePoint> trace;
 };
+
+namespace zkp {
+// marks "everything enqueued so far on this lane's stream has finished" under a stage name
+inline void trace_mark(zkp_ctx* ctx, int lane, cudaStream_t st, const char* name) {
+    if (!ctx->trace_on) return;
+    cudaEvent_t e;
+    if (cudaEventCreate(&e) != cudaSuccess) return;
+    cudaEventRecord(e, st);
+    ctx->trace.push_back({e, lane, name});
+}
+}  // namespace zkp

@@ -60,6 +60,14 @@ struct MsmPlan {
     uint32_t out_per_window = 0;      // bits_c + bits_r records per bucket window
 };
 constexpr uint32_t REDUCE_DIRECT_MAX = 1024;
+// tunables (compile-time so that experiments are separate builds): resident CTAs per SM the level-0
+// accumulation kernel is compiled for, and the slice length of the first slot level
+#ifndef ZKP_ACC_MIN_BLOCKS
+#define ZKP_ACC_MIN_BLOCKS 3
+#endif
+#ifndef ZKP_SLOT_L1
+#define ZKP_SLOT_L1 8
+#endif
 
 inline uint32_t ilog2_floor(uint32_t n) {
     uint32_t lg = 0;
@@ -89,7 +97,7 @@ inline MsmPlan msm_make_plan(uint32_t n, int sm_count, uint32_t c, bool precomp,
     while ((1ull << p.key_bits) <= p.discard) p.key_bits++;
     p.N = (size_t)n * p.W;
     // level 0: slice length chosen so that the grid is a whole number of waves of resident threads
-    const size_t resident = (size_t)sm_count * 384;
+    const size_t resident = (size_t)sm_count * 128 * ZKP_ACC_MIN_BLOCKS;
     // ~6 waves: long slices mean few slice-boundary partials for the slot levels, and because every
     // thread does the same work the last wave is as full as the first
     size_t waves = (p.N + resident * 48 - 1) / (resident * 48);
@@ -104,7 +112,10 @@ inline MsmPlan msm_make_plan(uint32_t n, int sm_count, uint32_t c, bool precomp,
         p.levels.push_back({items, L, threads});
         if (threads <= 1) break;
         items = threads * 2;
-        L = 8;  // shallow slot levels: every sequential addition costs ~17 us of latency
+        // shallow slot levels: every sequential addition costs ~17 us of latency.  For scalars that are not
+        // adversarial almost every slot run is one (tail_t, head_t+1) pair, so the first slot level can be
+        // made a single parallel addition per thread
+        L = lvl == 0 ? ZKP_SLOT_L1 : 8;
     }
     // reduction plan
     if (p.B > REDUCE_DIRECT_MAX) {
@@ -218,7 +229,7 @@ __device__ __forceinline__ G1Affine load_affine(const G1Affine* src) {
 // LEVEL0: items are (key, point index|sign) entries, points gathered from the affine SRS row.
 // else  : items are (key|flags, XYZZ) slots written by the previous level.
 template <bool LEVEL0>
-__global__ void __launch_bounds__(128, LEVEL0 ? 3 : 1)
+__global__ void __launch_bounds__(128, LEVEL0 ? ZKP_ACC_MIN_BLOCKS : 1)
 k_accumulate(const uint32_t* __restrict__ keys, const uint32_t* __restrict__ vals,
              const G1Affine* __restrict__ points, const G1Xyzz* __restrict__ slots_in, size_t items,
              uint32_t L, uint32_t discard, G1Xyzz* __restrict__ buckets, uint32_t* __restrict__ slot_keys,
@@ -334,6 +345,74 @@ k_rowcol_sums(const G1Xyzz* __restrict__ in, uint32_t log_rows, uint32_t log_col
         for (uint32_t lo = lane; lo < cols; lo += RC_LANES) {
             G1Xyzz p = load_xyzz(x + ((size_t)hi << log_cols) + lo);
             acc.add(p);
+        }
+    }
+    sh[threadIdx.x] = acc;
+    __syncthreads();
+    for (int st = RC_LANES / 2; st > 0; st >>= 1) {
+        if ((int)lane < st) {
+            G1Xyzz a = sh[threadIdx.x];
+            a.add(sh[threadIdx.x + st]);
+            sh[threadIdx.x] = a;
+        }
+        __syncthreads();
+    }
+    if (lane == 0 && s < cols + rows)
+        store_xyzz(s < cols ? out_c + (size_t)w * cols + s : out_r + (size_t)w * rows + (s - cols), sh[threadIdx.x]);
+}
+
+// Balanced two-stage form of the same sums (used when the bucket array is large).  Stage 1: every sum is cut
+// into Q interleaved shares (share k takes elements k, k + Q, ...), ONE THREAD per share, so that all threads
+// do the same number of sequential additions and the whole stage is a single wave of resident CTAs (the
+// one-warp-per-sum kernel above gave row sums twice the depth of column sums and left SMs with 2 or 3 CTAs:
+// measured 1.0 ms at 2^19 buckets against 0.47 ms of multiply-issue time).  Stage 2: one warp per sum adds its
+// Q partials (<= 2 per lane) and finishes with 5 tree steps.
+// share index space per window: [0, cols * q_c) column shares, then rows * q_r row shares.
+__global__ void __launch_bounds__(128, 3)
+k_rowcol_partial(const G1Xyzz* __restrict__ in, uint32_t log_rows, uint32_t log_cols, uint32_t q_c, uint32_t q_r,
+                 G1Xyzz* __restrict__ part) {
+    const uint32_t rows = 1u << log_rows, cols = 1u << log_cols, w = blockIdx.y;
+    const uint32_t n_c = cols * q_c, total = n_c + rows * q_r;
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= total) return;
+    const G1Xyzz* x = in + ((size_t)w << (log_rows + log_cols));
+    G1Xyzz acc = G1Xyzz::infinity();
+    if (t < n_c) {
+        // adjacent threads -> adjacent columns (contiguous 192-byte records), share k = t / cols
+        const uint32_t s = t & (cols - 1), k = t >> log_cols;
+        for (uint32_t hi = k; hi < rows; hi += q_c) {
+            G1Xyzz p = load_xyzz(x + ((size_t)hi << log_cols) + s);
+            acc.add(p);
+        }
+    } else {
+        // row hi = u / q_r, share k = u % q_r takes lo = k, k + q_r, ... (adjacent threads -> adjacent records)
+        const uint32_t u = t - n_c, hi = u / q_r, k = u - hi * q_r;
+        for (uint32_t lo = k; lo < cols; lo += q_r) {
+            G1Xyzz p = load_xyzz(x + ((size_t)hi << log_cols) + lo);
+            acc.add(p);
+        }
+    }
+    store_xyzz(part + (size_t)w * total + t, acc);
+}
+__global__ void __launch_bounds__(RC_THREADS)
+k_rowcol_finish(const G1Xyzz* __restrict__ part, uint32_t log_rows, uint32_t log_cols, uint32_t q_c, uint32_t q_r,
+                G1Xyzz* __restrict__ out_c, G1Xyzz* __restrict__ out_r) {
+    __shared__ G1Xyzz sh[RC_THREADS];
+    const uint32_t rows = 1u << log_rows, cols = 1u << log_cols, w = blockIdx.y;
+    const uint32_t n_c = cols * q_c, total = n_c + rows * q_r;
+    const uint32_t lane = threadIdx.x % RC_LANES;
+    const uint32_t s = blockIdx.x * RC_SUMS + threadIdx.x / RC_LANES;
+    const G1Xyzz* p = part + (size_t)w * total;
+    G1Xyzz acc = G1Xyzz::infinity();
+    if (s < cols) {
+        for (uint32_t k = lane; k < q_c; k += RC_LANES) {
+            G1Xyzz v = load_xyzz(p + (size_t)k * cols + s);
+            acc.add(v);
+        }
+    } else if (s < cols + rows) {
+        for (uint32_t k = lane; k < q_r; k += RC_LANES) {
+            G1Xyzz v = load_xyzz(p + n_c + (size_t)(s - cols) * q_r + k);
+            acc.add(v);
         }
     }
     sh[threadIdx.x] = acc;

@@ -42,12 +42,14 @@ inline int msm_enqueue(zkp_ctx* ctx, int lane, const MsmPlan& plan, const uint32
     if (!ws.h_bad) ZKP_CUDA(cudaMallocHost(&ws.h_bad, 8));
 
     // 1. digits
+    trace_mark(ctx, lane, st, "msm_begin");
     ZKP_CUDA(ws.bad.ensure(8));
     ZKP_CUDA(cudaMemsetAsync(ws.bad.p, 0, 4, st));
     k_decompose<<<(plan.n + 255) / 256, 256, 0, st>>>(d_scalars, plan.n, plan.c, plan.W, plan.B, plan.discard, fmt,
                                                       plan.precomp ? 1 : 0, plan.win_stride, ws.keys_a.as<uint32_t>(),
                                                       ws.vals_a.as<uint32_t>(), ws.bad.as<uint32_t>());
     ctx->launches++;
+    trace_mark(ctx, lane, st, "decompose");
     // 2. sort by (window, bucket)
     size_t temp_bytes = 0;
     ZKP_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, temp_bytes, ws.keys_a.as<uint32_t>(), ws.keys_b.as<uint32_t>(),
@@ -57,6 +59,7 @@ inline int msm_enqueue(zkp_ctx* ctx, int lane, const MsmPlan& plan, const uint32
     ZKP_CUDA(cub::DeviceRadixSort::SortPairs(ws.cub_temp.p, temp_bytes, ws.keys_a.as<uint32_t>(), ws.keys_b.as<uint32_t>(),
                                              ws.vals_a.as<uint32_t>(), ws.vals_b.as<uint32_t>(), (int64_t)N, 0,
                                              (int)plan.key_bits, st));
+    trace_mark(ctx, lane, st, "sort");
     // 3. balanced accumulation, level by level
     ZKP_CUDA(cudaMemsetAsync(ws.buckets.p, 0, nb * sizeof(G1Xyzz), st));
     for (size_t l = 0; l < plan.levels.size(); l++) {
@@ -70,6 +73,7 @@ inline int msm_enqueue(zkp_ctx* ctx, int lane, const MsmPlan& plan, const uint32
                                                        last ? nullptr : ws.slot_keys[0].as<uint32_t>(),
                                                        last ? nullptr : ws.slot_pts[0].as<G1Xyzz>(), last);
             if (ctx->time_acc) cudaEventRecord(ev1, st);
+            trace_mark(ctx, lane, st, "accumulate_l0");
         } else {
             k_accumulate<false><<<blocks, 128, 0, st>>>(ws.slot_keys[l - 1].as<uint32_t>(), nullptr, nullptr,
                                                         ws.slot_pts[l - 1].as<G1Xyzz>(), lv.items, lv.L, plan.discard,
@@ -79,6 +83,7 @@ inline int msm_enqueue(zkp_ctx* ctx, int lane, const MsmPlan& plan, const uint32
         }
         ctx->launches++;
     }
+    trace_mark(ctx, lane, st, "accumulate_slots");
     // 4. reduction -> per bucket window: bits_c column bit planes, then bits_r row bit planes
     const uint32_t opw = plan.out_per_window;
     ZKP_CUDA(ws.sums_out.ensure(out_records * sizeof(G1Xyzz)));
@@ -87,8 +92,25 @@ inline int msm_enqueue(zkp_ctx* ctx, int lane, const MsmPlan& plan, const uint32
         const uint32_t rows = 1u << plan.log_rows, cols = 1u << plan.log_cols;
         ZKP_CUDA(ws.sums_a.ensure((size_t)plan.Wb * cols * sizeof(G1Xyzz)));
         ZKP_CUDA(ws.sums_b.ensure((size_t)plan.Wb * rows * sizeof(G1Xyzz)));
-        k_rowcol_sums<<<dim3((cols + rows + RC_SUMS - 1) / RC_SUMS, plan.Wb), RC_THREADS, 0, st>>>(
-            ws.buckets.as<G1Xyzz>(), plan.log_rows, plan.log_cols, ws.sums_a.as<G1Xyzz>(), ws.sums_b.as<G1Xyzz>());
+        // shares per sum so that one wave of resident threads (3 CTAs of 128 per SM) covers all of them evenly
+        const size_t elems = 2ull * plan.Wb * rows * cols, resident = (size_t)ctx->sm_count * 384;
+        const uint32_t per_thread = (uint32_t)((elems + resident - 1) / resident);
+        uint32_t q_c = per_thread ? (rows + per_thread - 1) / per_thread : 1, q_r = per_thread ? (cols + per_thread - 1) / per_thread : 1;
+        if (q_c > 2 * RC_LANES) q_c = 2 * RC_LANES;
+        if (q_r > 2 * RC_LANES) q_r = 2 * RC_LANES;
+        if (q_c >= 4 && q_r >= 4) {
+            const uint32_t shares = cols * q_c + rows * q_r;
+            ZKP_CUDA(ws.pool.ensure((size_t)plan.Wb * shares * sizeof(G1Xyzz)));
+            k_rowcol_partial<<<dim3((shares + 127) / 128, plan.Wb), 128, 0, st>>>(ws.buckets.as<G1Xyzz>(), plan.log_rows, plan.log_cols,
+                                                                               q_c, q_r, ws.pool.as<G1Xyzz>());
+            k_rowcol_finish<<<dim3((cols + rows + RC_SUMS - 1) / RC_SUMS, plan.Wb), RC_THREADS, 0, st>>>(
+                ws.pool.as<G1Xyzz>(), plan.log_rows, plan.log_cols, q_c, q_r, ws.sums_a.as<G1Xyzz>(), ws.sums_b.as<G1Xyzz>());
+            ctx->launches++;
+        } else {
+            k_rowcol_sums<<<dim3((cols + rows + RC_SUMS - 1) / RC_SUMS, plan.Wb), RC_THREADS, 0, st>>>(
+                ws.buckets.as<G1Xyzz>(), plan.log_rows, plan.log_cols, ws.sums_a.as<G1Xyzz>(), ws.sums_b.as<G1Xyzz>());
+        }
+        trace_mark(ctx, lane, st, "rowcol_sums");
         k_bit_sums<<<dim3(plan.bits_c + plan.bits_r, plan.Wb), TAIL_THREADS, 0, st>>>(
             ws.sums_a.as<G1Xyzz>(), cols, plan.bits_c, ws.sums_b.as<G1Xyzz>(), rows, d_out, opw);
         ctx->launches += 2;
@@ -97,8 +119,10 @@ inline int msm_enqueue(zkp_ctx* ctx, int lane, const MsmPlan& plan, const uint32
                                                                         d_out, opw);
         ctx->launches++;
     }
+    trace_mark(ctx, lane, st, "bit_sums");
     ZKP_CUDA(cudaMemcpyAsync(ws.h_window, d_out, sizeof(G1Xyzz) * out_records, cudaMemcpyDeviceToHost, st));
     ZKP_CUDA(cudaMemcpyAsync(ws.h_bad, ws.bad.p, 4, cudaMemcpyDeviceToHost, st));
+    trace_mark(ctx, lane, st, "d2h");
     return ZKP_OK;
 }
 

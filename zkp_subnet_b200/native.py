@@ -10,7 +10,7 @@ import os
 from typing import Optional, Tuple
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libzkp_b200.so")
+LIB_PATH = os.environ.get("ZKP_B200_LIB") or os.path.join(_HERE, "libzkp_b200.so")  # env override: tuning builds
 
 ZKP_OK = 0
 ZKP_ERR_ARG = -1
@@ -71,6 +71,7 @@ _SIGNATURES = {
     "zkp_bench_commit_open": [_ctxp, ctypes.c_uint32, _u8p, ctypes.c_size_t, _u8p, ctypes.c_int, ctypes.c_int,
                               ctypes.POINTER(ctypes.c_float), ctypes.POINTER(ctypes.c_float),
                               ctypes.POINTER(ctypes.c_uint32), _u8p, _u8p, _u8p],
+    "zkp_bench_trace": [_ctxp, ctypes.c_uint32, _u8p, ctypes.c_size_t, _u8p, ctypes.c_int, ctypes.c_char_p, ctypes.c_size_t],
     "zkp_bench_ntt": [_ctxp, ctypes.c_size_t, ctypes.c_int, ctypes.c_int, ctypes.POINTER(ctypes.c_float)],
     "zkp_bench_last_kernel_ms": [_ctxp, ctypes.POINTER(ctypes.c_float)],
     "zkp_bench_peaks": [_ctxp, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_double)],
@@ -312,6 +313,16 @@ class Context:
         check(lib().zkp_bench_commit_open(self._h, row, _arg(poly_be), len(poly_be) // 32, x_be, reps, int(flush_l2),
                                           ctypes.byref(ms), ctypes.byref(ms_k), ctypes.byref(launches), com, y, proof))
         return ms.value, ms_k.value, launches.value, com.raw, y.raw, proof.raw
+
+    def bench_trace(self, row: int, poly_be: bytes, x_be: bytes, warm: int = 2):
+        """[(lane, stage, ms since request start)] of one commit+open, plus ("host", "total", ms)."""
+        buf = ctypes.create_string_buffer(8192)
+        check(lib().zkp_bench_trace(self._h, row, _arg(poly_be), len(poly_be) // 32, x_be, warm, buf, len(buf)))
+        rows = []
+        for line in buf.value.decode().splitlines():
+            a, b, c = line.split()
+            rows.append((a, b, float(c)))
+        return rows
 
     def bench_last_kernel_ms(self) -> float:
         ms = ctypes.c_float()
