@@ -14,7 +14,8 @@
  * known answer and the SURVEY section 8c vectors (tests/test_oracle.py).
  *
  * Deliberately different from the product: 64-bit limbs with unsigned __int128, Jacobian
- * coordinates, unsigned-window Pippenger, iNTT + synthetic division for the quotient.
+ * coordinates (madd-2007-bl mixed addition), unsigned-window Pippenger run as (window, point chunk) jobs on a
+ * pthread queue, iNTT + synthetic division for the quotient.
  *
  * Build: make -C oracle   (gcc -O2 -shared -fPIC -pthread)
  */
@@ -113,7 +114,32 @@ static int is_zero_n(const u64* a, int n) {
 
 /* ---- Fq ---- */
 typedef struct { u64 v[QL]; } fq;
-static void fq_mul(fq* r, const fq* a, const fq* b) { mont_mul(r->v, a->v, b->v, Q_MOD, Q_INV, QL); }
+/* fixed-size CIOS for the 6-limb base field (p < 2^383: one spare limb suffices); ~1.5x the generic loop */
+static inline __attribute__((always_inline)) void mont_mul6(u64* r, const u64* a, const u64* b) {
+    u64 t0 = 0, t1 = 0, t2 = 0, t3 = 0, t4 = 0, t5 = 0, t6 = 0;
+#define FQ_ROW(bi) do { u128 c; u64 m; \
+    c = (u128)a[0] * (bi) + t0; t0 = (u64)c; c >>= 64; \
+    c += (u128)a[1] * (bi) + t1; t1 = (u64)c; c >>= 64; \
+    c += (u128)a[2] * (bi) + t2; t2 = (u64)c; c >>= 64; \
+    c += (u128)a[3] * (bi) + t3; t3 = (u64)c; c >>= 64; \
+    c += (u128)a[4] * (bi) + t4; t4 = (u64)c; c >>= 64; \
+    c += (u128)a[5] * (bi) + t5; t5 = (u64)c; c >>= 64; \
+    t6 += (u64)c; \
+    m = t0 * Q_INV; \
+    c = ((u128)m * Q_MOD[0] + t0) >> 64; \
+    c += (u128)m * Q_MOD[1] + t1; t0 = (u64)c; c >>= 64; \
+    c += (u128)m * Q_MOD[2] + t2; t1 = (u64)c; c >>= 64; \
+    c += (u128)m * Q_MOD[3] + t3; t2 = (u64)c; c >>= 64; \
+    c += (u128)m * Q_MOD[4] + t4; t3 = (u64)c; c >>= 64; \
+    c += (u128)m * Q_MOD[5] + t5; t4 = (u64)c; c >>= 64; \
+    c += t6; t5 = (u64)c; t6 = (u64)(c >> 64); } while (0)
+    FQ_ROW(b[0]); FQ_ROW(b[1]); FQ_ROW(b[2]); FQ_ROW(b[3]); FQ_ROW(b[4]); FQ_ROW(b[5]);
+#undef FQ_ROW
+    u64 t[6] = {t0, t1, t2, t3, t4, t5};
+    if (t6 || ge_n(t, Q_MOD, 6)) sub_n(r, t, Q_MOD, 6);
+    else memcpy(r, t, sizeof(t));
+}
+static void fq_mul(fq* r, const fq* a, const fq* b) { mont_mul6(r->v, a->v, b->v); }
 static void fq_sqr(fq* r, const fq* a) { fq_mul(r, a, a); }
 static void fq_add(fq* r, const fq* a, const fq* b) { mod_add(r->v, a->v, b->v, Q_MOD, QL); }
 static void fq_sub(fq* r, const fq* a, const fq* b) { mod_sub(r->v, a->v, b->v, Q_MOD, QL); }
@@ -251,10 +277,30 @@ static void g1j_from_affine(g1j* r, const g1a* p) {
     if (p->inf) { g1j_set_inf(r); return; }
     r->x = p->x; r->y = p->y; fq_from_u64(&r->z, 1);
 }
+/* Jacobian + affine, madd-2007-bl (7M + 4S); every exceptional case falls back to the general formulas */
 static void g1j_add_affine(g1j* r, const g1j* p, const g1a* q) {
-    g1j t;
-    g1j_from_affine(&t, q);
-    g1j_add(r, p, &t);
+    if (q->inf) { *r = *p; return; }
+    if (g1j_is_inf(p)) { g1j_from_affine(r, q); return; }
+    fq z1z1, u2, s2, h, hh, i, j, rr, v, t;
+    fq_sqr(&z1z1, &p->z);
+    fq_mul(&u2, &q->x, &z1z1);
+    fq_mul(&s2, &q->y, &p->z); fq_mul(&s2, &s2, &z1z1);
+    fq_sub(&h, &u2, &p->x);
+    fq_sub(&rr, &s2, &p->y);
+    if (fq_is_zero(&h)) {
+        g1j tq; g1j_from_affine(&tq, q);
+        if (fq_is_zero(&rr)) g1j_double(r, &tq); else g1j_set_inf(r);
+        return;
+    }
+    fq_add(&rr, &rr, &rr);
+    fq_sqr(&hh, &h);
+    fq_add(&i, &hh, &hh); fq_add(&i, &i, &i);
+    fq_mul(&j, &h, &i);
+    fq_mul(&v, &p->x, &i);
+    fq x3; fq_sqr(&x3, &rr); fq_sub(&x3, &x3, &j); fq_sub(&x3, &x3, &v); fq_sub(&x3, &x3, &v);
+    fq y3; fq_sub(&y3, &v, &x3); fq_mul(&y3, &rr, &y3); fq_mul(&t, &p->y, &j); fq_add(&t, &t, &t); fq_sub(&y3, &y3, &t);
+    fq z3; fq_add(&z3, &p->z, &h); fq_sqr(&z3, &z3); fq_sub(&z3, &z3, &z1z1); fq_sub(&z3, &z3, &hh);
+    r->x = x3; r->y = y3; r->z = z3;
 }
 static void g1j_to_affine(g1a* r, const g1j* p) {
     if (g1j_is_inf(p)) { memset(r, 0, sizeof(*r)); r->inf = 1; return; }
@@ -308,7 +354,9 @@ static void g1_deserialize96(g1a* p, const uint8_t in[96]) {
 }
 
 /* ------------------------------------------------------------------------------------------ */
-/* Pippenger MSM, unsigned windows, per-thread point ranges                                     */
+/* Pippenger MSM, unsigned windows.  Parallel over (window, point chunk) jobs taken from a shared queue: */
+/* every job fills its own bucket array from its chunk, reduces it with the running-sum trick and      */
+/* leaves one window partial; the caller folds the windows with c doublings each (Horner).             */
 /* ------------------------------------------------------------------------------------------ */
 static unsigned window_bits(size_t n) {
     unsigned lg = 0;
@@ -323,55 +371,69 @@ static unsigned get_window(const fr* k, unsigned lo, unsigned c) {
     if (off + c > 64 && limb + 1 < RL) w |= k->v[limb + 1] << (64 - off);
     return (unsigned)(w & (((u64)1 << c) - 1));
 }
-static void msm_serial(g1j* out, const g1a* pts, const fr* scal, size_t n) {
-    g1j_set_inf(out);
-    if (n == 0) return;
-    unsigned c = window_bits(n);
-    unsigned nwin = (255 + c - 1) / c;
+/* sum over points [lo, hi) of digit_w(scalar) * point */
+static void msm_window_chunk(g1j* out, const g1a* pts, const fr* scal, size_t lo, size_t hi, unsigned w, unsigned c, g1j* buckets) {
     size_t nb = ((size_t)1 << c) - 1;
-    g1j* buckets = (g1j*)malloc(sizeof(g1j) * nb);
-    for (int w = (int)nwin - 1; w >= 0; w--) {
-        for (unsigned d = 0; d < c; d++) g1j_double(out, out);
-        for (size_t b = 0; b < nb; b++) g1j_set_inf(&buckets[b]);
-        for (size_t i = 0; i < n; i++) {
-            unsigned d = get_window(&scal[i], w * c, c);
-            if (d && !pts[i].inf) g1j_add_affine(&buckets[d - 1], &buckets[d - 1], &pts[i]);
-        }
-        g1j run, sum;
-        g1j_set_inf(&run); g1j_set_inf(&sum);
-        for (size_t b = nb; b-- > 0;) {
-            g1j_add(&run, &run, &buckets[b]);
-            g1j_add(&sum, &sum, &run);
-        }
-        g1j_add(out, out, &sum);
+    for (size_t b = 0; b < nb; b++) g1j_set_inf(&buckets[b]);
+    for (size_t i = lo; i < hi; i++) {
+        unsigned d = get_window(&scal[i], w * c, c);
+        if (d && !pts[i].inf) g1j_add_affine(&buckets[d - 1], &buckets[d - 1], &pts[i]);
+    }
+    g1j run, sum;
+    g1j_set_inf(&run); g1j_set_inf(&sum);
+    for (size_t b = nb; b-- > 0;) {
+        g1j_add(&run, &run, &buckets[b]);
+        g1j_add(&sum, &sum, &run);
+    }
+    *out = sum;
+}
+typedef struct {
+    const g1a* pts; const fr* scal; size_t n; unsigned c, nwin, chunks;
+    g1j* partial;            /* nwin * chunks window partials */
+    volatile long next;      /* job queue head */
+} msm_shared;
+static void* msm_worker(void* arg) {
+    msm_shared* sh = (msm_shared*)arg;
+    g1j* buckets = (g1j*)malloc(sizeof(g1j) * (((size_t)1 << sh->c) - 1 + 1));
+    for (;;) {
+        long job = __sync_fetch_and_add(&sh->next, 1);
+        if (job >= (long)(sh->nwin * sh->chunks)) break;
+        unsigned w = (unsigned)(job / sh->chunks), k = (unsigned)(job % sh->chunks);
+        size_t lo = sh->n * k / sh->chunks, hi = sh->n * (k + 1) / sh->chunks;
+        msm_window_chunk(&sh->partial[job], sh->pts, sh->scal, lo, hi, w, sh->c, buckets);
     }
     free(buckets);
-}
-typedef struct { const g1a* pts; const fr* scal; size_t n; g1j out; } msm_job;
-static void* msm_worker(void* arg) {
-    msm_job* j = (msm_job*)arg;
-    msm_serial(&j->out, j->pts, j->scal, j->n);
     return NULL;
 }
 static void msm_parallel(g1j* out, const g1a* pts, const fr* scal, size_t n, int threads) {
+    g1j_set_inf(out);
+    if (n == 0) return;
     if (threads < 1) threads = 1;
-    if ((size_t)threads > n / 64 + 1) threads = (int)(n / 64 + 1);
-    msm_job* jobs = (msm_job*)calloc(threads, sizeof(msm_job));
+    msm_shared sh;
+    sh.pts = pts; sh.scal = scal; sh.n = n; sh.next = 0;
+    /* enough jobs to keep every thread busy: split the points when there are fewer windows than ~3x threads */
+    sh.chunks = 1;
+    size_t per = n;
+    for (;;) {
+        sh.c = window_bits(per);
+        sh.nwin = (255 + sh.c - 1) / sh.c;
+        if (sh.nwin * sh.chunks >= 3u * (unsigned)threads || per < 1024 || threads == 1) break;
+        sh.chunks *= 2;
+        per = n / sh.chunks;
+    }
+    sh.partial = (g1j*)calloc((size_t)sh.nwin * sh.chunks, sizeof(g1j));
     pthread_t* th = (pthread_t*)calloc(threads, sizeof(pthread_t));
-    for (int t = 0; t < threads; t++) {
-        size_t lo = n * t / threads, hi = n * (t + 1) / threads;
-        jobs[t].pts = pts + lo; jobs[t].scal = scal + lo; jobs[t].n = hi - lo;
-        if (t) pthread_create(&th[t], NULL, msm_worker, &jobs[t]);
+    for (int t = 1; t < threads; t++) pthread_create(&th[t], NULL, msm_worker, &sh);
+    msm_worker(&sh);
+    for (int t = 1; t < threads; t++) pthread_join(th[t], NULL);
+    for (int w = (int)sh.nwin - 1; w >= 0; w--) {
+        for (unsigned d = 0; d < sh.c; d++) g1j_double(out, out);
+        for (unsigned k = 0; k < sh.chunks; k++) g1j_add(out, out, &sh.partial[(size_t)w * sh.chunks + k]);
     }
-    msm_worker(&jobs[0]);
-    *out = jobs[0].out;
-    for (int t = 1; t < threads; t++) {
-        pthread_join(th[t], NULL);
-        g1j_add(out, out, &jobs[t].out);
-    }
-    free(jobs); free(th);
+    free(sh.partial); free(th);
 }
 
+/* ------------------------------------------------------------------------------------------ */
 /* ------------------------------------------------------------------------------------------ */
 /* NTT (natural order in/out), Horner, quotient                                                 */
 /* ------------------------------------------------------------------------------------------ */
