@@ -53,3 +53,20 @@ def test_g1_xyzz_formulas(tmp_path):
         assert got == exp, k
         n += 1
     assert n >= 17
+
+
+def test_fq_inverse_binary_gcd(tmp_path):
+    """csrc/fq_inv.cuh (chunked binary GCD, the division of the batched-affine bucket accumulation) on random,
+    2^k, p - 2^k, small and short inputs: x * inv(x) == 1 (both in Montgomery form), canonical output, inv(0) = 0."""
+    out = subprocess.check_output([build("inv_host_test", tmp_path), "3000"]).decode().split("\n")
+    Rm = (1 << 384) % o.P
+    n = 0
+    for i in range(0, len(out) - 1, 2):
+        x, v = int(out[i].split()[1], 16), int(out[i + 1].split()[1], 16)
+        assert v < o.P
+        if x == 0:
+            assert v == 0
+        else:
+            assert x * v % o.P == Rm * Rm % o.P, hex(x)
+        n += 1
+    assert n == 3001

@@ -88,7 +88,29 @@ struct Fp {
         uint32_t even[N], odd[N];
         Fp r;
         if constexpr (N == 12) {
-#if defined(__CUDA_ARCH__) && !defined(ZKP_UNROLL_MONT_ROWS)
+#if defined(__CUDA_ARCH__) && defined(ZKP_MONT_ROWS_PER_ITER)
+            // Uniform rolled form: ALL rows are generic rows on zero-initialised accumulators, ZKP_MONT_ROWS_PER_ITER
+            // (even, divides 12) rows per trip.  Every trip ends by physically moving the loop-carried
+            // accumulator and b registers (~26 MOV / IMAD.MOV per trip, part of them on the multiply pipe --
+            // ncu, profiles/), so fewer, longer trips trade code size for moves and loop back-edges.
+            constexpr int RPI = ZKP_MONT_ROWS_PER_ITER;
+            static_assert(N % RPI == 0 && RPI % 2 == 0, "rows per iteration must be even and divide N");
+#pragma unroll
+            for (int k = 0; k < N; k++) even[k] = odd[k] = 0;
+            uint32_t bb[N];
+#pragma unroll
+            for (int k = 0; k < N; k++) bb[k] = b.v[k];
+#pragma unroll 1
+            for (int i = 0; i < N; i += RPI) {
+#pragma unroll
+                for (int k = 0; k < RPI; k += 2) {
+                    chains::fq_row(even, odd, a.v, bb[k]);
+                    chains::fq_row(odd, even, a.v, bb[k + 1]);
+                }
+#pragma unroll
+                for (int k = 0; k + RPI < N; k++) bb[k] = bb[k + RPI];
+            }
+#elif defined(__CUDA_ARCH__) && !defined(ZKP_UNROLL_MONT_ROWS)
             // All 12 rows as a ROLLED loop of row pairs (a generic row on zero accumulators is the first
             // row): the bucket-accumulation kernel inlines ten of these products and was instruction-fetch
             // bound when fully unrolled (ncu: stall_no_instruction 1.7 per issue, profiles/).  b's limbs
