@@ -158,6 +158,10 @@ int zkp_set_msm_window(zkp_ctx* ctx, uint32_t c);
 /* 1 (default): keep per-row fixed-base tables [2^(c w)] P_i in HBM (W x the row) so that all digit positions
  * share one bucket set; 0: classic per-window buckets.  Results are identical either way. */
 int zkp_set_msm_mode(zkp_ctx* ctx, int fixed_base_tables);
+/* rounds of batched-affine pairwise additions in front of the XYZZ bucket accumulation (6 instead of 10 field
+ * products per addition): -1 (default) = automatic, on for large MSMs; 0 = off; 1..6 = forced.  Results are
+ * identical for every setting. */
+int zkp_set_msm_affine_rounds(zkp_ctx* ctx, int rounds);
 int zkp_msm_info(zkp_ctx* ctx, size_t n, uint32_t* c, uint32_t* windows, uint64_t* fq_muls);
 
 /* ---- pairing check exposed for tests: prod e(P_k, Q_k) == 1, P compressed G1 (48 B), Q affine G2 as

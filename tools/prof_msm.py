@@ -6,6 +6,8 @@ lg = int(sys.argv[1]) if len(sys.argv) > 1 else 20
 mode = sys.argv[2] if len(sys.argv) > 2 else "msm"
 reps = int(sys.argv[3]) if len(sys.argv) > 3 else 2
 ctx = native.Context(0)
+if os.environ.get('ZKP_AFFINE_ROUNDS'):
+    ctx.set_msm_affine_rounds(int(os.environ['ZKP_AFFINE_ROUNDS']))
 ctx.srs_generate(1927409816240961209460912649124, 0x1234567890ABCDEF1234567890ABCDEF, lg, 0)
 n = 1 << lg
 sc = ctx.random_poly(0xB200 + lg, n)

@@ -148,6 +148,11 @@ int commit_open_resident(zkp_ctx* ctx, uint32_t i, size_t n, const Fr64& x, uint
     cudaStream_t s0 = ctx->stream, s1 = ctx->stream2;
     ZKP_CUDA(cudaEventRecord(ctx->ev_ready, s0));
     ZKP_CUDA(cudaStreamWaitEvent(s1, ctx->ev_ready, 0));
+    struct DualLane {  // both MSMs of this request will share the device: plan_for may pick batched-affine rounds
+        zkp_ctx* c;
+        explicit DualLane(zkp_ctx* ctx, bool on) : c(ctx) { c->dual_lane = on; }
+        ~DualLane() { c->dual_lane = false; }
+    } dual(ctx, commitment48 != nullptr);
     if (commitment48) {
         rc = msm_device_enqueue(ctx, 0, i, ctx->scalars.as<uint32_t>(), SCALAR_BE, n, &plan_c);
         if (rc) return rc;

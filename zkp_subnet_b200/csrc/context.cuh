@@ -7,7 +7,7 @@
 
 #include "../../include/zkp_b200.h"
 #include "host/pairing.hpp"
-#include "msm.cuh"
+#include "msm_affine.cuh"
 
 namespace zkp {
 
@@ -51,6 +51,9 @@ struct DevBuf {
 struct MsmWorkspace {
     DevBuf keys_a, keys_b, vals_a, vals_b, cub_temp, buckets, next_a, next_b, pool, sums_a, sums_b, sums_out, bad;
     std::vector<DevBuf> slot_keys, slot_pts;
+    // batched-affine rounds: per-round bucket starts, scan input, ping-pong point lists, keys of the last list,
+    // prefix-product scratch
+    DevBuf aff_start[8], aff_len, aff_pts[2], aff_keys, aff_scratch;
     G1Xyzz* h_window = nullptr;  // pinned, W records
     size_t h_window_cap = 0;
     uint32_t* h_bad = nullptr;   // pinned
@@ -61,6 +64,8 @@ struct MsmWorkspace {
             b->release();
         for (auto& b : slot_keys) b.release();
         for (auto& b : slot_pts) b.release();
+        for (auto& b : aff_start) b.release();
+        for (DevBuf* b : {&aff_len, &aff_pts[0], &aff_pts[1], &aff_keys, &aff_scratch}) b->release();
         if (h_window) cudaFreeHost(h_window);
         h_window = nullptr;
         h_window_cap = 0;
@@ -94,6 +99,8 @@ struct zkp_ctx {
     cudaEvent_t ev_ready = nullptr;           // polynomial uploaded + converted (lane 0 -> lane 1)
     cudaEvent_t ev_acc2_0 = nullptr, ev_acc2_1 = nullptr;
     uint32_t c_override = 0;
+    int affine_rounds_override = -1;          // -1: automatic (see plan_for); 0..6: forced (tests, tuning)
+    bool dual_lane = false;                   // set while a commit+open enqueues its two MSMs (plan_for reads it)
     // fixed-base tables: per SRS row, [2^(c w)] P_i for w < W (slice w at w * 2^log_n); built lazily
     struct Precomp { zkp::DevBuf table; uint32_t c = 0, W = 0; };
     std::vector<Precomp> precomp;

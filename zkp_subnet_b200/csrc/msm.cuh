@@ -49,6 +49,7 @@ struct MsmPlan {
     uint32_t discard = 0;  // key of zero digits
     bool precomp = false;  // vals index the table [2^(c w)] P_i at w * win_stride + i
     uint32_t win_stride = 0;
+    uint32_t neg_offset = 0; // precomp: the table holds a second, negated half at +neg_offset (sign folded into the index)
     size_t N = 0;          // entries = n * W
     // accumulation levels: level 0 consumes entries, level k>0 consumes the slots of level k-1
     struct Level { size_t items; uint32_t L; size_t threads; };
@@ -58,7 +59,13 @@ struct MsmPlan {
     uint32_t log_rows = 0, log_cols = 0;
     uint32_t bits_c = 0, bits_r = 0;  // bit planes of the column / row weights
     uint32_t out_per_window = 0;      // bits_c + bits_r records per bucket window
+    // batched-affine pre-reduction (msm_affine.cuh): rounds of pairwise additions before the XYZZ accumulation;
+    // bound[r] = upper bound on the list length after r rounds (bound[0] = N), acc_items = bound[affine_rounds]
+    uint32_t affine_rounds = 0;
+    size_t bound[8] = {0};
+    size_t acc_items = 0;
 };
+constexpr uint32_t AFFINE_MAX_ROUNDS = 6;
 constexpr uint32_t REDUCE_DIRECT_MAX = 1024;
 // tunables (compile-time so that experiments are separate builds): resident CTAs per SM the level-0
 // accumulation kernel is compiled for, and the slice length of the first slot level
@@ -83,7 +90,7 @@ inline uint32_t msm_window_bits(uint32_t n, bool precomp) {
     return (uint32_t)c;
 }
 
-inline MsmPlan msm_make_plan(uint32_t n, int sm_count, uint32_t c, bool precomp, uint32_t win_stride) {
+inline MsmPlan msm_make_plan(uint32_t n, int sm_count, uint32_t c, bool precomp, uint32_t win_stride, uint32_t affine_rounds = 0) {
     MsmPlan p;
     p.n = n;
     p.c = c;
@@ -96,15 +103,19 @@ inline MsmPlan msm_make_plan(uint32_t n, int sm_count, uint32_t c, bool precomp,
     p.key_bits = 1;
     while ((1ull << p.key_bits) <= p.discard) p.key_bits++;
     p.N = (size_t)n * p.W;
+    p.affine_rounds = affine_rounds > AFFINE_MAX_ROUNDS ? AFFINE_MAX_ROUNDS : affine_rounds;
+    p.bound[0] = p.N;
+    for (uint32_t r = 0; r < p.affine_rounds; r++) p.bound[r + 1] = (p.bound[r] + p.discard + 1) / 2;  // sum ceil(len/2) <= (N + buckets)/2
+    p.acc_items = p.bound[p.affine_rounds];
     // level 0: slice length chosen so that the grid is a whole number of waves of resident threads
     const size_t resident = (size_t)sm_count * 128 * ZKP_ACC_MIN_BLOCKS;
     // ~6 waves: long slices mean few slice-boundary partials for the slot levels, and because every
     // thread does the same work the last wave is as full as the first
-    size_t waves = (p.N + resident * 48 - 1) / (resident * 48);
+    size_t waves = (p.acc_items + resident * 48 - 1) / (resident * 48);
     if (waves < 1) waves = 1;
-    uint32_t L0 = (uint32_t)((p.N + waves * resident - 1) / (waves * resident));
+    uint32_t L0 = (uint32_t)((p.acc_items + waves * resident - 1) / (waves * resident));
     if (L0 < 8) L0 = 8;
-    size_t items = p.N;
+    size_t items = p.acc_items;
     uint32_t L = L0;
     for (int lvl = 0;; lvl++) {
         size_t shift = lvl ? 1 : 0;  // slot levels slice on odd indices (see k_accumulate)
@@ -143,7 +154,7 @@ enum { SCALAR_LE = 0, SCALAR_BE = 1, SCALAR_MONT = 2 };
 // precomp: every digit position shares the bucket set (key = |digit| - 1) and val indexes the table
 // [2^(c w)] P_i at w * win_stride + i.
 __global__ void k_decompose(const uint32_t* __restrict__ scalars, uint32_t n, uint32_t c, uint32_t W,
-                            uint32_t B, uint32_t discard, int fmt, int precomp, uint32_t win_stride,
+                            uint32_t B, uint32_t discard, int fmt, int precomp, uint32_t win_stride, uint32_t neg_offset,
                             uint32_t* __restrict__ keys, uint32_t* __restrict__ vals, uint32_t* __restrict__ bad) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
@@ -190,7 +201,8 @@ __global__ void k_decompose(const uint32_t* __restrict__ scalars, uint32_t n, ui
         carry = neg;
         size_t o = (size_t)w * n + i;
         keys[o] = mag ? (precomp ? 0u : w * B) + mag - 1 : discard;
-        vals[o] = (precomp ? w * win_stride + i : i) | (neg << 31);
+        // with a negated table half the sign selects the half and no kernel ever negates a y-coordinate
+        vals[o] = neg_offset ? w * win_stride + i + (neg ? neg_offset : 0u) : ((precomp ? w * win_stride + i : i) | (neg << 31));
     }
 }
 
@@ -292,8 +304,9 @@ k_accumulate(const uint32_t* __restrict__ keys, const uint32_t* __restrict__ val
         }
         last_key = k;
         if (LEVEL0) {
-            uint32_t v = vals[i];
-            if (i + 1 < end) {
+            // vals == nullptr: the items ARE the points (output of the batched-affine rounds), in list order
+            uint32_t v = vals ? vals[i] : (uint32_t)i;
+            if (vals && i + 1 < end) {
                 // the gather is a 96-byte random read of a table far larger than L2: pull the NEXT point
                 // towards L2 while this one is being added (no registers held, unlike a software pipeline)
                 const char* nx = reinterpret_cast<const char*>(points + (vals[i + 1] & 0x7fffffffu));
@@ -301,7 +314,8 @@ k_accumulate(const uint32_t* __restrict__ keys, const uint32_t* __restrict__ val
                 asm volatile("prefetch.global.L2 [%0];" ::"l"(nx + 64));
             }
             G1Affine p = load_affine(points + (v & 0x7fffffffu));
-            acc.madd(p, v >> 31);
+            if (v >> 31) p.y = p.y.neg();  // never taken with a negated table half (-(0, 0) stays the infinity marker)
+            acc.madd(p, 0);
         } else if (!(raw & KEY_EMPTY_FLAG)) {
             G1Xyzz p = load_xyzz(slots_in + i);
             acc.add(p);

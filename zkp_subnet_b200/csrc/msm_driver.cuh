@@ -1,5 +1,7 @@
 // Host driver of the MSM pipeline described in msm.cuh.
 #pragma once
+#include <cub/device/device_scan.cuh>
+
 #include "context.cuh"
 
 namespace zkp {
@@ -46,7 +48,7 @@ inline int msm_enqueue(zkp_ctx* ctx, int lane, const MsmPlan& plan, const uint32
     ZKP_CUDA(ws.bad.ensure(8));
     ZKP_CUDA(cudaMemsetAsync(ws.bad.p, 0, 4, st));
     k_decompose<<<(plan.n + 255) / 256, 256, 0, st>>>(d_scalars, plan.n, plan.c, plan.W, plan.B, plan.discard, fmt,
-                                                      plan.precomp ? 1 : 0, plan.win_stride, ws.keys_a.as<uint32_t>(),
+                                                      plan.precomp ? 1 : 0, plan.win_stride, plan.neg_offset, ws.keys_a.as<uint32_t>(),
                                                       ws.vals_a.as<uint32_t>(), ws.bad.as<uint32_t>());
     ctx->launches++;
     trace_mark(ctx, lane, st, "decompose");
@@ -60,6 +62,55 @@ inline int msm_enqueue(zkp_ctx* ctx, int lane, const MsmPlan& plan, const uint32
                                              ws.vals_a.as<uint32_t>(), ws.vals_b.as<uint32_t>(), (int64_t)N, 0,
                                              (int)plan.key_bits, st));
     trace_mark(ctx, lane, st, "sort");
+    // 2b. batched-affine rounds: pairwise additions inside every bucket, 6 Fq products each instead of 10
+    const uint32_t* acc_keys = ws.keys_b.as<uint32_t>();
+    const uint32_t* acc_vals = ws.vals_b.as<uint32_t>();
+    const G1Affine* acc_points = d_points;
+    if (plan.affine_rounds) {
+        const uint32_t nbk = plan.discard, R = plan.affine_rounds;
+        for (uint32_t r = 0; r <= R; r++) ZKP_CUDA(ws.aff_start[r].ensure(((size_t)nbk + 1) * 4));
+        ZKP_CUDA(ws.aff_len.ensure(((size_t)nbk + 1) * 4));
+        size_t scan_bytes = 0;
+        ZKP_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, scan_bytes, ws.aff_len.as<uint32_t>(), ws.aff_start[1].as<uint32_t>(), (int)(nbk + 1), st));
+        if (scan_bytes > temp_bytes) ZKP_CUDA(ws.cub_temp.ensure(scan_bytes));
+        k_bucket_bounds<<<(unsigned)((N + 1 + 255) / 256), 256, 0, st>>>(ws.keys_b.as<uint32_t>(), N, nbk, ws.aff_start[0].as<uint32_t>());
+        ctx->launches++;
+        const size_t resident = (size_t)ctx->sm_count * 128 * ZKP_AFF_MIN_BLOCKS;
+        for (uint32_t r = 0; r < R; r++) {
+            const size_t bound_out = plan.bound[r + 1];
+            k_next_len<<<(nbk + 1 + 255) / 256, 256, 0, st>>>(ws.aff_start[r].as<uint32_t>(), nbk, ws.aff_len.as<uint32_t>());
+            ZKP_CUDA(cub::DeviceScan::ExclusiveSum(ws.cub_temp.p, scan_bytes, ws.aff_len.as<uint32_t>(), ws.aff_start[r + 1].as<uint32_t>(),
+                                                   (int)(nbk + 1), st));
+            // outputs per thread: one wave of resident threads, but never fewer than a full inversion batch
+            uint32_t K = (uint32_t)((bound_out + resident - 1) / resident);
+            if (K < (uint32_t)AFF_KB) K = AFF_KB;
+            const size_t threads = (bound_out + K - 1) / K;
+            const unsigned blocks = (unsigned)((threads + 127) / 128);
+            const uint32_t total_threads = blocks * 128;
+            ZKP_CUDA(ws.aff_scratch.ensure((size_t)AFF_KB * total_threads * sizeof(Fq)));
+            ZKP_CUDA(ws.aff_pts[r & 1].ensure(bound_out * sizeof(G1Affine)));
+            const bool last = r + 1 == R;
+            uint32_t* out_keys = nullptr;
+            if (last) {
+                ZKP_CUDA(ws.aff_keys.ensure(bound_out * 4));
+                ZKP_CUDA(cudaMemsetAsync(ws.aff_keys.p, 0xff, bound_out * 4, st));  // unused tail = discard keys
+                out_keys = ws.aff_keys.as<uint32_t>();
+            }
+            if (r == 0)
+                k_affine_round<true><<<blocks, 128, 0, st>>>(ws.aff_start[0].as<uint32_t>(), ws.aff_start[1].as<uint32_t>(), nbk,
+                                                             ws.vals_b.as<uint32_t>(), d_points, ws.aff_pts[0].as<G1Affine>(), out_keys, K,
+                                                             ws.aff_scratch.as<Fq>(), total_threads, (uint32_t)ctx->sm_count);
+            else
+                k_affine_round<false><<<blocks, 128, 0, st>>>(ws.aff_start[r].as<uint32_t>(), ws.aff_start[r + 1].as<uint32_t>(), nbk, nullptr,
+                                                              ws.aff_pts[(r - 1) & 1].as<G1Affine>(), ws.aff_pts[r & 1].as<G1Affine>(), out_keys,
+                                                              K, ws.aff_scratch.as<Fq>(), total_threads, (uint32_t)ctx->sm_count);
+            ctx->launches += 3;
+        }
+        acc_keys = ws.aff_keys.as<uint32_t>();
+        acc_vals = nullptr;
+        acc_points = ws.aff_pts[(R - 1) & 1].as<G1Affine>();
+        trace_mark(ctx, lane, st, "affine_rounds");
+    }
     // 3. balanced accumulation, level by level
     ZKP_CUDA(cudaMemsetAsync(ws.buckets.p, 0, nb * sizeof(G1Xyzz), st));
     for (size_t l = 0; l < plan.levels.size(); l++) {
@@ -68,7 +119,7 @@ inline int msm_enqueue(zkp_ctx* ctx, int lane, const MsmPlan& plan, const uint32
         unsigned blocks = (unsigned)((lv.threads + 127) / 128);
         if (l == 0) {
             if (ctx->time_acc) cudaEventRecord(ev0, st);
-            k_accumulate<true><<<blocks, 128, 0, st>>>(ws.keys_b.as<uint32_t>(), ws.vals_b.as<uint32_t>(), d_points, nullptr,
+            k_accumulate<true><<<blocks, 128, 0, st>>>(acc_keys, acc_vals, acc_points, nullptr,
                                                        lv.items, lv.L, plan.discard, ws.buckets.as<G1Xyzz>(),
                                                        last ? nullptr : ws.slot_keys[0].as<uint32_t>(),
                                                        last ? nullptr : ws.slot_pts[0].as<G1Xyzz>(), last);

@@ -123,6 +123,15 @@ k_table_next(const G1Affine* __restrict__ in, size_t n, uint32_t c, G1Xyzz* __re
     out[i] = acc;
 }
 
+// out[i] = -in[i] (the negated half of a fixed-base table; the infinity marker (0, 0) maps to itself)
+__global__ void k_negate_points(const G1Affine* __restrict__ in, size_t n, G1Affine* __restrict__ out) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    G1Affine p = in[i];
+    p.y = p.y.neg();
+    out[i] = p;
+}
+
 // XYZZ -> affine with one inversion per run of E points (prefix products parked in scratch)
 __global__ void __launch_bounds__(128)
 k_xyzz_to_affine(const G1Xyzz* __restrict__ in, size_t n, uint32_t E, Fq* __restrict__ scratch, G1Affine* __restrict__ out) {

@@ -69,7 +69,8 @@ int ensure_precomp(zkp_ctx* ctx, uint32_t row, uint32_t c, bool* ok) {
     const uint32_t W = 255 / c + 1;
     if (pc.table.p && pc.c == c && pc.W == W) { *ok = true; return ZKP_OK; }
     const size_t n_row = (size_t)1 << ctx->log_n;
-    const size_t bytes = (size_t)W * n_row * sizeof(G1Affine);
+    // W slices [2^(c w)] P_i followed by the same W slices negated: the sign of a digit picks the half
+    const size_t bytes = 2 * (size_t)W * n_row * sizeof(G1Affine);
     pc.table.release();
     pc.c = 0;
     size_t free_b = 0, total_b = 0;
@@ -89,6 +90,8 @@ int ensure_precomp(zkp_ctx* ctx, uint32_t row, uint32_t c, bool* ok) {
                                                            tab + (size_t)w * n_row);
         ctx->launches += 2;
     }
+    k_negate_points<<<(unsigned)(((size_t)W * n_row + 255) / 256), 256, 0, st>>>(tab, (size_t)W * n_row, tab + (size_t)W * n_row);
+    ctx->launches++;
     ZKP_CUDA(cudaStreamSynchronize(st));
     ZKP_CUDA(cudaGetLastError());
     pc.c = c;
@@ -104,7 +107,22 @@ void drop_precomp(zkp_ctx* ctx, int row /* -1 = all */) {
 
 MsmPlan plan_for(zkp_ctx* ctx, size_t n, bool precomp) {
     uint32_t c = ctx->c_override ? ctx->c_override : msm_window_bits((uint32_t)n, precomp);
-    return msm_make_plan((uint32_t)n, ctx->sm_count, c, precomp, 1u << ctx->log_n);
+    // Batched-affine rounds (msm_affine.cuh).  Measured on B200 at 2^20: a round costs about as
+    // much per addition as the XYZZ kernel (it runs at ~50% of the multiply pipe, the XYZZ kernel at ~89%), so a
+    // lone MSM is 9% SLOWER with 3 rounds; when the two MSMs of a commit+open share the GPU on two streams the
+    // shorter, stall-heavy round kernels interleave better and 2 rounds make the pair 5% faster.  Automatic mode
+    // therefore uses 2 rounds only there, for lists of >= 2^22 entries with >= 16 entries per bucket.
+    uint32_t rounds = 0;
+    if (ctx->affine_rounds_override >= 0) {
+        rounds = (uint32_t)ctx->affine_rounds_override;
+    } else if (ctx->dual_lane) {
+        const uint32_t W = 255 / c + 1;
+        const size_t N = n * (size_t)W, buckets = (size_t)(precomp ? 1 : W) << (c - 1);
+        if (N >= ((size_t)1 << 22) && N >= 16 * buckets) rounds = 2;
+    }
+    MsmPlan plan = msm_make_plan((uint32_t)n, ctx->sm_count, c, precomp, 1u << ctx->log_n, rounds);
+    if (precomp) plan.neg_offset = plan.W << ctx->log_n;
+    return plan;
 }
 
 // Enqueue an MSM over row `row` with device-resident scalars on a lane (no host sync).
@@ -221,6 +239,13 @@ int zkp_set_msm_mode(zkp_ctx* ctx, int fixed_base_tables) {
     if (!ctx) return fail(ZKP_ERR_ARG, "null context");
     std::lock_guard<std::mutex> lk(ctx->mu);
     ctx->use_precomp = fixed_base_tables != 0;
+    return ZKP_OK;
+}
+
+int zkp_set_msm_affine_rounds(zkp_ctx* ctx, int rounds) {
+    if (!ctx || rounds < -1 || rounds > (int)AFFINE_MAX_ROUNDS) return fail(ZKP_ERR_ARG, "affine rounds must be -1 (auto) or 0..6");
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    ctx->affine_rounds_override = rounds;
     return ZKP_OK;
 }
 

@@ -77,6 +77,7 @@ _SIGNATURES = {
     "zkp_bench_peaks": [_ctxp, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_double)],
     "zkp_set_msm_mode": [_ctxp, ctypes.c_int],
     "zkp_set_msm_window": [_ctxp, ctypes.c_uint32],
+    "zkp_set_msm_affine_rounds": [_ctxp, ctypes.c_int],
     "zkp_msm_info": [_ctxp, ctypes.c_size_t, ctypes.POINTER(ctypes.c_uint32), ctypes.POINTER(ctypes.c_uint32),
                      ctypes.POINTER(ctypes.c_uint64)],
     "zkp_pairing_check": [_u8p, _u8p, ctypes.c_size_t, ctypes.POINTER(ctypes.c_int)],
@@ -293,6 +294,9 @@ class Context:
 
     def set_msm_mode(self, fixed_base_tables: bool) -> None:
         check(lib().zkp_set_msm_mode(self._h, int(fixed_base_tables)))
+
+    def set_msm_affine_rounds(self, rounds: int) -> None:
+        check(lib().zkp_set_msm_affine_rounds(self._h, rounds))
 
     def msm_info(self, n: int) -> Tuple[int, int, int]:
         c, w, m = ctypes.c_uint32(), ctypes.c_uint32(), ctypes.c_uint64()
