@@ -32,7 +32,7 @@ template <class F, class P> static void run(const char* name, int iters) {
         printf("field %s\n", name);
         pr("a", a); pr("b", b);
         pr("mul", a * b); pr("add", a + b); pr("sub", a - b); pr("neg", a.neg());
-        pr("sqr", a.sqr()); pr("tom", a.to_mont()); pr("fromm", a.from_mont());
+        pr("sqr", a.sqr()); pr("mul2", F::mul2(a, b, b, a.sqr())); pr("tom", a.to_mont()); pr("fromm", a.from_mont());
         if (it < 8) pr("inv", a.inverse());
     }
 }

@@ -32,7 +32,7 @@ def test_field_arithmetic(tmp_path):
         cur[k] = v
         a, b = cur.get("a"), cur.get("b")
         exp = {"mul": lambda: a * b * Ri % m, "add": lambda: (a + b) % m, "sub": lambda: (a - b) % m, "neg": lambda: (-a) % m,
-               "sqr": lambda: a * a * Ri % m, "tom": lambda: a * Rm % m, "fromm": lambda: a * Ri % m,
+               "sqr": lambda: a * a * Ri % m, "mul2": lambda: (a * b * Ri + b * (a * a * Ri % m) * Ri) % m, "tom": lambda: a * Rm % m, "fromm": lambda: a * Ri % m,
                "inv": lambda: (pow(a * Ri % m, -1, m) * Rm % m if a else 0)}
         if k in exp:
             assert exp[k]() == v, (k, hex(a), hex(b))

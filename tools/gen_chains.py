@@ -221,6 +221,108 @@ def gen_field(name, mod, n):
     return out
 
 
+
+def gen_extra(name, mod, n):
+    """Dedicated squaring rows and the fused two-product row (see ff.cuh: Fp::sqr, Fp::mul2)."""
+    m = limbs(mod, n)
+    inv = (-pow(mod, -1, 1 << 32)) % (1 << 32)
+    out = ""
+
+    def reduction(b, x, y):
+        b.operand("mi", "=r", "mi")
+        b.emit("mul.lo.u32", "mi", x(0), inv)
+        for j in range(0, n, 2):
+            b.emit("mad.lo.cc.u32" if j == 0 else "madc.lo.cc.u32", y(j), "mi", m[j + 1], y(j))
+            b.emit("madc.hi.cc.u32" if j < n - 2 else "madc.hi.u32", y(j + 1), "mi", m[j + 1], y(j + 1))
+        for j in range(0, n, 2):
+            b.emit("mad.lo.cc.u32" if j == 0 else "madc.lo.cc.u32", x(j), "mi", m[j], x(j))
+            b.emit("madc.hi.cc.u32", x(j + 1), "mi", m[j], x(j + 1))
+        b.emit("addc.u32", y(n - 1), y(n - 1), 0)
+
+    pre = "    uint32_t mi;\n"
+    # ---- squaring row i: multiplies a_i with the limbs of  a_i 2^(32 i) + 2 (a with limbs 0..i cleared);
+    #      positions below i are plain shifts of the accumulator (no multiply issued).  d = limbs of 2a.
+    for i in range(n):
+        b = Block()
+        x = lambda j: b.operand(f"x{j}", "+r", f"x[{j}]")
+        y = lambda j: b.operand(f"y{j}", "+r", f"y[{j}]")
+        for j in range(n):
+            x(j)
+        for j in range(n):
+            y(j)
+        b.operand("mi", "=r", "mi")
+        b.operand("bi", "r", f"a[{i}]")
+
+        def mult(j):
+            if j < i:
+                return None
+            if j == i:
+                return "bi"
+            if j == i + 1:  # lowest limb of 2 * (a with limbs 0..i cleared): no bit carried in from a_i
+                return b.operand(f"e{j}", "r", f"(a[{j}] << 1)")
+            return b.operand(f"d{j}", "r", f"d[{j}]")
+
+        b.emit("add.cc.u32", x(0), x(0), y(1))
+        for j in range(0, n - 2, 2):
+            op = mult(j + 1)
+            if op:
+                b.emit("madc.lo.cc.u32", y(j), op, "bi", y(j + 2))
+                b.emit("madc.hi.cc.u32", y(j + 1), op, "bi", y(j + 3))
+            else:
+                b.emit("addc.cc.u32", y(j), y(j + 2), 0)
+                b.emit("addc.cc.u32", y(j + 1), y(j + 3), 0)
+        op = mult(n - 1)  # always present: n - 1 >= i
+        b.emit("madc.lo.cc.u32", y(n - 2), op, "bi", 0)
+        b.emit("madc.hi.u32", y(n - 1), op, "bi", 0)
+        first = True
+        for j in range(0, n, 2):
+            op = mult(j)
+            if not op:
+                continue
+            b.emit("mad.lo.cc.u32" if first else "madc.lo.cc.u32", x(j), op, "bi", x(j))
+            b.emit("madc.hi.cc.u32", x(j + 1), op, "bi", x(j + 1))
+            first = False
+        if not first:
+            b.emit("addc.u32", y(n - 1), y(n - 1), 0)
+        reduction(b, x, y)
+        out += func(f"{name}_sqr_row_{i}(uint32_t* x, uint32_t* y, const uint32_t* a, const uint32_t* d)", [pre, b])
+
+    # ---- fused row: x, y += a * bi + c * di, then one reduction step (a*b + c*d with ONE Montgomery reduction)
+    b = Block()
+    x = lambda j: b.operand(f"x{j}", "+r", f"x[{j}]")
+    y = lambda j: b.operand(f"y{j}", "+r", f"y[{j}]")
+    a = lambda j: b.operand(f"a{j}", "r", f"a[{j}]")
+    c = lambda j: b.operand(f"c{j}", "r", f"c[{j}]")
+    for j in range(n):
+        x(j)
+    for j in range(n):
+        y(j)
+    b.operand("mi", "=r", "mi")
+    b.operand("bi", "r", "bi")
+    b.operand("di", "r", "di")
+    b.emit("add.cc.u32", x(0), x(0), y(1))
+    for j in range(0, n - 2, 2):
+        b.emit("madc.lo.cc.u32", y(j), a(j + 1), "bi", y(j + 2))
+        b.emit("madc.hi.cc.u32", y(j + 1), a(j + 1), "bi", y(j + 3))
+    b.emit("madc.lo.cc.u32", y(n - 2), a(n - 1), "bi", 0)
+    b.emit("madc.hi.u32", y(n - 1), a(n - 1), "bi", 0)
+    for j in range(0, n, 2):
+        b.emit("mad.lo.cc.u32" if j == 0 else "madc.lo.cc.u32", x(j), a(j), "bi", x(j))
+        b.emit("madc.hi.cc.u32", x(j + 1), a(j), "bi", x(j + 1))
+    b.emit("addc.u32", y(n - 1), y(n - 1), 0)
+    # second product, no shift
+    for j in range(0, n, 2):
+        b.emit("mad.lo.cc.u32" if j == 0 else "madc.lo.cc.u32", y(j), c(j + 1), "di", y(j))
+        b.emit("madc.hi.cc.u32" if j < n - 2 else "madc.hi.u32", y(j + 1), c(j + 1), "di", y(j + 1))
+    for j in range(0, n, 2):
+        b.emit("mad.lo.cc.u32" if j == 0 else "madc.lo.cc.u32", x(j), c(j), "di", x(j))
+        b.emit("madc.hi.cc.u32", x(j + 1), c(j), "di", x(j + 1))
+    b.emit("addc.u32", y(n - 1), y(n - 1), 0)
+    reduction(b, x, y)
+    out += func(f"{name}_row2(uint32_t* x, uint32_t* y, const uint32_t* a, uint32_t bi, const uint32_t* c, uint32_t di)", [pre, b])
+    return out
+
+
 hdr = """// GENERATED by tools/gen_chains.py -- do not edit.
 // One inline-asm statement per carry chain (see the generator's docstring).
 #pragma once
@@ -230,7 +332,7 @@ namespace zkp {
 namespace chains {
 
 """
-body = gen_field("fq", P, 12) + gen_field("fr", R, 8)
+body = gen_field("fq", P, 12) + gen_extra("fq", P, 12) + gen_field("fr", R, 8)
 path = os.path.join(os.path.dirname(__file__), "..", "zkp_subnet_b200", "csrc", "mont_chains.cuh")
 open(path, "w").write(hdr + body + "}  // namespace chains\n}  // namespace zkp\n")
 print("wrote", os.path.abspath(path))

@@ -118,6 +118,54 @@ __global__ void k_faddsub(F* out, const F* in, int iters) {
     out[tid] = x + y;
 }
 
+// One Fq product followed by ADDS dependent Fq additions (~40 alu-pipe instructions each): is alu work hidden
+// under the multiply pipe at the occupancy of the real kernels (12 warps/SM)?
+template <int ADDS>
+__global__ void k_fmul_adds(Fq* out, const Fq* in, int iters) {
+    int tid = blockIdx.x * blockDim.x + threadIdx.x;
+    Fq x = in[0], y = in[1], z = in[1];
+    x.v[0] += tid; x.v[11] &= 0x0fffffffu;
+    for (int it = 0; it < iters; it++) {
+        x = x * y;
+#pragma unroll
+        for (int k = 0; k < ADDS; k++) z = z + x;
+    }
+    out[tid] = x + z;
+}
+// FP64 pipe: dependent DFMA chains, alone and interleaved 1:1 with IMAD.WIDE chains
+template <int ILP>
+__global__ void k_dfma(double* out, double m, double c) {
+    double acc[ILP];
+#pragma unroll
+    for (int k = 0; k < ILP; k++) acc[k] = threadIdx.x * 1e-3 + k;
+    for (int it = 0; it < ITERS; it++) {
+#pragma unroll
+        for (int k = 0; k < ILP; k++) acc[k] = fma(acc[k], m, c);
+    }
+    double s = 0;
+#pragma unroll
+    for (int k = 0; k < ILP; k++) s += acc[k];
+    out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+template <int ILP>
+__global__ void k_dfma_plus_wide(double* out, double m, double c, uint32_t mi) {
+    double acc[ILP];
+    uint64_t w[ILP];
+#pragma unroll
+    for (int k = 0; k < ILP; k++) { acc[k] = threadIdx.x * 1e-3 + k; w[k] = threadIdx.x * 0x9e3779b97f4a7c15ull + k; }
+    for (int it = 0; it < ITERS; it++) {
+#pragma unroll
+        for (int k = 0; k < ILP; k++) {
+            acc[k] = fma(acc[k], m, c);
+            w[k] = (uint64_t)(uint32_t)w[k] * mi + w[k];
+        }
+    }
+    double s = 0;
+#pragma unroll
+    for (int k = 0; k < ILP; k++) s += acc[k] + (double)(w[k] & 0xff);
+    out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
 struct Timer {
     cudaEvent_t a, b;
     Timer() { cudaEventCreate(&a); cudaEventCreate(&b); }
@@ -171,6 +219,21 @@ int main(int argc, char** argv) {
         RUN("fr_mul_ilp1", 1.0 * iters, k_fmul<Fr, 1><<<blocks, threads>>>((Fr*)fq_out, (Fr*)fq_in, iters))
         RUN("fr_mul_ilp2", 2.0 * iters, k_fmul<Fr, 2><<<blocks, threads>>>((Fr*)fq_out, (Fr*)fq_in, iters))
         RUN("fq_addsub", 2.0 * iters, k_faddsub<Fq><<<blocks, threads>>>(fq_out, fq_in, iters))
+    }
+    for (int wps : {12, 32}) {
+        int threads = 128, blocks = sms * wps * 32 / threads;
+        double nthreads = (double)threads * blocks;
+        int iters = 512;
+        RUN("fq_mul_plus_0_adds", 1.0 * iters, k_fmul_adds<0><<<blocks, threads>>>(fq_out, fq_in, iters))
+        RUN("fq_mul_plus_1_adds", 1.0 * iters, k_fmul_adds<1><<<blocks, threads>>>(fq_out, fq_in, iters))
+        RUN("fq_mul_plus_3_adds", 1.0 * iters, k_fmul_adds<3><<<blocks, threads>>>(fq_out, fq_in, iters))
+        RUN("fq_mul_plus_6_adds", 1.0 * iters, k_fmul_adds<6><<<blocks, threads>>>(fq_out, fq_in, iters))
+    }
+    for (int wps : {16, 64}) {
+        int threads = 256, blocks = sms * wps * 32 / threads;
+        double nthreads = (double)threads * blocks;
+        RUN("dfma_ilp8", 8.0 * ITERS, k_dfma<8><<<blocks, threads>>>((double*)out, 1.0000001, 1e-9))
+        RUN("dfma_plus_wide_ilp4(pairs)", 4.0 * ITERS, k_dfma_plus_wide<4><<<blocks, threads>>>((double*)out, 1.0000001, 1e-9, 0x9e3779b1u))
     }
     CK(cudaDeviceSynchronize());
     // correctness spot check of the device Fq product against the host emulation of the same code

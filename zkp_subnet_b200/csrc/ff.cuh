@@ -154,7 +154,72 @@ struct Fp {
         }
         return r;
     }
-    ZKP_HD Fp sqr() const { return *this * *this; }
+    // Dedicated squaring (Fq): row i multiplies a_i with (a_i, 2a_{i+1}, .., 2a_{N-1}) only -- N(N+1)/2 = 78
+    // products instead of 144, plus the same 156 of the reduction: 234 wide multiply-accumulates instead of 300.
+    // 2a < 2^382 fits the 12 limbs.  Fully unrolled (every row has its own shape).
+    ZKP_HD Fp sqr() const {
+        if constexpr (N == 12) {
+            uint32_t even[N], odd[N], d[N];
+#pragma unroll
+            for (int k = 0; k < N; k++) even[k] = odd[k] = 0;
+            d[0] = v[0] << 1;
+#pragma unroll
+            for (int k = 1; k < N; k++) d[k] = (v[k] << 1) | (v[k - 1] >> 31);
+            chains::fq_sqr_row_0(even, odd, v, d);
+            chains::fq_sqr_row_1(odd, even, v, d);
+            chains::fq_sqr_row_2(even, odd, v, d);
+            chains::fq_sqr_row_3(odd, even, v, d);
+            chains::fq_sqr_row_4(even, odd, v, d);
+            chains::fq_sqr_row_5(odd, even, v, d);
+            chains::fq_sqr_row_6(even, odd, v, d);
+            chains::fq_sqr_row_7(odd, even, v, d);
+            chains::fq_sqr_row_8(even, odd, v, d);
+            chains::fq_sqr_row_9(odd, even, v, d);
+            chains::fq_sqr_row_10(even, odd, v, d);
+            chains::fq_sqr_row_11(odd, even, v, d);
+            Fp r;
+            chains::fq_merge(r.v, odd, even);
+            chains::fq_reduce_once(r.v, 0);
+            return r;
+        } else {
+            return *this * *this;
+        }
+    }
+    // a*b + c*d with ONE Montgomery reduction (Fq): every row adds a*b_i and c*d_i before its reduction step,
+    // 2*144 + 156 = 444 wide multiply-accumulates instead of 600 for two products, and no separate addition.
+    // Inputs in [0, p); the accumulator stays below a + c + p < 3p and the result below 1.2p before the final
+    // conditional subtraction.
+    static ZKP_HD Fp mul2(const Fp& a, const Fp& b, const Fp& c, const Fp& d) {
+        if constexpr (N == 12) {
+            uint32_t even[N], odd[N];
+#pragma unroll
+            for (int k = 0; k < N; k++) even[k] = odd[k] = 0;
+#if defined(__CUDA_ARCH__)
+            uint32_t bb[N], dd[N];
+#pragma unroll
+            for (int k = 0; k < N; k++) { bb[k] = b.v[k]; dd[k] = d.v[k]; }
+#pragma unroll 1
+            for (int i = 0; i < N; i += 2) {
+                chains::fq_row2(even, odd, a.v, bb[0], c.v, dd[0]);
+                chains::fq_row2(odd, even, a.v, bb[1], c.v, dd[1]);
+#pragma unroll
+                for (int k = 0; k < N - 2; k++) { bb[k] = bb[k + 2]; dd[k] = dd[k + 2]; }
+            }
+#else
+#pragma unroll
+            for (int i = 0; i < N; i += 2) {
+                chains::fq_row2(even, odd, a.v, b.v[i], c.v, d.v[i]);
+                chains::fq_row2(odd, even, a.v, b.v[i + 1], c.v, d.v[i + 1]);
+            }
+#endif
+            Fp r;
+            chains::fq_merge(r.v, odd, even);
+            chains::fq_reduce_once(r.v, 0);
+            return r;
+        } else {
+            return a * b + c * d;
+        }
+    }
 
     // ---------------------------------------------------------------- Montgomery domain
     ZKP_HD Fp to_mont() const { return *this * r2(); }

@@ -49,7 +49,7 @@ struct G1Xyzz {
         Fq xx = px.sqr();
         Fq m = xx.dbl() + xx;
         r.x = m.sqr() - s.dbl();
-        r.y = m * (s - r.x) - w * py;
+        r.y = Fq::mul2(m, s - r.x, w, py.neg());  // m (s - x3) - w y with one reduction
         r.zz = v;
         r.zzz = w;
         return r;
@@ -66,7 +66,7 @@ struct G1Xyzz {
         Fq xx = x.sqr();
         Fq m = xx.dbl() + xx;
         r.x = m.sqr() - s.dbl();
-        r.y = m * (s - r.x) - w * y;
+        r.y = Fq::mul2(m, s - r.x, w, y.neg());
         r.zz = v * zz;
         r.zzz = w * zzz;
         return r;
@@ -92,7 +92,7 @@ struct G1Xyzz {
         Fq ppp = p * pp;
         Fq q = x * pp;
         Fq x3 = r.sqr() - ppp - q.dbl();
-        y = r * (q - x3) - y * ppp;
+        y = Fq::mul2(r, q - x3, ppp, y.neg());  // r (q - x3) - y ppp: two products, one Montgomery reduction
         x = x3;
         zz = zz * pp;
         zzz = zzz * ppp;
@@ -121,7 +121,7 @@ struct G1Xyzz {
         Fq ppp = p * pp;
         Fq q = u1 * pp;
         Fq x3 = r.sqr() - ppp - q.dbl();
-        y = r * (q - x3) - s1 * ppp;
+        y = Fq::mul2(r, q - x3, ppp, s1.neg());
         x = x3;
         zz = zz * o.zz * pp;
         zzz = zzz * o.zzz * ppp;
