@@ -95,8 +95,8 @@ def test_batched_affine_rounds_vs_oracle(gpu_ctx, rounds):
 
 
 def test_batched_affine_commit_open_full_size(gpu_ctx):
-    """2^20 commit+open: automatic mode (2 rounds on the two-lane path), rounds forced off and 3 rounds forced on
-    give identical bytes, and the proof verifies."""
+    """2^20 commit+open: default (no batched-affine rounds), 2 and 3 rounds forced on give identical bytes, and
+    the proof verifies."""
     log_n = 20
     n = 1 << log_n
     gpu_ctx.srs_generate(TAU_X, TAU_Y, log_n, 0)
@@ -104,7 +104,7 @@ def test_batched_affine_commit_open_full_size(gpu_ctx):
     x = gpu_ctx.random_point(0xAFF2)
     try:
         auto = gpu_ctx.worker_commit_open(0, f, x)
-        gpu_ctx.set_msm_affine_rounds(0)
+        gpu_ctx.set_msm_affine_rounds(2)
         assert gpu_ctx.worker_commit_open(0, f, x) == auto
         gpu_ctx.set_msm_affine_rounds(3)
         assert gpu_ctx.worker_commit_open(0, f, x) == auto

@@ -99,8 +99,7 @@ struct zkp_ctx {
     cudaEvent_t ev_ready = nullptr;           // polynomial uploaded + converted (lane 0 -> lane 1)
     cudaEvent_t ev_acc2_0 = nullptr, ev_acc2_1 = nullptr;
     uint32_t c_override = 0;
-    int affine_rounds_override = -1;          // -1: automatic (see plan_for); 0..6: forced (tests, tuning)
-    bool dual_lane = false;                   // set while a commit+open enqueues its two MSMs (plan_for reads it)
+    int affine_rounds_override = -1;          // <= 0: off (default, see plan_for); 1..6: rounds of batched-affine additions
     // fixed-base tables: per SRS row, [2^(c w)] P_i for w < W (slice w at w * 2^log_n); built lazily
     struct Precomp { zkp::DevBuf table; uint32_t c = 0, W = 0; };
     std::vector<Precomp> precomp;

@@ -107,19 +107,12 @@ void drop_precomp(zkp_ctx* ctx, int row /* -1 = all */) {
 
 MsmPlan plan_for(zkp_ctx* ctx, size_t n, bool precomp) {
     uint32_t c = ctx->c_override ? ctx->c_override : msm_window_bits((uint32_t)n, precomp);
-    // Batched-affine rounds (msm_affine.cuh).  Measured on B200 at 2^20: a round costs about as
-    // much per addition as the XYZZ kernel (it runs at ~50% of the multiply pipe, the XYZZ kernel at ~89%), so a
-    // lone MSM is 9% SLOWER with 3 rounds; when the two MSMs of a commit+open share the GPU on two streams the
-    // shorter, stall-heavy round kernels interleave better and 2 rounds make the pair 5% faster.  Automatic mode
-    // therefore uses 2 rounds only there, for lists of >= 2^22 entries with >= 16 entries per bucket.
-    uint32_t rounds = 0;
-    if (ctx->affine_rounds_override >= 0) {
-        rounds = (uint32_t)ctx->affine_rounds_override;
-    } else if (ctx->dual_lane) {
-        const uint32_t W = 255 / c + 1;
-        const size_t N = n * (size_t)W, buckets = (size_t)(precomp ? 1 : W) << (c - 1);
-        if (N >= ((size_t)1 << 22) && N >= 16 * buckets) rounds = 2;
-    }
+    // Batched-affine rounds (msm_affine.cuh) are OFF unless forced with zkp_set_msm_affine_rounds.  Measured on
+    // B200 at 2^20: a round costs about as much per addition as the XYZZ kernel (6 instead of
+    // 10 products, but it keeps the multiply pipe only ~55% busy against ~87%), so a lone MSM is 9% slower with
+    // 3 rounds and the two-stream commit+open only 2.7% faster with 2 rounds (12.69 vs 13.04 ms) -- not worth
+    // a second set of point lists in HBM and a dominant kernel split three ways.
+    uint32_t rounds = ctx->affine_rounds_override > 0 ? (uint32_t)ctx->affine_rounds_override : 0;
     MsmPlan plan = msm_make_plan((uint32_t)n, ctx->sm_count, c, precomp, 1u << ctx->log_n, rounds);
     if (precomp) plan.neg_offset = plan.W << ctx->log_n;
     return plan;
