@@ -152,6 +152,7 @@ def main():
     ap.add_argument("--ref-log-n", type=int, default=16, help="sample size of the CPU arm")
     ap.add_argument("--cpu-baseline-log-n", type=int, default=16)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-config2", action="store_true", help="skip the 2^16 latency / batch-throughput measurement")
     ap.add_argument("--no-msm24", action="store_true", help="skip the sharded 2^24 MSM (BASELINE configs[3])")
     ap.add_argument("--msm-log-n", type=int, default=24)
     args = ap.parse_args()
@@ -294,6 +295,45 @@ def main():
             dist.destroy_process_group()
         return 0 if ok else 1
 
+    # ---- BASELINE configs[1]: degree 2^16 (the mainnet row size: scale 24, machines_scale 8) -- latency of one
+    #      commit+open through the C ABI and throughput of a batch of 32 independent polynomials pushed through 4
+    #      contexts on 4 host threads (a 2^16 request is latency-bound: ~30 dependent launches, so several
+    #      requests in flight are what fills the GPU; ctypes releases the GIL during the call)
+    cfg2 = None
+    if not args.no_config2:
+        import concurrent.futures
+        lg2, nctx, batch = 16, 4, 32
+        ctxs = [native.Context(local) for _ in range(nctx)]
+        polys2 = []
+        for k, c2 in enumerate(ctxs):
+            c2.srs_generate(TAU_X, TAU_Y, lg2, 0)
+            pb = native.PinnedBuffer(32 << lg2).write(c2.random_poly(0xB200 + 2 + k, 1 << lg2))
+            polys2.append(pb)
+            c2.worker_commit_open(0, pb, x)  # builds the fixed-base table
+        t0 = time.perf_counter()
+        for _ in range(batch):
+            r16 = ctxs[0].worker_commit_open(0, polys2[0], x)
+        lat_ms = (time.perf_counter() - t0) * 1e3 / batch
+
+        def work(k):
+            out = None
+            for _ in range(batch // nctx):
+                out = ctxs[k].worker_commit_open(0, polys2[k], x)
+            return out
+        with concurrent.futures.ThreadPoolExecutor(nctx) as ex:
+            list(ex.map(work, range(nctx)))  # warm
+            t0 = time.perf_counter()
+            outs = list(ex.map(work, range(nctx)))
+            thr = batch / (time.perf_counter() - t0)
+        ok16 = outs[0] == r16 and ctxs[0].worker_verify(0, r16[2], x, r16[1], r16[0])
+        cfg2 = {"log_n": lg2, "latency_ms_per_commit_open": lat_ms, "commit_open_per_s_1_context": 1e3 / lat_ms,
+                "commit_open_per_s_batch32_4_contexts": thr, "verified": bool(ok16),
+                "note": "host buffers (pinned) in, results on host; per-GPU figure of rank 0"}
+        for c2 in ctxs:
+            c2.close()
+        for pb in polys2:
+            pb.close()
+
     imad_peak, fq_chain_peak = ctx.bench_peaks()
     ms_msm, _ = ctx.bench_msm(row, poly, 5, True)
     ms_kernel_alone = ctx.bench_last_kernel_ms()  # the dominant kernel with nothing else on the device
@@ -355,6 +395,7 @@ def main():
         "ntt": {"ms": ms_ntt, "achieved_gbs": 64.0 * n / (ms_ntt * 1e-3) / 1e9, "hbm_peak_gbs": hbm_peak,
                 "frac_hbm": 64.0 * n / (ms_ntt * 1e-3) / 1e9 / hbm_peak,
                 "fr_mul_frac_of_imad_peak": (n / 2 * log_n) * 136 / (ms_ntt * 1e-3) / imad_peak},
+        "config_2p16": cfg2,
         "msm_sharded": msm24,
         "combine_ms_per_step": combine_ms,
         "verified": bool(ok),
