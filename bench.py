@@ -382,8 +382,10 @@ def main():
         "roofline": {"bound": "imad", "kernel": "k_accumulate<level0>", "achieved": achieved, "peak": peak,
                      "unit": "G Fq-mul/s", "frac": achieved / peak, "traffic": traffic,
                      "note": "bound is INT32 multiply issue (IMAD.WIDE.U32, fmaheavy pipe), neither HBM nor tensor: "
-                             "10 Fq products x 300 wide MACs per bucket addition; peak = IMAD.WIDE rate measured in "
-                             "this process / 300",
+                             "algorithmic work = 10 Fq products x 300 wide MACs per bucket addition (SURVEY 8d); the kernel "
+                             "executes 2712 of those 3000 MACs (dedicated squaring, one fused two-product reduction); "
+                             "peak = IMAD.WIDE rate measured in this process / 300",
+                     "executed_wide_macs_per_addition": 2712, "algorithmic_wide_macs_per_addition": 3000,
                      "imad_wide_per_s_measured": imad_peak, "fq_mul_chain_per_s_measured": fq_chain_peak,
                      "kernel_ms": ms_kernel_alone, "kernel_ms_in_step": ms_kernel_max,
                      "kernel_share_of_step": 2 * ms_kernel_alone / (t_job / args.steps),
