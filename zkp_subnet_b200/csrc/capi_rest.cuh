@@ -68,9 +68,10 @@ int open_device(zkp_ctx* ctx, cudaStream_t st, const Fr* d_f, uint32_t n, const 
     if (rc) return rc;
     ZKP_CUDA(ctx->fr_b.ensure((size_t)n * 32));
     ZKP_CUDA(ctx->fr_c.ensure((size_t)n * 32));
-    uint32_t E = n >> 14;
-    if (E < 8) E = 8;
-    if (E > 64) E = 64;
+    // elements per thread: with one inversion per BLOCK (k_open_pass1) short runs cost nothing extra
+    uint32_t E = n >> 16;
+    if (E < 4) E = 4;
+    if (E > 16) E = 16;
     uint32_t threads = (n + E - 1) / E, blocks = (threads + 127) / 128;
     uint32_t blocks2 = (n + 255) / 256;
     ZKP_CUDA(ctx->partials.ensure((size_t)(blocks > blocks2 ? blocks : blocks2) * 32));
@@ -148,15 +149,28 @@ int commit_open_resident(zkp_ctx* ctx, uint32_t i, size_t n, const Fr64& x, uint
     cudaStream_t s0 = ctx->stream, s1 = ctx->stream2;
     ZKP_CUDA(cudaEventRecord(ctx->ev_ready, s0));
     ZKP_CUDA(cudaStreamWaitEvent(s1, ctx->ev_ready, 0));
+    // Front halves of both lanes are enqueued first (digits + sort of the commitment; opening field kernels, digits +
+    // sort of the proof), then the two accumulation/reduction back halves.  Measured alternatives at 2^20
+    // (tools/variant_bench.py): holding the first accumulation until the proof's front half is done 13.14 ms,
+    // a higher stream priority for the lane that accumulates first 13.26 ms, both 13.53 ms, neither 12.95 ms --
+    // the front half of lane 1 and the reduction tail of lane 0 are real work; hiding them under an accumulation
+    // slows that accumulation by about as much as running them in the open would cost.
+    const G1Affine *pts_c = nullptr, *pts_o = nullptr;
     if (commitment48) {
-        rc = msm_device_enqueue(ctx, 0, i, ctx->scalars.as<uint32_t>(), SCALAR_BE, n, &plan_c);
+        rc = msm_device_prep(ctx, 0, i, ctx->scalars.as<uint32_t>(), SCALAR_BE, n, &plan_c, &pts_c);
         if (rc) return rc;
     }
     trace_mark(ctx, 1, s1, "open_begin");
     rc = open_device(ctx, s1, ctx->fr_a.as<Fr>(), (uint32_t)n, x);
     if (rc) return rc;
     trace_mark(ctx, 1, s1, "open_field_kernels");
-    rc = msm_device_enqueue(ctx, 1, i, ctx->fr_c.as<uint32_t>(), SCALAR_MONT, n, &plan_o);
+    rc = msm_device_prep(ctx, 1, i, ctx->fr_c.as<uint32_t>(), SCALAR_MONT, n, &plan_o, &pts_o);
+    if (rc) return rc;
+    if (commitment48) {
+        rc = msm_enqueue_main(ctx, 0, plan_c, pts_c);
+        if (rc) return rc;
+    }
+    rc = msm_enqueue_main(ctx, 1, plan_o, pts_o);
     if (rc) return rc;
     rc = fetch_y_enqueue(ctx, s1);
     if (rc) return rc;
@@ -537,9 +551,9 @@ int shard_pass1(zkp_ctx* ctx, const uint8_t* slice_be, size_t n_local, const Fr6
     cudaStream_t st = ctx->stream;
     const uint32_t n = (uint32_t)n_local;
     ZKP_CUDA(ctx->fr_b.ensure((size_t)n * 32));
-    uint32_t E = n >> 14;
-    if (E < 8) E = 8;
-    if (E > 64) E = 64;
+    uint32_t E = n >> 16;
+    if (E < 4) E = 4;
+    if (E > 16) E = 16;
     uint32_t threads = (n + E - 1) / E, blocks = (threads + 127) / 128;
     ZKP_CUDA(ctx->partials.ensure((size_t)blocks * 32));
     ZKP_CUDA(cudaMemsetAsync(small_at<uint32_t>(ctx, SM_HIT), 0xff, 4, st));

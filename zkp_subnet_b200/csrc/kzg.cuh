@@ -98,18 +98,25 @@ __global__ void k_fr_reduce(const Fr* __restrict__ partial, uint32_t count, Fr* 
 }
 
 // ---- opening, pass 1: inv_d[j] = 1/(w^j - x), partial sums of f_j w^j / (w^j - x).
-// Thread t owns elements [t*E, (t+1)*E).  wt[k] = w^(2^k), wt_inv[0] = w^-1.
+// Thread t owns elements [t*E, (t+1)*E).  wt[k] = w^(2^k), w_inv = w^-1.
+// Montgomery's trick on two levels: prefix products inside the thread (parked in inv_d), then an inclusive
+// prefix and suffix product scan over the block's 128 thread products in shared memory, and ONE Fermat inversion
+// per block (a lone thread needs ~0.2 ms for the 255 dependent squarings -- with one inversion per thread that
+// latency, times a handful of resident warps, was 1 ms of the opening's critical path at 2^20).
 __global__ void __launch_bounds__(128)
 k_open_pass1(const Fr* __restrict__ f, uint32_t n, uint32_t E, Fr x, const Fr* __restrict__ wt, Fr w_inv,
              Fr* __restrict__ inv_d, Fr* __restrict__ partial, uint32_t* __restrict__ hit, uint64_t j0) {
-    uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    __shared__ Fr pre[128], suf[128];
+    __shared__ Fr total_inv;
+    const uint32_t tid = threadIdx.x;
+    uint32_t t = blockIdx.x * blockDim.x + tid;
     uint64_t lo = (uint64_t)t * E;
+    const uint32_t cnt = lo < n ? (n - lo < E ? (uint32_t)(n - lo) : E) : 0;
     Fr s1 = Fr::zero();
-    if (lo < n) {
-        uint32_t cnt = n - lo < E ? (uint32_t)(n - lo) : E;
-        const Fr w = load_fr(wt);
-        Fr a = pow_from_table(wt, j0 + lo);  // w^(j0 + lo): element lo of a shard that starts at domain index j0
-        Fr run = Fr::one();
+    const Fr w = load_fr(wt);
+    Fr a = Fr::one(), run = Fr::one();
+    if (cnt) {
+        a = pow_from_table(wt, j0 + lo);  // w^(j0 + lo): element lo of a shard that starts at domain index j0
         // forward: prefix products of d_j parked in inv_d
         for (uint32_t i = 0; i < cnt; i++) {
             Fr d = a - x;
@@ -121,7 +128,27 @@ k_open_pass1(const Fr* __restrict__ f, uint32_t n, uint32_t E, Fr x, const Fr* _
             store_fr(inv_d + lo + i, run);
             if (i + 1 < cnt) a = a * w;
         }
-        Fr u = run.inverse();  // 1 / (d_0 ... d_{cnt-1})
+    }
+    // block level: pre[k] = run_0 .. run_k, suf[k] = run_k .. run_127 (Hillis-Steele, 7 steps each)
+    pre[tid] = run;
+    suf[tid] = run;
+    __syncthreads();
+    for (uint32_t s = 1; s < 128; s <<= 1) {
+        Fr p = pre[tid], q = suf[tid];
+        if (tid >= s) p = pre[tid - s] * p;
+        if (tid + s < 128) q = q * suf[tid + s];
+        __syncthreads();
+        pre[tid] = p;
+        suf[tid] = q;
+        __syncthreads();
+    }
+    if (tid == 0) total_inv = pre[127].inverse();
+    __syncthreads();
+    if (cnt) {
+        // 1 / run_tid = (product of the other threads' runs) / (product of all runs)
+        Fr u = total_inv;
+        if (tid > 0) u = u * pre[tid - 1];
+        if (tid < 127) u = u * suf[tid + 1];
         // backward: a currently holds w^(lo+cnt-1)
         for (int i = (int)cnt - 1; i >= 0; i--) {
             Fr d = a - x;

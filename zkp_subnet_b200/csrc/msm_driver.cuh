@@ -12,14 +12,13 @@ inline uint64_t msm_fq_muls(const MsmPlan& p) {
     return 10ull * p.n * p.W + 14ull * 2ull * p.B * p.Wb;
 }
 
-// Launches the whole device pipeline on ctx->stream and copies the bit-plane sums to pinned host
-// memory; synchronises the stream before returning.  d_points: the SRS row (classic) or the fixed-base
-// table of the row (plan.precomp).
-inline int msm_enqueue(zkp_ctx* ctx, int lane, const MsmPlan& plan, const uint32_t* d_scalars, int fmt,
-                       const G1Affine* d_points) {
+// The device pipeline of one MSM on a lane's stream, in two halves so that a commit+open can enqueue the cheap
+// front halves (digits + sort) of BOTH lanes before either bucket accumulation: an accumulation grid keeps every
+// SM busy for milliseconds and starves whatever small kernels another stream launches after it.
+// Front half: workspaces, signed digits, radix sort.
+inline int msm_enqueue_prep(zkp_ctx* ctx, int lane, const MsmPlan& plan, const uint32_t* d_scalars, int fmt) {
     MsmWorkspace& ws = lane ? ctx->ws2 : ctx->ws;
     cudaStream_t st = lane ? ctx->stream2 : ctx->stream;
-    cudaEvent_t ev0 = lane ? ctx->ev_acc2_0 : ctx->ev_acc0, ev1 = lane ? ctx->ev_acc2_1 : ctx->ev_acc1;
     const size_t N = plan.N;
     ZKP_CUDA(ws.keys_a.ensure(N * 4));
     ZKP_CUDA(ws.keys_b.ensure(N * 4));
@@ -62,6 +61,19 @@ inline int msm_enqueue(zkp_ctx* ctx, int lane, const MsmPlan& plan, const uint32
                                              ws.vals_a.as<uint32_t>(), ws.vals_b.as<uint32_t>(), (int64_t)N, 0,
                                              (int)plan.key_bits, st));
     trace_mark(ctx, lane, st, "sort");
+    return ZKP_OK;
+}
+
+// Back half: (optional batched-affine rounds,) balanced accumulation, reduction, copy of the bit-plane sums to pinned
+// host memory.  d_points: the SRS row (classic) or the fixed-base table of the row (plan.precomp).
+inline int msm_enqueue_main(zkp_ctx* ctx, int lane, const MsmPlan& plan, const G1Affine* d_points) {
+    MsmWorkspace& ws = lane ? ctx->ws2 : ctx->ws;
+    cudaStream_t st = lane ? ctx->stream2 : ctx->stream;
+    cudaEvent_t ev0 = lane ? ctx->ev_acc2_0 : ctx->ev_acc0, ev1 = lane ? ctx->ev_acc2_1 : ctx->ev_acc1;
+    const size_t N = plan.N;
+    const size_t nb = (size_t)plan.Wb * plan.B;
+    const size_t out_records = (size_t)plan.Wb * plan.out_per_window;
+    const size_t temp_bytes = ws.cub_temp.cap;
     // 2b. batched-affine rounds: pairwise additions inside every bucket, 6 Fq products each instead of 10
     const uint32_t* acc_keys = ws.keys_b.as<uint32_t>();
     const uint32_t* acc_vals = ws.vals_b.as<uint32_t>();
@@ -175,6 +187,13 @@ inline int msm_enqueue(zkp_ctx* ctx, int lane, const MsmPlan& plan, const uint32
     ZKP_CUDA(cudaMemcpyAsync(ws.h_bad, ws.bad.p, 4, cudaMemcpyDeviceToHost, st));
     trace_mark(ctx, lane, st, "d2h");
     return ZKP_OK;
+}
+
+inline int msm_enqueue(zkp_ctx* ctx, int lane, const MsmPlan& plan, const uint32_t* d_scalars, int fmt,
+                       const G1Affine* d_points) {
+    int rc = msm_enqueue_prep(ctx, lane, plan, d_scalars, fmt);
+    if (rc) return rc;
+    return msm_enqueue_main(ctx, lane, plan, d_points);
 }
 
 // waits for the lane's pipeline; afterwards ws.h_window holds the bit-plane sums

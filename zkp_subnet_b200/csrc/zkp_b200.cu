@@ -118,8 +118,10 @@ MsmPlan plan_for(zkp_ctx* ctx, size_t n, bool precomp) {
     return plan;
 }
 
-// Enqueue an MSM over row `row` with device-resident scalars on a lane (no host sync).
-int msm_device_enqueue(zkp_ctx* ctx, int lane, uint32_t row, const uint32_t* d_scalars, int fmt, size_t n, MsmPlan* plan_out) {
+// Enqueue an MSM over row `row` with device-resident scalars on a lane (no host sync), in two halves
+// (msm_driver.cuh): digits + sort, then accumulation + reduction.
+int msm_device_prep(zkp_ctx* ctx, int lane, uint32_t row, const uint32_t* d_scalars, int fmt, size_t n, MsmPlan* plan_out,
+                    const G1Affine** pts_out) {
     bool precomp = false;
     MsmPlan plan;
     if (ctx->use_precomp && n >= 256) {
@@ -128,9 +130,15 @@ int msm_device_enqueue(zkp_ctx* ctx, int lane, uint32_t row, const uint32_t* d_s
         if (rc) return rc;
     }
     if (!precomp) plan = plan_for(ctx, n, false);
-    const G1Affine* pts = precomp ? ctx->precomp[row].table.as<G1Affine>() : row_ptr(ctx, row);
+    *pts_out = precomp ? ctx->precomp[row].table.as<G1Affine>() : row_ptr(ctx, row);
     *plan_out = plan;
-    return msm_enqueue(ctx, lane, plan, d_scalars, fmt, pts);
+    return msm_enqueue_prep(ctx, lane, plan, d_scalars, fmt);
+}
+int msm_device_enqueue(zkp_ctx* ctx, int lane, uint32_t row, const uint32_t* d_scalars, int fmt, size_t n, MsmPlan* plan_out) {
+    const G1Affine* pts;
+    int rc = msm_device_prep(ctx, lane, row, d_scalars, fmt, n, plan_out, &pts);
+    if (rc) return rc;
+    return msm_enqueue_main(ctx, lane, *plan_out, pts);
 }
 int msm_device_finish(zkp_ctx* ctx, int lane, const MsmPlan& plan, uint8_t out48[48]) {
     int rc = msm_wait(ctx, lane);
