@@ -107,6 +107,12 @@ int zkp_worker_commit_open(zkp_ctx* ctx, uint32_t i, const uint8_t* poly_be, siz
  * (reference tests/test_validator.py:66,79-86 expect reward 0, not an exception). */
 int zkp_worker_verify(zkp_ctx* ctx, uint32_t i, const uint8_t proof48[48], const uint8_t alpha_be[32],
                       const uint8_t eval_be[32], const uint8_t commitment48[48], int* valid);
+/* The responses of ONE challenge (common alpha) verified together: a random linear combination, two Miller loops
+ * and one final exponentiation for the whole batch instead of per response (the reference scores responses one
+ * by one, neurons/validator.py:168-170,178-192).  valid[k] is exactly what zkp_worker_verify would say for item k
+ * (if the combined check fails the items are re-verified individually). */
+int zkp_worker_verify_batch(zkp_ctx* ctx, size_t count, const uint32_t* indices, const uint8_t* proofs48,
+                            const uint8_t alpha_be[32], const uint8_t* evals_be, const uint8_t* commitments48, int* valid);
 /* Client.fft(poly, left, inverse)  (reference neurons/validator.py:58-65): natural-order (i)NTT over the
  * size-n X-domain (left != 0) or Y-domain (left == 0); n a power of two */
 int zkp_fft(zkp_ctx* ctx, const uint8_t* in_be, size_t n, int left, int inverse, uint8_t* out_be);

@@ -101,6 +101,43 @@ def test_reward(client, missing_info, too_late, invalid_proof, half_time, expect
     assert validator.get_rewards(challenge, responses, times, timeout) == expected_value
 
 
+def test_worker_verify_batch_matches_individual(client, golden):
+    """Batched verification (one random linear combination for the whole challenge) gives, item by item, the
+    answer of worker_verify: all-valid batches, and batches where some items are wrong in different ways (the
+    fallback must single out exactly those)."""
+    alpha = golden["test_point"]
+    good = []
+    for rec in golden["pianist_4x16"]:
+        good.append({"i": rec["row"], "proof": base64.b64encode(bytes.fromhex(rec["proof"])).decode(), "eval": rec["eval"],
+                     "commitment": base64.b64encode(bytes.fromhex(rec["commitment"])).decode()})
+
+    def individual(items):
+        out = []
+        for it in items:
+            with client.worker_verify(it["i"], it["proof"], alpha, it["eval"], it["commitment"]) as r:
+                assert r.status_code == 200
+                out.append(r.json()["valid"])
+        return out
+
+    def batch(items):
+        with client.worker_verify_batch(items, alpha) as r:
+            assert r.status_code == 200
+            return r.json()["valid"]
+
+    assert batch(good) == individual(good) == [True] * 4
+    assert batch(good[:1]) == [True] and batch([]) == []
+    bad = [dict(it) for it in good] + [dict(good[0])]
+    bad[1]["eval"] = good[0]["eval"][:-1] + ("A" if good[0]["eval"][-1] != "A" else "E")   # wrong evaluation
+    bad[2]["commitment"] = good[3]["commitment"]                                           # someone else's commitment
+    bad[3]["proof"] = "!!not base64!!"                                                     # garbage
+    got = batch(bad)
+    assert got == individual(bad) and got[0] is True and got[4] is True and got[1:4] == [False, False, False]
+    wrong_row = [dict(good[0], i=1)]                                                       # right bytes, wrong SRS row
+    assert batch(wrong_row + good[1:]) == [False, True, True, True]
+    with client.worker_verify_batch(good, "not a field element") as r:
+        assert r.status_code == 200 and r.json()["valid"] == [False] * 4
+
+
 def test_challenge_shape_and_wire_format(client):
     with client.random_poly() as r:
         poly = r.json()["poly"]

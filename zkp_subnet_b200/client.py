@@ -197,6 +197,30 @@ class Client:
         except native.ZkpError as e:
             return self._fail(e)
 
+    def worker_verify_batch(self, items: Sequence[Dict[str, Any]], alpha: str) -> Response:
+        """All responses of one challenge in one call: `items` are dicts with keys i, proof, eval, commitment (the
+        arguments of worker_verify); answers {"valid": [bool, ...]} in the same order.  Not part of the reference's
+        Client (it verifies one response per call, neurons/validator.py:168-170); malformed items are False."""
+        try:
+            zero48, zero32 = b"\xff" * 48, b"\xff" * 32  # placeholders that fail to decode -> valid = False
+            idx, proofs, evals, coms = [], [], [], []
+            for it in items:
+                idx.append(int(it["i"]))
+                try:
+                    p, e, c = _decode_any(it["proof"], 48), _decode_any(it["eval"], 32), _decode_any(it["commitment"], 48)
+                except (ValueError, TypeError, KeyError):
+                    p, e, c = zero48, zero32, zero48
+                proofs.append(p); evals.append(e); coms.append(c)
+            try:
+                a = _decode_any(alpha, 32)
+            except (ValueError, TypeError):
+                return Response(200, {"valid": [False] * len(idx)})
+            if not idx:
+                return Response(200, {"valid": []})
+            return Response(200, {"valid": self._need().worker_verify_batch(idx, b"".join(proofs), a, b"".join(evals), b"".join(coms))})
+        except native.ZkpError as e:
+            return self._fail(e)
+
     # ---- Pianist master node.  Not part of the reference's Client yet ("multi-miner proofs ... not yet
     #      implemented", reference neurons/validator.py:198; roadmap README.md:38); named after the worker_* calls.
     def master_commit(self, commitments: Sequence[str]) -> Response:

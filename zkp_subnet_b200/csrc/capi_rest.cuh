@@ -2,6 +2,7 @@
 // generation / files, wire codec and the benchmark entries.  Included at the end of zkp_b200.cu.
 #pragma once
 #include <chrono>
+#include <random>
 
 namespace {
 
@@ -748,6 +749,84 @@ int zkp_master_verify(zkp_ctx* ctx, const uint8_t commitment48[48], const uint8_
     std::vector<G1AffineHost> ps = {g1_affine_host(a), g1_affine_host(px.neg()), g1_affine_host(py.neg())};
     std::vector<const G2Lines*> qs = {&ctx->lines_g2, &ctx->lines_tau, &ctx->lines_tau_y};
     *valid = pairing_product_is_one(ps, qs) ? 1 : 0;
+    return ZKP_OK;
+}
+
+// Batched form of zkp_worker_verify for the validator's scoring loop (reference neurons/validator.py:168-170,
+// 178-192 verifies the responses of one challenge one by one; they share alpha).  One random linear combination,
+// two Miller loops and one final exponentiation for the whole batch:
+//   e( sum_k r_k (C_k - y_k S_{i_k}) + alpha * sum_k r_k pi_k , g2 ) * e( -sum_k r_k pi_k , [tau_x]_2 ) == 1
+// with fresh 128-bit r_k from the OS entropy source (an invalid proof survives with probability 2^-128).  If the
+// combined check fails, every well-formed item is verified on its own so that valid[] still says which ones are
+// bad.  Malformed encodings are valid = 0, never an error.
+int zkp_worker_verify_batch(zkp_ctx* ctx, size_t count, const uint32_t* indices, const uint8_t* proofs48, const uint8_t alpha_be[32],
+                            const uint8_t* evals_be, const uint8_t* commitments48, int* valid) {
+    if (!ctx || (count && (!indices || !proofs48 || !evals_be || !commitments48 || !valid)) || !alpha_be)
+        return fail(ZKP_ERR_ARG, "null argument");
+    if (!ctx->shaped || !ctx->have_lines) return fail(ZKP_ERR_STATE, "SRS (G2 part) not loaded");
+    using namespace host;
+    for (size_t k = 0; k < count; k++) {
+        valid[k] = 0;
+        if (indices[k] >= (1u << ctx->log_m)) return fail(ZKP_ERR_ARG, "worker index out of range");
+    }
+    Fr64 alpha;
+    if (!Fr64::from_be(alpha, alpha_be)) return ZKP_OK;  // malformed challenge point: nothing verifies
+    std::vector<G1J> scale;
+    {
+        std::lock_guard<std::mutex> lk(ctx->mu);
+        scale = ctx->scale_points;
+    }
+    struct Item { size_t k; G1J proof, com; Fr64 y; };
+    std::vector<Item> items;
+    items.reserve(count);
+    for (size_t k = 0; k < count; k++) {
+        Item it;
+        it.k = k;
+        if (!g1_decompress(it.proof, proofs48 + 48 * k) || !g1_decompress(it.com, commitments48 + 48 * k)) continue;
+        if (!Fr64::from_be(it.y, evals_be + 32 * k)) continue;
+        items.push_back(it);
+    }
+    if (items.empty()) return ZKP_OK;
+    const Fr64 ac = alpha.from_mont();
+    auto single = [&](const Item& it) {
+        Fr64 yc = it.y.from_mont();
+        G1J a = it.com.add(scale[indices[it.k]].mul(yc.v, 4).neg()).add(it.proof.mul(ac.v, 4));
+        std::vector<G1AffineHost> ps = {g1_affine_host(a), g1_affine_host(it.proof.neg())};
+        std::vector<const G2Lines*> qs = {&ctx->lines_g2, &ctx->lines_tau};
+        return pairing_product_is_one(ps, qs);
+    };
+    if (items.size() == 1) {
+        valid[items[0].k] = single(items[0]) ? 1 : 0;
+        return ZKP_OK;
+    }
+    std::random_device rd;
+    G1J sum_c = G1J::infinity(), sum_pi = G1J::infinity();
+    std::vector<Fr64> t(scale.size(), Fr64::zero());  // t_i = sum of r_k y_k over the items of row i
+    std::vector<uint8_t> row_used(scale.size(), 0);
+    for (const Item& it : items) {
+        uint64_t r[4] = {((uint64_t)rd() << 32) | rd(), ((uint64_t)rd() << 32) | rd(), 0, 0};
+        if (!(r[0] | r[1])) r[0] = 1;
+        sum_c = sum_c.add(it.com.mul(r, 2));
+        sum_pi = sum_pi.add(it.proof.mul(r, 2));
+        Fr64 rk;
+        memcpy(rk.v, r, 32);
+        rk = rk.to_mont();
+        t[indices[it.k]] = t[indices[it.k]] + rk * it.y;
+        row_used[indices[it.k]] = 1;
+    }
+    G1J a = sum_c.add(sum_pi.mul(ac.v, 4));
+    for (size_t i = 0; i < scale.size(); i++)
+        if (row_used[i]) {
+            Fr64 tc = t[i].from_mont();
+            a = a.add(scale[i].mul(tc.v, 4).neg());
+        }
+    std::vector<G1AffineHost> ps = {g1_affine_host(a), g1_affine_host(sum_pi.neg())};
+    std::vector<const G2Lines*> qs = {&ctx->lines_g2, &ctx->lines_tau};
+    if (pairing_product_is_one(ps, qs)) {
+        for (const Item& it : items) valid[it.k] = 1;
+        return ZKP_OK;
+    }
+    for (const Item& it : items) valid[it.k] = single(it) ? 1 : 0;
     return ZKP_OK;
 }
 

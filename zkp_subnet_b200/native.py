@@ -59,6 +59,7 @@ _SIGNATURES = {
     "zkp_worker_open": [_ctxp, ctypes.c_uint32, _u8p, ctypes.c_size_t, _u8p, _u8p, _u8p],
     "zkp_worker_commit_open": [_ctxp, ctypes.c_uint32, _u8p, ctypes.c_size_t, _u8p, _u8p, _u8p, _u8p],
     "zkp_worker_verify": [_ctxp, ctypes.c_uint32, _u8p, _u8p, _u8p, _u8p, ctypes.POINTER(ctypes.c_int)],
+    "zkp_worker_verify_batch": [_ctxp, ctypes.c_size_t, ctypes.POINTER(ctypes.c_uint32), _u8p, _u8p, _u8p, _u8p, ctypes.POINTER(ctypes.c_int)],
     "zkp_fft": [_ctxp, _u8p, ctypes.c_size_t, ctypes.c_int, ctypes.c_int, _u8p],
     "zkp_eval": [_ctxp, _u8p, ctypes.c_size_t, _u8p, _u8p],
     "zkp_random_poly": [_ctxp, ctypes.c_uint64, _u8p, ctypes.c_size_t],
@@ -238,6 +239,14 @@ class Context:
         valid = ctypes.c_int(0)
         check(lib().zkp_worker_verify(self._h, i, proof48, alpha_be, eval_be, commitment48, ctypes.byref(valid)))
         return bool(valid.value)
+
+    def worker_verify_batch(self, indices, proofs48: bytes, alpha_be: bytes, evals_be: bytes, commitments48: bytes):
+        """Verify the responses of one challenge together; returns a list of bools (same answers as worker_verify)."""
+        n = len(indices)
+        idx = (ctypes.c_uint32 * n)(*indices)
+        valid = (ctypes.c_int * n)()
+        check(lib().zkp_worker_verify_batch(self._h, n, idx, proofs48, alpha_be, evals_be, commitments48, valid))
+        return [bool(v) for v in valid]
 
     # ---- opening split by point range over several GPUs (see include/zkp_b200.h)
     def shard_eval_partial(self, i: int, slice_be: bytes, x_be: bytes) -> bytes:

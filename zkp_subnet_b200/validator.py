@@ -72,4 +72,18 @@ class Validator:
 
     def get_rewards(self, challenge: Challenge, responses: List[Prove], process_times: List[Optional[float]],
                     timeout: float) -> List[float]:
-        return [self.reward(challenge, r, t, timeout) for r, t in zip(responses, process_times)]
+        """reference neurons/validator.py:178-192.  Same rewards as calling `reward` per response; when the client
+        offers `worker_verify_batch` the responses that are complete and on time are verified in one call."""
+        if not hasattr(self.client, "worker_verify_batch"):
+            return [self.reward(challenge, r, t, timeout) for r, t in zip(responses, process_times)]
+        rewards = [0.0] * len(responses)
+        live = [k for k, (r, t) in enumerate(zip(responses, process_times))
+                if r.commitment is not None and r.proof is not None and t is not None and t <= timeout]
+        if live:
+            items = [{"i": responses[k].index, "proof": responses[k].proof, "eval": challenge.evals[responses[k].index],
+                      "commitment": responses[k].commitment} for k in live]
+            valid = self._call(self.client.worker_verify_batch(items, challenge.alpha), "valid", "Failed to verify the proofs.")
+            for k, ok in zip(live, valid):
+                if ok:
+                    rewards[k] = 1.0 - process_times[k] / timeout
+        return rewards
