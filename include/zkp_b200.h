@@ -118,6 +118,10 @@ int zkp_worker_verify_batch(zkp_ctx* ctx, size_t count, const uint32_t* indices,
 int zkp_fft(zkp_ctx* ctx, const uint8_t* in_be, size_t n, int left, int inverse, uint8_t* out_be);
 /* Client.eval(poly, x)  (reference neurons/validator.py:97-104): coefficient-form Horner */
 int zkp_eval(zkp_ctx* ctx, const uint8_t* coeffs_be, size_t n, const uint8_t x_be[32], uint8_t y_be[32]);
+/* Validator.generate_challenge's evaluations in one call (reference neurons/validator.py:106-120: per row one
+ * inverse fft and one eval through two RPCs): evals[i] = f_i(alpha) for `rows` rows of n evaluations each. */
+int zkp_challenge_evals(zkp_ctx* ctx, const uint8_t* polys_be, size_t rows, size_t n, const uint8_t alpha_be[32],
+                        uint8_t* evals_be);
 /* Client.random_poly() / random_point()  (reference neurons/validator.py:68-75,88-95) */
 int zkp_random_poly(zkp_ctx* ctx, uint64_t seed, uint8_t* out_be, size_t count);
 int zkp_random_point(zkp_ctx* ctx, uint64_t seed, uint8_t out_be[32]);

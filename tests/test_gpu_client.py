@@ -138,6 +138,28 @@ def test_worker_verify_batch_matches_individual(client, golden):
         assert r.status_code == 200 and r.json()["valid"] == [False] * 4
 
 
+def test_batched_challenge_equals_reference_flow(client):
+    """generate_challenge through the one-call barycentric entry equals the reference's per-row
+    inverse-fft + Horner flow (neurons/validator.py:106-120) on the same polynomial and point."""
+    with client.random_poly() as r:
+        rows = r.json()["poly"]
+    with client.random_point() as r:
+        alpha = r.json()["point"]
+    v = Validator(client, batched=False)
+    per_row = [v.rpc_eval(v.rpc_fft(row, left=True, inverse=True), alpha) for row in rows]
+    with client.challenge_evals(rows, alpha) as r:
+        assert r.status_code == 200 and r.json()["evals"] == per_row
+    # alpha inside the domain: the evaluation is the stored value itself
+    w = o.root_of_unity(len(rows[0]))
+    xin = o.fr_to_b64(pow(w, 3, o.R))
+    with client.challenge_evals(rows, xin) as r:
+        assert r.json()["evals"] == [row[3] for row in rows]
+    with client.challenge_evals([rows[0], rows[1][:-1]], alpha) as r:
+        assert r.status_code == 400
+    ch = Validator(client).generate_challenge(TEST_MACHINE_COUNT)
+    assert len(ch.evals) == TEST_MACHINE_COUNT and all(len(e) == 43 for e in ch.evals)
+
+
 def test_challenge_shape_and_wire_format(client):
     with client.random_poly() as r:
         poly = r.json()["poly"]

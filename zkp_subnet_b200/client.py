@@ -268,6 +268,20 @@ class Client:
         except (ValueError, TypeError, native.ZkpError) as e:
             return self._fail(e)
 
+    def challenge_evals(self, polys: Sequence[Sequence[str]], x: str) -> Response:
+        """The evaluations a validator needs for one challenge, f_i(x) for every row, in one call (the reference
+        does an inverse fft and an eval per row: neurons/validator.py:106-120).  Not part of the reference's Client."""
+        try:
+            rows = len(polys)
+            if rows == 0 or any(len(p) != len(polys[0]) for p in polys):
+                raise ValueError("rows of equal, non-zero length expected")
+            with self._lock:
+                flat = [s for p in polys for s in p]
+                raw = self._need().challenge_evals(self._decode(flat), rows, _decode_any(x, 32))
+            return Response(200, {"evals": [_b64_fr(raw[32 * i:32 * i + 32]) for i in range(rows)]})
+        except (ValueError, TypeError, native.ZkpError) as e:
+            return self._fail(e)
+
     def random_poly(self) -> Response:
         """Random bivariate polynomial as 2^machines_scale rows of 2^(scale-machines_scale) evaluations
         (reference neurons/validator.py:67-75)."""

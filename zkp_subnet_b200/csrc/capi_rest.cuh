@@ -896,6 +896,48 @@ int zkp_eval(zkp_ctx* ctx, const uint8_t* coeffs_be, size_t n, const uint8_t x_b
     return fetch_y(ctx, y_be);
 }
 
+// Validator.generate_challenge in one call (reference neurons/validator.py:106-120 does, per row, an inverse fft
+// and a Horner evaluation through two RPCs): f_i(alpha) for every row of `rows` x n evaluations, by the barycentric
+// formula with the weights w^j / (w^j - alpha) shared by all rows.
+int zkp_challenge_evals(zkp_ctx* ctx, const uint8_t* polys_be, size_t rows, size_t n, const uint8_t alpha_be[32], uint8_t* evals_be) {
+    if (!ctx || !polys_be || !alpha_be || !evals_be || !rows) return fail(ZKP_ERR_ARG, "bad argument");
+    if (!is_pow2(n) || n > ((size_t)1 << 28) || rows > 65535) return fail(ZKP_ERR_ARG, "rows of a power-of-two length (at most 65535 rows)");
+    Fr64 x;
+    if (!Fr64::from_be(x, alpha_be)) return fail(ZKP_ERR_ENCODING, "evaluation point is not canonical");
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    DeviceGuard g(ctx->device);
+    const uint32_t log_n = ilog2(n);
+    int rc = upload_poly(ctx, polys_be, rows * n);  // raw bytes -> ctx->scalars, Montgomery form -> fr_a, sets SM_BAD
+    if (rc) return rc;
+    zkp_ctx::Domain* dom;
+    rc = get_domain(ctx, log_n, false, &dom);
+    if (rc) return rc;
+    cudaStream_t st = ctx->stream;
+    const uint32_t nn = (uint32_t)n;
+    ZKP_CUDA(ctx->fr_b.ensure(n * 32));
+    uint32_t E = 16, threads = (nn + E - 1) / E, blocks = (threads + 127) / 128;
+    const uint32_t per_block = 4096, parts = (nn + per_block - 1) / per_block;
+    ZKP_CUDA(ctx->partials.ensure(((size_t)(blocks > parts * rows ? blocks : parts * rows)) * 32));
+    ZKP_CUDA(cudaMemsetAsync(small_at<uint32_t>(ctx, SM_HIT), 0xff, 4, st));
+    k_open_pass1<<<blocks, 128, 0, st>>>(nullptr, nn, E, to_dev(x), dom->wt.as<Fr>(), to_dev(dom->w_inv), ctx->fr_b.as<Fr>(),
+                                         ctx->partials.as<Fr>(), small_at<uint32_t>(ctx, SM_HIT), 0);
+    k_bary_weights<<<(threads + 127) / 128, 128, 0, st>>>(ctx->fr_b.as<Fr>(), nn, dom->wt.as<Fr>());
+    k_bary_rows<<<dim3(parts, (unsigned)rows), 256, 0, st>>>(ctx->fr_a.as<Fr>(), ctx->fr_b.as<Fr>(), nn, per_block, ctx->partials.as<Fr>());
+    Fr64 zn = x;
+    for (uint32_t k = 0; k < log_n; k++) zn = zn.sqr();
+    zn = (zn - Fr64::one()) * dom->n_inv;
+    ZKP_CUDA(ctx->fr_c.ensure(rows * 32));
+    k_bary_finish<<<(unsigned)rows, 32, 0, st>>>(ctx->fr_a.as<Fr>(), nn, ctx->partials.as<Fr>(), parts, to_dev(zn),
+                                                 small_at<uint32_t>(ctx, SM_HIT), ctx->fr_c.as<uint32_t>());
+    ctx->launches += 4;
+    ZKP_CUDA(cudaMemcpyAsync(evals_be, ctx->fr_c.p, rows * 32, cudaMemcpyDeviceToHost, st));
+    ZKP_CUDA(cudaMemcpyAsync(ctx->h_small + 64, small_at<uint8_t>(ctx, SM_BAD), 4, cudaMemcpyDeviceToHost, st));
+    ZKP_CUDA(cudaStreamSynchronize(st));
+    ZKP_CUDA(cudaGetLastError());
+    if (*reinterpret_cast<uint32_t*>(ctx->h_small + 64)) return fail(ZKP_ERR_ENCODING, "polynomial holds a non-canonical field element");
+    return ZKP_OK;
+}
+
 int zkp_random_poly(zkp_ctx* ctx, uint64_t seed, uint8_t* out_be, size_t count) {
     if (!ctx || !out_be || !count) return fail(ZKP_ERR_ARG, "bad argument");
     std::lock_guard<std::mutex> lk(ctx->mu);

@@ -201,6 +201,54 @@ __global__ void k_open_fix_apply(Fr* __restrict__ q, const uint32_t* __restrict_
     if (*hit != HIT_NONE) store_fr(q + *hit, load_fr(s2).neg());
 }
 
+// ---- batched barycentric evaluation (validator challenge: every row of the random bivariate polynomial at the
+// same alpha).  k_bary_weights: wd[j] = w^j / (w^j - x) from inv_d (in place); k_bary_rows: block (bx, row)
+// sums f[row][j] * wd[j] over its share -> partial[row * gridDim.x + bx].
+__global__ void k_bary_weights(Fr* __restrict__ inv_d, uint32_t n, const Fr* __restrict__ wt) {
+    constexpr uint32_t E = 16;
+    uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    uint64_t lo = (uint64_t)t * E;
+    if (lo >= n) return;
+    Fr a = pow_from_table(wt, lo);
+    const Fr w = load_fr(wt);
+    for (uint32_t i = 0; i < E && lo + i < n; i++) {
+        store_fr(inv_d + lo + i, load_fr(inv_d + lo + i) * a);
+        a = a * w;
+    }
+}
+__global__ void __launch_bounds__(256)
+k_bary_rows(const Fr* __restrict__ f, const Fr* __restrict__ wd, uint32_t n, uint32_t per_block, Fr* __restrict__ partial) {
+    const uint32_t row = blockIdx.y;
+    const Fr* fr = f + (size_t)row * n;
+    const uint32_t lo = blockIdx.x * per_block, hi = lo + per_block < n ? lo + per_block : n;
+    Fr acc = Fr::zero();
+    for (uint32_t j = lo + threadIdx.x; j < hi; j += blockDim.x) acc = acc + load_fr(fr + j) * load_fr(wd + j);
+    __shared__ Fr sh[256];
+    sh[threadIdx.x] = acc;
+    __syncthreads();
+    for (int s = 128; s > 0; s >>= 1) {
+        if ((int)threadIdx.x < s) sh[threadIdx.x] = sh[threadIdx.x] + sh[threadIdx.x + s];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) store_fr(partial + (size_t)row * gridDim.x + blockIdx.x, sh[0]);
+}
+// y[row] = hit ? f[row][hit] : -(zn) * sum of the row's partials       (one block per row)
+__global__ void __launch_bounds__(32)
+k_bary_finish(const Fr* __restrict__ f, uint32_t n, const Fr* __restrict__ partial, uint32_t parts, Fr zn,
+              const uint32_t* __restrict__ hit, uint32_t* __restrict__ out_be) {
+    const uint32_t row = blockIdx.x;
+    if (threadIdx.x) return;
+    Fr y;
+    if (*hit != HIT_NONE) {
+        y = load_fr(f + (size_t)row * n + *hit);
+    } else {
+        Fr acc = Fr::zero();
+        for (uint32_t k = 0; k < parts; k++) acc = acc + load_fr(partial + (size_t)row * parts + k);
+        y = (zn * acc).neg();
+    }
+    fr_bswap_store(out_be + (size_t)row * 8, y.from_mont());
+}
+
 // ---- Horner on coefficient form: thread t evaluates its run of E coefficients and scales by x^(tE)
 // xt[k] = x^(2^k)
 __global__ void __launch_bounds__(128)

@@ -62,6 +62,7 @@ _SIGNATURES = {
     "zkp_worker_verify_batch": [_ctxp, ctypes.c_size_t, ctypes.POINTER(ctypes.c_uint32), _u8p, _u8p, _u8p, _u8p, ctypes.POINTER(ctypes.c_int)],
     "zkp_fft": [_ctxp, _u8p, ctypes.c_size_t, ctypes.c_int, ctypes.c_int, _u8p],
     "zkp_eval": [_ctxp, _u8p, ctypes.c_size_t, _u8p, _u8p],
+    "zkp_challenge_evals": [_ctxp, _u8p, ctypes.c_size_t, ctypes.c_size_t, _u8p, _u8p],
     "zkp_random_poly": [_ctxp, ctypes.c_uint64, _u8p, ctypes.c_size_t],
     "zkp_random_point": [_ctxp, ctypes.c_uint64, _u8p],
     "zkp_b64_decode_fr": [ctypes.c_char_p, ctypes.c_size_t, ctypes.c_size_t, _u8p],
@@ -280,6 +281,12 @@ class Context:
     def eval(self, coeffs_be: bytes, x_be: bytes) -> bytes:
         out = ctypes.create_string_buffer(32)
         check(lib().zkp_eval(self._h, _arg(coeffs_be), len(coeffs_be) // 32, x_be, out))
+        return out.raw
+
+    def challenge_evals(self, polys_be: bytes, rows: int, alpha_be: bytes) -> bytes:
+        """f_i(alpha) for `rows` concatenated rows of evaluations (rows x 32 bytes out)."""
+        out = ctypes.create_string_buffer(32 * rows)
+        check(lib().zkp_challenge_evals(self._h, _arg(polys_be), rows, len(polys_be) // 32 // rows, alpha_be, out))
         return out.raw
 
     def random_poly(self, seed: int, count: int) -> bytes:

@@ -23,8 +23,9 @@ class Challenge:
 
 
 class Validator:
-    def __init__(self, client: Client):
+    def __init__(self, client: Client, batched: bool = True):
         self.client = client
+        self.batched = batched  # use the one-call challenge / verification entries when the client offers them
 
     def _call(self, response, key: str, what: str):
         with response as r:
@@ -51,6 +52,10 @@ class Validator:
     def generate_challenge(self, machines_count: int) -> Challenge:
         poly = self.rpc_random_poly()
         alpha = self.rpc_random_x()
+        if self.batched and hasattr(self.client, "challenge_evals"):
+            # same numbers as the per-row inverse fft + Horner below, in one call (barycentric form on the GPU)
+            evals = self._call(self.client.challenge_evals(poly[:machines_count], alpha), "evals", "Failed to evaluate the challenge.")
+            return Challenge(polys=poly, alpha=alpha, evals=evals)
         evals = []
         for i in range(machines_count):
             fft_coeffs = self.rpc_fft(poly[i], left=True, inverse=True)
@@ -74,7 +79,7 @@ class Validator:
                     timeout: float) -> List[float]:
         """reference neurons/validator.py:178-192.  Same rewards as calling `reward` per response; when the client
         offers `worker_verify_batch` the responses that are complete and on time are verified in one call."""
-        if not hasattr(self.client, "worker_verify_batch"):
+        if not self.batched or not hasattr(self.client, "worker_verify_batch"):
             return [self.reward(challenge, r, t, timeout) for r, t in zip(responses, process_times)]
         rewards = [0.0] * len(responses)
         live = [k for k, (r, t) in enumerate(zip(responses, process_times))
