@@ -200,7 +200,8 @@ int ntt_device(zkp_ctx* ctx, const Fr* in, Fr* out, uint32_t log_n, int inverse)
     int rc = get_domain(ctx, log_n, true, &dom);
     if (rc) return rc;
     const Fr n_inv = to_dev(dom->n_inv);
-    const size_t smem_per_elt = 32;
+    // shared memory of a pass: the tile (32 B per element) + the butterfly twiddles of the sub-transform (m/2 x 32 B)
+    auto smem_for = [](uint32_t log_tile, uint32_t log_m) -> size_t { return ((size_t)32 << log_tile) + ((size_t)16 << log_m); };
     auto sub_table = [&](uint32_t log_m, const Fr** out_tw) -> int {
         if (log_m == 0) { *out_tw = dom->tw.as<Fr>(); return ZKP_OK; }
         zkp_ctx::Domain* d;
@@ -210,7 +211,7 @@ int ntt_device(zkp_ctx* ctx, const Fr* in, Fr* out, uint32_t log_n, int inverse)
         return ZKP_OK;
     };
     auto threads_for = [](uint32_t log_tile) -> unsigned {
-        unsigned t = log_tile > 3 ? 1u << (log_tile - 3) : 1u;
+        unsigned t = log_tile > 2 ? 1u << (log_tile - 2) : 1u;  // one radix-4 group per thread and stage pair
         if (t < 32) t = 32;
         if (t > (unsigned)NTT_MAX_THREADS) t = NTT_MAX_THREADS;
         return t;
@@ -224,7 +225,7 @@ int ntt_device(zkp_ctx* ctx, const Fr* in, Fr* out, uint32_t log_n, int inverse)
     };
     if (log_n <= NTT_MAX_TILE_LOG) {
         NttPass p = {log_n, 0, 1, 1, 0, 1, 0, 1, log_n, 0, (uint32_t)inverse, (uint32_t)inverse};
-        k_ntt_pass<<<1, threads_for(log_n), smem_per_elt << log_n, ctx->stream>>>(in, out, dom->tw.as<Fr>(), dom->tw.as<Fr>(), p, n_inv);
+        k_ntt_pass<<<1, threads_for(log_n), smem_for(log_n, log_n), ctx->stream>>>(in, out, dom->tw.as<Fr>(), dom->tw.as<Fr>(), p, n_inv);
         ctx->launches++;
         return ZKP_OK;
     }
@@ -240,10 +241,10 @@ int ntt_device(zkp_ctx* ctx, const Fr* in, Fr* out, uint32_t log_n, int inverse)
     uint32_t lc1 = cols_for(l1, l2), lc2 = cols_for(l2, l1);
     // pass 1: columns i2 (n2 of them), rows i1; element (r, c) at r*n2 + c; twiddle w^(c*k)
     NttPass p1 = {l1, lc1, (uint32_t)n2, n2, 1, n2, 1, 0, log_n, 1, (uint32_t)inverse, 0};
-    k_ntt_pass<<<(unsigned)(n2 >> lc1), threads_for(l1 + lc1), smem_per_elt << (l1 + lc1), ctx->stream>>>(in, tmp, dom->tw.as<Fr>(), tw1, p1, n_inv);
+    k_ntt_pass<<<(unsigned)(n2 >> lc1), threads_for(l1 + lc1), smem_for(l1 + lc1, l1), ctx->stream>>>(in, tmp, dom->tw.as<Fr>(), tw1, p1, n_inv);
     // pass 2: columns k1 (n1 of them), rows i2; element (r, c) at c*n2 + r; output (k2, c) at k2*n1 + c
     NttPass p2 = {l2, lc2, (uint32_t)n1, 1, n2, n1, 1, 1, log_n, 0, (uint32_t)inverse, (uint32_t)inverse};
-    k_ntt_pass<<<(unsigned)(n1 >> lc2), threads_for(l2 + lc2), smem_per_elt << (l2 + lc2), ctx->stream>>>(tmp, out, dom->tw.as<Fr>(), tw2, p2, n_inv);
+    k_ntt_pass<<<(unsigned)(n1 >> lc2), threads_for(l2 + lc2), smem_for(l2 + lc2, l2), ctx->stream>>>(tmp, out, dom->tw.as<Fr>(), tw2, p2, n_inv);
     ctx->launches += 2;
     return ZKP_OK;
 }

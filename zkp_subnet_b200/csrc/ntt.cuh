@@ -3,7 +3,8 @@
 // and the evaluation-form <-> coefficient-form bridge of the commit path.
 //
 // Two-pass ("four-step") decomposition n = n1 * n2 with every sub-transform done entirely in shared
-// memory by one CTA (radix-2 DIT stages on a bit-reversed tile, up to 4096 elements = 128 KB):
+// memory by one CTA (radix-4 DIT stage pairs in registers on a bit-reversed tile, up to 4096 elements = 128 KB,
+// butterfly twiddles staged in shared memory):
 //   pass 1: for each i2, size-n1 transform over i1 of x[i1*n2 + i2], times w_n^(i2*k1)  -> Y[k1*n2 + i2]
 //   pass 2: for each k1, size-n2 transform over i2 of Y[k1*n2 + i2]                    -> X[k1 + n1*k2]
 // Each element is read and written exactly once per pass; a 32-byte Fr is exactly one DRAM sector, so
@@ -15,7 +16,7 @@
 
 namespace zkp {
 
-constexpr int NTT_MAX_THREADS = 512;  // launched with tile/8 threads: 4 butterflies per thread and stage
+constexpr int NTT_MAX_THREADS = 512;  // launched with tile/4 threads: one radix-4 group per thread and stage pair
 constexpr uint32_t NTT_MAX_TILE_LOG = 12;  // 4096 elements * 32 B = 128 KB dynamic shared memory
 
 // tw[e] = w^e, e < half; wt[k] = w^(2^k)
@@ -76,25 +77,74 @@ k_ntt_pass(const Fr* __restrict__ in, Fr* __restrict__ out, const Fr* __restrict
     }
     __syncthreads();
 
-    // radix-2 DIT stages
+    // butterfly twiddles w_m^e (e < m/2) staged in shared memory once per CTA: a butterfly reads its twiddle
+    // with shared-memory latency instead of waiting for L2 (ncu: long-scoreboard was the top stall)
+    uint4* twl = smem + 2 * tile;
+    uint4* twh = twl + (m >> 1);
+    for (uint32_t e = threadIdx.x; e < (m >> 1); e += NTT_THREADS) {
+        const uint4* src = reinterpret_cast<const uint4*>(tw_sub + e);
+        twl[e] = src[0];
+        twh[e] = src[1];
+    }
+    __syncthreads();
     const uint32_t half_m = m >> 1;
-    for (uint32_t s = 1; s <= p.log_m; s++) {
+    auto twiddle = [&](uint32_t e) -> Fr {  // w_m^e (forward) or w_m^-e (inverse), e < m
+        if (p.inverse) e = e ? m - e : 0;
+        const bool negate = e >= half_m;
+        if (negate) e -= half_m;
+        uint4 a0 = twl[e], a1 = twh[e];
+        Fr t;
+        t.v[0] = a0.x; t.v[1] = a0.y; t.v[2] = a0.z; t.v[3] = a0.w; t.v[4] = a1.x; t.v[5] = a1.y; t.v[6] = a1.z; t.v[7] = a1.w;
+        return negate ? t.neg() : t;
+    };
+    auto ld = [&](uint32_t i) -> Fr {
+        uint4 a0 = lo[i], a1 = hi[i];
+        Fr t;
+        t.v[0] = a0.x; t.v[1] = a0.y; t.v[2] = a0.z; t.v[3] = a0.w; t.v[4] = a1.x; t.v[5] = a1.y; t.v[6] = a1.z; t.v[7] = a1.w;
+        return t;
+    };
+    auto st = [&](uint32_t i, const Fr& t) {
+        lo[i] = make_uint4(t.v[0], t.v[1], t.v[2], t.v[3]);
+        hi[i] = make_uint4(t.v[4], t.v[5], t.v[6], t.v[7]);
+    };
+
+    // radix-4 DIT: stages s and s + 1 on four elements held in registers (same four twiddle products as two
+    // radix-2 stages, half the shared-memory traffic and barriers)
+    uint32_t s = 1;
+    for (; s + 1 <= p.log_m; s += 2) {
+        const uint32_t h = 1u << (s - 1);
+        for (uint32_t g = threadIdx.x; g < tile / 4; g += NTT_THREADS) {
+            const uint32_t c = g >> (p.log_m - 2), gi = g & ((m >> 2) - 1);
+            const uint32_t jj = gi & (h - 1), blk = gi >> (s - 1);
+            const uint32_t i0 = c * m + (blk << (s + 1)) + jj, i1 = i0 + h, i2 = i1 + h, i3 = i2 + h;
+            Fr x0 = ld(i0), x1 = ld(i1), x2 = ld(i2), x3 = ld(i3);
+            if (jj) {
+                const Fr ta = twiddle(jj << (p.log_m - s));
+                x1 = x1 * ta;
+                x3 = x3 * ta;
+            }
+            Fr u0 = x0 + x1, u1 = x0 - x1, u2 = x2 + x3, u3 = x2 - x3;
+            if (jj) u2 = u2 * twiddle(jj << (p.log_m - s - 1));
+            u3 = u3 * twiddle((jj << (p.log_m - s - 1)) + (m >> 2));
+            st(i0, u0 + u2);
+            st(i2, u0 - u2);
+            st(i1, u1 + u3);
+            st(i3, u1 - u3);
+        }
+        __syncthreads();
+    }
+    // odd log_m: one radix-2 stage left
+    for (; s <= p.log_m; s++) {
         const uint32_t half = 1u << (s - 1);
         for (uint32_t b = threadIdx.x; b < tile / 2; b += NTT_THREADS) {
             uint32_t c = b >> (p.log_m - 1), j = b & (m / 2 - 1);
             uint32_t jj = j & (half - 1);
             uint32_t pos = ((j >> (s - 1)) << s) + jj;
             uint32_t i0 = c * m + pos, i1 = i0 + half;
-            uint4 a0 = lo[i0], a1 = hi[i0], b0 = lo[i1], b1 = hi[i1];
-            Fr u, v;
-            u.v[0] = a0.x; u.v[1] = a0.y; u.v[2] = a0.z; u.v[3] = a0.w; u.v[4] = a1.x; u.v[5] = a1.y; u.v[6] = a1.z; u.v[7] = a1.w;
-            v.v[0] = b0.x; v.v[1] = b0.y; v.v[2] = b0.z; v.v[3] = b0.w; v.v[4] = b1.x; v.v[5] = b1.y; v.v[6] = b1.z; v.v[7] = b1.w;
-            if (jj) v = v * ntt_twiddle(tw_sub, jj << (p.log_m - s), half_m, p.inverse);
-            Fr x = u + v, y = u - v;
-            lo[i0] = make_uint4(x.v[0], x.v[1], x.v[2], x.v[3]);
-            hi[i0] = make_uint4(x.v[4], x.v[5], x.v[6], x.v[7]);
-            lo[i1] = make_uint4(y.v[0], y.v[1], y.v[2], y.v[3]);
-            hi[i1] = make_uint4(y.v[4], y.v[5], y.v[6], y.v[7]);
+            Fr u = ld(i0), v = ld(i1);
+            if (jj) v = v * twiddle(jj << (p.log_m - s));
+            st(i0, u + v);
+            st(i1, u - v);
         }
         __syncthreads();
     }

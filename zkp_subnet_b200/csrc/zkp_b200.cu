@@ -198,7 +198,7 @@ int zkp_ctx_create(int device, zkp_ctx** out) {
     ZKP_CUDA(cudaEventCreate(&ctx->ev_acc2_0));
     ZKP_CUDA(cudaEventCreate(&ctx->ev_acc2_1));
     ZKP_CUDA(cudaEventCreateWithFlags(&ctx->ev_ready, cudaEventDisableTiming));
-    ZKP_CUDA(cudaFuncSetAttribute(k_ntt_pass, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * 16 * (1 << NTT_MAX_TILE_LOG)));
+    ZKP_CUDA(cudaFuncSetAttribute(k_ntt_pass, cudaFuncAttributeMaxDynamicSharedMemorySize, 3 * 16 * (1 << NTT_MAX_TILE_LOG)));
     *out = ctx.release();
     return ZKP_OK;
 }
