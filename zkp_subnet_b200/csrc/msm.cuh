@@ -114,7 +114,10 @@ inline MsmPlan msm_make_plan(uint32_t n, int sm_count, uint32_t c, bool precomp,
     size_t waves = (p.acc_items + resident * 48 - 1) / (resident * 48);
     if (waves < 1) waves = 1;
     uint32_t L0 = (uint32_t)((p.acc_items + waves * resident - 1) / (waves * resident));
-    if (L0 < 8) L0 = 8;
+#ifndef ZKP_MIN_L0
+#define ZKP_MIN_L0 8
+#endif
+    if (L0 < ZKP_MIN_L0) L0 = ZKP_MIN_L0;
     size_t items = p.acc_items;
     uint32_t L = L0;
     for (int lvl = 0;; lvl++) {
