@@ -242,9 +242,11 @@ def main():
         t0 = time.perf_counter()
         reps = 20
         for _ in range(reps):
-            parts = sharding.gather_bytes(dist, com + proof, dev)
+            # every rank expands its two partial points (2 square roots, in parallel on the ranks); rank 0 adds
+            # 2 x N affine points and compresses the two sums
+            parts = sharding.gather_bytes(dist, sharding.expand_partials(com + proof), dev)
             if rank == 0:
-                agg = sharding.combine_partials(parts)  # aggregated commitment and proof (Pianist)
+                agg = sharding.combine_expanded(parts)  # aggregated commitment and proof (Pianist)
         combine_ms = (time.perf_counter() - t0) * 1e3 / reps
         t = torch.tensor([t_rank + combine_ms * args.steps, e2e_rank + combine_ms * args.steps, ms_kernel],
                          dtype=torch.float64, device=dev)

@@ -82,6 +82,10 @@ int zkp_shard_open_partial(zkp_ctx* ctx, uint32_t i, const uint8_t* slice_be, si
 /* sum of `count` compressed G1 points: the cross-GPU combine of partial commitments / Pianist
  * aggregation com = sum_i com_i, pi = sum_i pi_i (host arithmetic, 48 bytes per GPU) */
 int zkp_g1_sum(const uint8_t* points48, size_t count, uint8_t out48[48]);
+/* the same with 96-byte ZCash-uncompressed inputs (no square roots on the combining rank); zkp_g1_uncompress
+ * expands a compressed point on the rank that produced it */
+int zkp_g1_uncompress(const uint8_t in48[48], uint8_t out96[96]);
+int zkp_g1_sum_uncompressed(const uint8_t* points96, size_t count, uint8_t out48[48]);
 /* import one row from 96-byte ZCash-uncompressed points (validated on curve), and its scale point */
 int zkp_srs_set_shape(zkp_ctx* ctx, uint32_t log_n, uint32_t log_machines);
 int zkp_srs_import_row(zkp_ctx* ctx, uint32_t row, const uint8_t* points96, size_t n,

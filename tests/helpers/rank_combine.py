@@ -22,9 +22,12 @@ mine_c = native.g1_sum(b"".join(bytes.fromhex(r["commitment"]) for r in rows[lo:
 mine_p = native.g1_sum(b"".join(bytes.fromhex(r["proof"]) for r in rows[lo:hi]))
 parts = sharding.gather_bytes(dist, mine_c + mine_p)
 assert len(parts) == world and parts[rank] == mine_c + mine_p
+# the uncompressed route (what bench.py uses: no square roots on the combining rank) must give the same sums
+parts96 = sharding.gather_bytes(dist, sharding.expand_partials(mine_c + mine_p))
 ok = True
 if rank == 0:
     com, proof = sharding.combine_partials(parts)
+    assert sharding.combine_expanded(parts96) == (com, proof)
     # identical rows: sum_i R_i(tau_y) = 1, so the aggregate equals the commitment / proof under the plain SRS
     ok = com.hex() == golden["B_eval_form"]["commitment"] and proof.hex() == golden["B_eval_form"]["proof"]
     print("COMBINE_OK" if ok else "COMBINE_BAD", flush=True)

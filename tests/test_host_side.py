@@ -65,6 +65,16 @@ def test_g1_sum(golden):
     assert native.g1_sum(g + g).hex() == golden["g1_encodings"]["2G"]
     with pytest.raises(native.ZkpError):
         native.g1_sum(b"\xff" * 48)
+    # uncompressed route: same sums without square roots on the combining side
+    exp = b"".join(native.g1_uncompress(p) for p in pts)
+    assert len(exp) == 96 * len(pts)
+    assert native.g1_sum_uncompressed(exp).hex() == golden["B_eval_form"]["commitment"]
+    gx, gy = o.G1_GEN
+    assert native.g1_uncompress(g) == gx.to_bytes(48, "big") + gy.to_bytes(48, "big")
+    inf96 = native.g1_uncompress(bytes.fromhex(golden["g1_encodings"]["inf"]))
+    assert inf96[0] == 0x40 and native.g1_sum_uncompressed(inf96 + exp[:96]) == pts[0]
+    with pytest.raises(native.ZkpError):  # off-curve
+        native.g1_sum_uncompressed(exp[:95] + bytes([exp[95] ^ 1]))
 
 
 def _g2(pt):

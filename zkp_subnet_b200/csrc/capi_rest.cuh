@@ -403,6 +403,28 @@ int zkp_g1_sum(const uint8_t* points48, size_t count, uint8_t out48[48]) {
     return ZKP_OK;
 }
 
+// The same combine without the square roots: every rank expands its own partial to the 96-byte ZCash
+// uncompressed form (one sqrt each, in parallel on the ranks), rank 0 adds affine points (8 x 2 decompressions
+// were 0.8 ms of a 0.95 ms combine at 8 GPUs).
+int zkp_g1_uncompress(const uint8_t in48[48], uint8_t out96[96]) {
+    if (!in48 || !out96) return fail(ZKP_ERR_ARG, "null argument");
+    host::G1J p;
+    if (!host::g1_decompress(p, in48, false)) return fail(ZKP_ERR_ENCODING, "bad G1 point");
+    host::g1_serialize96(out96, p);
+    return ZKP_OK;
+}
+int zkp_g1_sum_uncompressed(const uint8_t* points96, size_t count, uint8_t out48[48]) {
+    if (!points96 || !out48) return fail(ZKP_ERR_ARG, "null argument");
+    host::G1J acc = host::G1J::infinity();
+    for (size_t k = 0; k < count; k++) {
+        host::G1J p;
+        if (!host::g1_deserialize96(p, points96 + 96 * k, true)) return fail(ZKP_ERR_ENCODING, "bad G1 point");
+        acc = acc.add(p);
+    }
+    host::g1_compress(out48, acc);
+    return ZKP_OK;
+}
+
 int zkp_srs_import_g2_tau(zkp_ctx* ctx, const uint8_t tau_x_be[32]) {
     if (!ctx || !tau_x_be) return fail(ZKP_ERR_ARG, "null argument");
     Fr64 t;

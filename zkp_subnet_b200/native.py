@@ -42,6 +42,8 @@ _SIGNATURES = {
     "zkp_srs_generate": [_ctxp, _u8p, _u8p, ctypes.c_uint32, ctypes.c_uint32],
     "zkp_srs_generate_shard": [_ctxp, _u8p, _u8p, ctypes.c_uint32, ctypes.c_uint32, ctypes.c_uint32, ctypes.c_uint32],
     "zkp_g1_sum": [_u8p, ctypes.c_size_t, _u8p],
+    "zkp_g1_uncompress": [_u8p, _u8p],
+    "zkp_g1_sum_uncompressed": [_u8p, ctypes.c_size_t, _u8p],
     "zkp_shard_eval_partial": [_ctxp, ctypes.c_uint32, _u8p, ctypes.c_size_t, _u8p, _u8p],
     "zkp_shard_eval_combine": [_u8p, ctypes.c_size_t, ctypes.c_uint32, _u8p, _u8p],
     "zkp_shard_open_partial": [_ctxp, ctypes.c_uint32, _u8p, ctypes.c_size_t, _u8p, _u8p, _u8p],
@@ -436,6 +438,18 @@ def shard_eval_combine(partials_be: bytes, log_n: int, x_be: bytes) -> bytes:
 def g1_sum(points48: bytes) -> bytes:
     out = ctypes.create_string_buffer(48)
     check(lib().zkp_g1_sum(points48, len(points48) // 48, out))
+    return out.raw
+
+
+def g1_uncompress(point48: bytes) -> bytes:
+    out = ctypes.create_string_buffer(96)
+    check(lib().zkp_g1_uncompress(point48, out))
+    return out.raw
+
+
+def g1_sum_uncompressed(points96: bytes) -> bytes:
+    out = ctypes.create_string_buffer(48)
+    check(lib().zkp_g1_sum_uncompressed(points96, len(points96) // 96, out))
     return out.raw
 
 

@@ -21,10 +21,12 @@ def shard_range(n: int, rank: int, world: int) -> Tuple[int, int]:
 def gather_bytes(dist, mine: bytes, device: str = "cpu") -> List[bytes]:
     """all_gather of a fixed-size byte string (the N partial points) over the process group."""
     import torch
-    t = torch.tensor(list(mine), dtype=torch.uint8, device=device)
-    out = [torch.empty_like(t) for _ in range(dist.get_world_size())]
-    dist.all_gather(out, t)
-    return [bytes(o.cpu().tolist()) for o in out]
+    world, n = dist.get_world_size(), len(mine)
+    t = torch.frombuffer(bytearray(mine), dtype=torch.uint8).to(device)
+    out = torch.empty(world * n, dtype=torch.uint8, device=device)
+    dist.all_gather_into_tensor(out, t)
+    raw = out.cpu().numpy().tobytes()
+    return [raw[r * n:(r + 1) * n] for r in range(world)]
 
 
 def combine_partials(parts: Sequence[bytes]) -> Tuple[bytes, ...]:
@@ -33,6 +35,20 @@ def combine_partials(parts: Sequence[bytes]) -> Tuple[bytes, ...]:
         raise ValueError("nothing to combine")
     k = len(parts[0]) // 48
     return tuple(native.g1_sum(b"".join(p[48 * j:48 * (j + 1)] for p in parts)) for j in range(k))
+
+
+def expand_partials(points48: bytes) -> bytes:
+    """k concatenated compressed points -> k uncompressed (96-byte) points: done by every rank on its own partials,
+    so that the combining rank adds affine points instead of taking 2 N square roots."""
+    return b"".join(native.g1_uncompress(points48[i:i + 48]) for i in range(0, len(points48), 48))
+
+
+def combine_expanded(parts: Sequence[bytes]) -> Tuple[bytes, ...]:
+    """Like combine_partials for parts made by expand_partials (96 bytes per point); returns compressed sums."""
+    if not parts:
+        raise ValueError("nothing to combine")
+    k = len(parts[0]) // 96
+    return tuple(native.g1_sum_uncompressed(b"".join(p[96 * j:96 * (j + 1)] for p in parts)) for j in range(k))
 
 
 def sharded_commit_open(dist, ctx, row: int, slice_be: bytes, x_be: bytes, log_n: int, device: str = "cpu") -> Tuple[bytes, bytes, bytes]:
