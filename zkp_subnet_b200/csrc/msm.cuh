@@ -32,7 +32,7 @@
 #include <stdint.h>
 #include <vector>
 
-#include "g1.cuh"
+#include "g1_coop.cuh"
 
 namespace zkp {
 
@@ -111,7 +111,10 @@ inline MsmPlan msm_make_plan(uint32_t n, int sm_count, uint32_t c, bool precomp,
     const size_t resident = (size_t)sm_count * 128 * ZKP_ACC_MIN_BLOCKS;
     // ~6 waves: long slices mean few slice-boundary partials for the slot levels, and because every
     // thread does the same work the last wave is as full as the first
-    size_t waves = (p.acc_items + resident * 48 - 1) / (resident * 48);
+#ifndef ZKP_L0_TARGET
+#define ZKP_L0_TARGET 48
+#endif
+    size_t waves = (p.acc_items + resident * ZKP_L0_TARGET - 1) / (resident * ZKP_L0_TARGET);
     if (waves < 1) waves = 1;
     uint32_t L0 = (uint32_t)((p.acc_items + waves * resident - 1) / (waves * resident));
 #ifndef ZKP_MIN_L0
@@ -243,13 +246,22 @@ __device__ __forceinline__ G1Affine load_affine(const G1Affine* src) {
 
 // LEVEL0: items are (key, point index|sign) entries, points gathered from the affine SRS row.
 // else  : items are (key|flags, XYZZ) slots written by the previous level.
-template <bool LEVEL0>
+template <bool LEVEL0, bool COOP = false>
 __global__ void __launch_bounds__(128, LEVEL0 ? ZKP_ACC_MIN_BLOCKS : 1)
 k_accumulate(const uint32_t* __restrict__ keys, const uint32_t* __restrict__ vals,
              const G1Affine* __restrict__ points, const G1Xyzz* __restrict__ slots_in, size_t items,
              uint32_t L, uint32_t discard, G1Xyzz* __restrict__ buckets, uint32_t* __restrict__ slot_keys,
              G1Xyzz* __restrict__ slot_pts, int last_level) {
-    size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    // Level 0: one thread per slice.  Small slot levels (COOP): FOUR lanes per slice -- they run the same control flow
+    // on the same slice and share every point addition (coop_add4), because these levels are pure latency: a few
+    // dependent additions per slice and far fewer slices than the machine has lanes.  A slot level with more slices
+    // than resident lanes is throughput-bound and keeps one thread per slice (the shared addition issues 1.37x the
+    // multiplies).
+    static_assert(!(LEVEL0 && COOP), "level 0 is one thread per slice");
+    constexpr int LANES = COOP ? 4 : 1;
+    size_t t = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) / LANES;
+    const int lane_id = threadIdx.x & 31, gl = lane_id & (LANES - 1), gbase = lane_id - gl;
+    const uint32_t gmask = COOP ? (0xfu << gbase) : 0u;
     // Slot lists hold (head_k, tail_k) pairs and the runs worth merging join tail_k with head_{k+1}
     // (odd index, even index): slices of the slot levels therefore start on ODD indices so that a
     // slice boundary falls between head_k and tail_k, never inside such a pair.
@@ -276,12 +288,12 @@ k_accumulate(const uint32_t* __restrict__ keys, const uint32_t* __restrict__ val
     auto flush = [&](bool continues_after) {
         bool starts_before = is_first_run && cur == prev_key;
         if (last_level || (!starts_before && !continues_after)) {
-            if (!acc.is_inf()) store_xyzz(buckets + cur, acc);
+            if (!acc.is_inf() && gl == 0) store_xyzz(buckets + cur, acc);
         } else if (is_first_run) {
-            store_xyzz(slot_pts + 2 * t, acc);
+            if (gl == 0) store_xyzz(slot_pts + 2 * t, acc);
             have_head = true;
         } else {
-            store_xyzz(slot_pts + 2 * t + 1, acc);
+            if (gl == 0) store_xyzz(slot_pts + 2 * t + 1, acc);
             have_tail = true;
         }
     };
@@ -321,11 +333,12 @@ k_accumulate(const uint32_t* __restrict__ keys, const uint32_t* __restrict__ val
             acc.madd(p, 0);
         } else if (!(raw & KEY_EMPTY_FLAG)) {
             G1Xyzz p = load_xyzz(slots_in + i);
-            acc.add(p);
+            if (COOP) coop_add4(acc, p, gmask, gbase, gl);
+            else acc.add(p);
         }
     }
     if (cur != KEY_NONE) flush(next_key == cur);
-    if (!last_level) {
+    if (!last_level && gl == 0) {
         // every slice with at least one item publishes both keys so the next level can detect
         // run boundaries by looking at adjacent slots only
         slot_keys[2 * t] = first_key == KEY_NONE ? KEY_NONE : (have_head ? first_key : (first_key | KEY_EMPTY_FLAG));
@@ -411,72 +424,79 @@ k_rowcol_partial(const G1Xyzz* __restrict__ in, uint32_t log_rows, uint32_t log_
     }
     store_xyzz(part + (size_t)w * total + t, acc);
 }
+// One warp per sum, as 8 groups of 4 lanes sharing every addition (coop_add4): group j adds the partials
+// j, j + 8, ... one after the other, then three pairwise steps between groups.
 __global__ void __launch_bounds__(RC_THREADS)
 k_rowcol_finish(const G1Xyzz* __restrict__ part, uint32_t log_rows, uint32_t log_cols, uint32_t q_c, uint32_t q_r,
                 G1Xyzz* __restrict__ out_c, G1Xyzz* __restrict__ out_r) {
-    __shared__ G1Xyzz sh[RC_THREADS];
     const uint32_t rows = 1u << log_rows, cols = 1u << log_cols, w = blockIdx.y;
     const uint32_t n_c = cols * q_c, total = n_c + rows * q_r;
-    const uint32_t lane = threadIdx.x % RC_LANES;
-    const uint32_t s = blockIdx.x * RC_SUMS + threadIdx.x / RC_LANES;
+    const int lane = threadIdx.x & 31, gl = lane & 3, gbase = lane - gl, grp = lane >> 2;
+    const uint32_t gmask = 0xfu << gbase;
+    const uint32_t s = blockIdx.x * RC_SUMS + threadIdx.x / 32;
+    if (s >= cols + rows) return;  // whole warp
     const G1Xyzz* p = part + (size_t)w * total;
+    const bool is_col = s < cols;
+    const uint32_t q = is_col ? q_c : q_r;
     G1Xyzz acc = G1Xyzz::infinity();
-    if (s < cols) {
-        for (uint32_t k = lane; k < q_c; k += RC_LANES) {
-            G1Xyzz v = load_xyzz(p + (size_t)k * cols + s);
-            acc.add(v);
-        }
-    } else if (s < cols + rows) {
-        for (uint32_t k = lane; k < q_r; k += RC_LANES) {
-            G1Xyzz v = load_xyzz(p + n_c + (size_t)(s - cols) * q_r + k);
-            acc.add(v);
-        }
+    for (uint32_t k = grp; k < q; k += 8) {
+        G1Xyzz v = load_xyzz(is_col ? p + (size_t)k * cols + s : p + n_c + (size_t)(s - cols) * q_r + k);
+        coop_add4(acc, v, gmask, gbase, gl);
     }
-    sh[threadIdx.x] = acc;
-    __syncthreads();
-    for (int st = RC_LANES / 2; st > 0; st >>= 1) {
-        if ((int)lane < st) {
-            G1Xyzz a = sh[threadIdx.x];
-            a.add(sh[threadIdx.x + st]);
-            sh[threadIdx.x] = a;
-        }
-        __syncthreads();
+    for (int st = 4; st > 0; st >>= 1) {
+        G1Xyzz o;
+        uint32_t* ov = o.x.v;
+        const uint32_t* av = acc.x.v;
+#pragma unroll
+        for (int i = 0; i < 48; i++) ov[i] = __shfl_down_sync(0xffffffffu, av[i], 4 * st);
+        if (grp < st) coop_add4(acc, o, gmask, gbase, gl);
     }
-    if (lane == 0 && s < cols + rows)
-        store_xyzz(s < cols ? out_c + (size_t)w * cols + s : out_r + (size_t)w * rows + (s - cols), sh[threadIdx.x]);
+    if (lane == 0) store_xyzz(is_col ? out_c + (size_t)w * cols + s : out_r + (size_t)w * rows + (s - cols), acc);
 }
 
 // Bit planes: block (j, w) computes P[w][j] = sum of the inputs whose weight has bit j set.  Planes
 // j < bits_a come from array a (n_a inputs per window, weight k + 1), planes j >= bits_a from array b
 // (n_b inputs per window, weight k).  The host finishes with Horner passes (sum_j 2^j P_j).
-constexpr int TAIL_THREADS = 128;
+constexpr int TAIL_THREADS = 256;
+// 8 warps x 8 groups of 4 lanes (coop_add4): group g adds the selected inputs g, g + 64, ... one after the other,
+// three pairwise steps inside the warp, the 8 warp results through shared memory, three more steps in warp 0.
 __global__ void __launch_bounds__(TAIL_THREADS)
 k_bit_sums(const G1Xyzz* __restrict__ a, uint32_t n_a, uint32_t bits_a, const G1Xyzz* __restrict__ b, uint32_t n_b,
            G1Xyzz* __restrict__ out, uint32_t out_stride) {
-    __shared__ G1Xyzz sh[TAIL_THREADS];
+    __shared__ G1Xyzz sh[TAIL_THREADS / 32];
     const uint32_t w = blockIdx.y;
     const bool first = blockIdx.x < bits_a;
     const uint32_t j = first ? blockIdx.x : blockIdx.x - bits_a;
     const uint32_t n_in = first ? n_a : n_b, one = first ? 1u : 0u;
     const G1Xyzz* in = (first ? a : b) + (size_t)w * n_in;
+    const int lane = threadIdx.x & 31, gl = lane & 3, gbase = lane - gl, warp = threadIdx.x >> 5;
+    const uint32_t gmask = 0xfu << gbase, grp_global = threadIdx.x >> 2, grp = lane >> 2;
+    constexpr uint32_t GROUPS = TAIL_THREADS / 4;
     G1Xyzz acc = G1Xyzz::infinity();
-    for (uint32_t k = threadIdx.x; k < n_in; k += TAIL_THREADS) {
-        if (((k + one) >> j) & 1) {
+    for (uint32_t k = grp_global; k < n_in; k += GROUPS) {
+        if (((k + one) >> j) & 1) {  // uniform inside a group
             G1Xyzz p = load_xyzz(in + k);
-            acc.add(p);
+            coop_add4(acc, p, gmask, gbase, gl);
         }
     }
-    sh[threadIdx.x] = acc;
+    auto fold_warp = [&]() {
+        for (int st = 4; st > 0; st >>= 1) {
+            G1Xyzz o;
+            uint32_t* ov = o.x.v;
+            const uint32_t* av = acc.x.v;
+#pragma unroll
+            for (int i = 0; i < 48; i++) ov[i] = __shfl_down_sync(0xffffffffu, av[i], 4 * st);
+            if (grp < st) coop_add4(acc, o, gmask, gbase, gl);
+        }
+    };
+    fold_warp();
+    if (lane == 0) sh[warp] = acc;
     __syncthreads();
-    for (int s = TAIL_THREADS / 2; s > 0; s >>= 1) {
-        if ((int)threadIdx.x < s) {
-            G1Xyzz t = sh[threadIdx.x];
-            t.add(sh[threadIdx.x + s]);
-            sh[threadIdx.x] = t;
-        }
-        __syncthreads();
+    if (warp == 0) {
+        acc = grp < TAIL_THREADS / 32 ? sh[grp] : G1Xyzz::infinity();
+        fold_warp();
+        if (lane == 0) store_xyzz(out + (size_t)w * out_stride + blockIdx.x, acc);
     }
-    if (threadIdx.x == 0) store_xyzz(out + (size_t)w * out_stride + blockIdx.x, sh[0]);
 }
 
 }  // namespace zkp

@@ -128,7 +128,9 @@ inline int msm_enqueue_main(zkp_ctx* ctx, int lane, const MsmPlan& plan, const G
     for (size_t l = 0; l < plan.levels.size(); l++) {
         const auto& lv = plan.levels[l];
         int last = l + 1 == plan.levels.size();
-        unsigned blocks = (unsigned)((lv.threads + 127) / 128);
+        // slot levels whose slices (x 4 lanes) fit the machine once are latency-bound: 4 lanes per slice
+        const bool coop = l > 0 && lv.threads * 4 <= (size_t)ctx->sm_count * 512;
+        unsigned blocks = (unsigned)((lv.threads * (coop ? 4 : 1) + 127) / 128);
         if (l == 0) {
             if (ctx->time_acc) cudaEventRecord(ev0, st);
             k_accumulate<true><<<blocks, 128, 0, st>>>(acc_keys, acc_vals, acc_points, nullptr,
@@ -137,12 +139,18 @@ inline int msm_enqueue_main(zkp_ctx* ctx, int lane, const MsmPlan& plan, const G
                                                        last ? nullptr : ws.slot_pts[0].as<G1Xyzz>(), last);
             if (ctx->time_acc) cudaEventRecord(ev1, st);
             trace_mark(ctx, lane, st, "accumulate_l0");
+        } else if (coop) {
+            k_accumulate<false, true><<<blocks, 128, 0, st>>>(ws.slot_keys[l - 1].as<uint32_t>(), nullptr, nullptr,
+                                                              ws.slot_pts[l - 1].as<G1Xyzz>(), lv.items, lv.L, plan.discard,
+                                                              ws.buckets.as<G1Xyzz>(),
+                                                              last ? nullptr : ws.slot_keys[l].as<uint32_t>(),
+                                                              last ? nullptr : ws.slot_pts[l].as<G1Xyzz>(), last);
         } else {
-            k_accumulate<false><<<blocks, 128, 0, st>>>(ws.slot_keys[l - 1].as<uint32_t>(), nullptr, nullptr,
-                                                        ws.slot_pts[l - 1].as<G1Xyzz>(), lv.items, lv.L, plan.discard,
-                                                        ws.buckets.as<G1Xyzz>(),
-                                                        last ? nullptr : ws.slot_keys[l].as<uint32_t>(),
-                                                        last ? nullptr : ws.slot_pts[l].as<G1Xyzz>(), last);
+            k_accumulate<false, false><<<blocks, 128, 0, st>>>(ws.slot_keys[l - 1].as<uint32_t>(), nullptr, nullptr,
+                                                               ws.slot_pts[l - 1].as<G1Xyzz>(), lv.items, lv.L, plan.discard,
+                                                               ws.buckets.as<G1Xyzz>(),
+                                                               last ? nullptr : ws.slot_keys[l].as<uint32_t>(),
+                                                               last ? nullptr : ws.slot_pts[l].as<G1Xyzz>(), last);
         }
         ctx->launches++;
     }
