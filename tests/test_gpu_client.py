@@ -160,6 +160,55 @@ def test_batched_challenge_equals_reference_flow(client):
     assert len(ch.evals) == TEST_MACHINE_COUNT and all(len(e) == 43 for e in ch.evals)
 
 
+def test_master_node_through_client(client, golden):
+    """Client.master_commit / master_open / master_verify (Pianist master node) against the golden vectors: the
+    four workers commit and open different rotations of TEST_POLY, the master aggregates and opens in Y."""
+    M = golden["pianist_master_4x16"]
+    poly, alpha = golden["test_poly"], golden["test_point"]
+    coms, evals, proofs = [], [], []
+    for i, rec in enumerate(M["rows"]):
+        with client.worker_commit_and_open(i, poly[i:] + poly[:i], alpha) as r:
+            assert r.status_code == 200
+            j = r.json()
+        assert base64.b64decode(j["commitment"]).hex() == rec["commitment"] and j["eval"] == rec["eval"]
+        coms.append(j["commitment"]); evals.append(j["eval"]); proofs.append(j["proof"])
+    with client.master_commit(coms) as r:
+        com = r.json()["commitment"]
+    assert base64.b64decode(com).hex() == M["commitment"]
+    with client.master_open(evals, proofs, M["beta"]) as r:
+        assert r.status_code == 200
+        j = r.json()
+    assert j["eval"] == M["z"] and base64.b64decode(j["proof_x"]).hex() == M["proof_x"]
+    assert base64.b64decode(j["proof_y"]).hex() == M["proof_y"]
+    with client.master_verify(j["proof_x"], j["proof_y"], alpha, M["beta"], j["eval"], com) as r:
+        assert r.status_code == 200 and r.json()["valid"] is True
+    with client.master_verify(j["proof_y"], j["proof_x"], alpha, M["beta"], j["eval"], com) as r:
+        assert r.json()["valid"] is False
+    with client.master_verify("garbage", j["proof_y"], alpha, M["beta"], j["eval"], com) as r:
+        assert r.status_code == 200 and r.json()["valid"] is False
+    with client.master_open(evals[:3], proofs[:3], M["beta"]) as r:
+        assert r.status_code == 400  # one evaluation per worker
+
+
+def test_pinned_staging_and_trace(client, golden):
+    """A polynomial handed over in a page-locked buffer (zkp_host_alloc) gives the same bytes as one in ordinary
+    memory; the stage trace entry reports both lanes."""
+    from zkp_subnet_b200 import native
+    ctx = client._need()
+    raw = b"".join(o.b64_decode(s) for s in golden["test_poly"])
+    x = o.b64_decode(golden["test_point"])
+    pin = native.PinnedBuffer(1 << 12).write(raw)
+    assert len(pin) == len(raw) and pin.tobytes() == raw
+    assert ctx.worker_commit_open(0, pin, x) == ctx.worker_commit_open(0, raw, x)
+    assert ctx.worker_commit(0, pin) == ctx.worker_commit(0, raw) and ctx.fft(pin) == ctx.fft(raw)
+    rows = ctx.bench_trace(0, raw, x, 1)
+    stages = {(lane, stage) for lane, stage, _ in rows}
+    assert ("0", "accumulate_l0") in stages and ("1", "open_field_kernels") in stages and rows[-1][0] == "host"
+    pin.close()
+    with pytest.raises(ValueError):
+        native.PinnedBuffer(64).write(b"x" * 65)
+
+
 def test_challenge_shape_and_wire_format(client):
     with client.random_poly() as r:
         poly = r.json()["poly"]

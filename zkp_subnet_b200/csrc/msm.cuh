@@ -3,9 +3,11 @@
 //
 // Pipeline (all on one stream, no host sync until the W window sums are read back):
 //   1. k_decompose      scalars (32 B, canonical) -> W signed c-bit digits each; emits
-//                       key = window * 2^(c-1) + |digit| - 1, val = point index | sign << 31
+//                       key = window * 2^(c-1) + |digit| - 1 and val = point index | sign << 31, or, with
+//                       fixed-base tables, key = |digit| - 1 and val = index into the table half of that sign
 //                       (zero digits get the DISCARD key and sort to the end).
 //   2. radix sort       (cub::DeviceRadixSort over the key bits actually used) -> bucket order.
+//  (2b. optional        rounds of batched-affine pairwise additions inside every bucket, msm_affine.cuh; off by default)
 //   3. k_accumulate     BALANCED bucket accumulation: thread t owns the fixed-length slice
 //                       [t*L, (t+1)*L) of the sorted entries, whatever buckets it spans, so every
 //                       thread performs the same number of mixed additions regardless of the
@@ -14,17 +16,19 @@
 //                       buckets and are written straight to the bucket array; the (at most two)
 //                       runs cut by a slice boundary go to a "slot" list, which is itself a sorted
 //                       (key, point) sequence and is reduced by the same kernel (XYZZ + XYZZ
-//                       instead of XYZZ + affine) level by level until one thread sees it all.
+//                       instead of XYZZ + affine) level by level until one thread sees it all; small slot
+//                       levels use four lanes per slice that share every addition (g1_coop.cuh).
 //                       Deterministic: no atomics anywhere.
-//   4. reduction        sum_b (b+1) B[b] with b = hi * 2^cl + lo: k_rowcol_sums forms the row sums R_hi and
-//                       column sums C_lo as plain tree sums (2 additions per bucket, depth ~11), k_bit_sums the
-//                       bit planes P_j = sum of the R (resp. C) whose weight has bit j set; the host finishes
-//                       with two Horner passes.  No long sequential chains: a lone warp needs ~17 us per point
-//                       addition on this machine, so depth, not work, is what the tail of an MSM costs.
+//   4. reduction        sum_b (b+1) B[b] with b = hi * 2^cl + lo: k_rowcol_partial / k_rowcol_finish form the row
+//                       sums R_hi and column sums C_lo (2 additions per bucket: one thread per interleaved
+//                       share of a sum, then one warp per sum), k_bit_sums the bit planes P_j = sum of the R
+//                       (resp. C) whose weight has bit j set; the host finishes with two Horner passes.  No long
+//                       sequential chains: a lone warp needs ~17 us per point addition on this machine, so depth,
+//                       not work, is what the tail of an MSM costs.
 //   5. host             Horner over the bit planes, window fold (classic mode only), to affine, compress.
 //
-// Fixed-base mode (plan.precomp): the SRS row is resident, so the context keeps [2^(c w)] P_i for every
-// digit position w (W x the row in HBM).  All digits then feed ONE set of 2^(c-1) buckets: no window fold,
+// Fixed-base mode (plan.precomp): the SRS row is resident, so the context keeps [+-2^(c w)] P_i for every
+// digit position w (2 W x the row in HBM).  All digits then feed ONE set of 2^(c-1) buckets: no window fold,
 // a 16x smaller reduction, and room for a wider window (c = log2 n), i.e. ~19% fewer bucket additions.
 #pragma once
 #include <cub/device/device_radix_sort.cuh>
