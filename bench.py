@@ -256,6 +256,10 @@ def main():
         t_job, e2e_job, ms_kernel_max = t_rank, e2e_rank, ms_kernel
 
     ok = ctx.worker_verify(row, proof, x, y, com)
+    t0 = time.perf_counter()
+    for _ in range(5):
+        ctx.worker_verify(row, proof, x, y, com)
+    verify_ms = (time.perf_counter() - t0) * 1e3 / 5  # host arithmetic (pairing): the validator's cost per response
 
     # ---- BASELINE configs[3]: one G1 MSM of 2^24 points (SRS row 1.5 GiB), point-range sharded over the N GPUs --
     #      rank g holds points [g n/N, (g+1) n/N) and the matching scalars, runs the whole Pippenger locally and
@@ -402,7 +406,7 @@ def main():
         "config_2p16": cfg2,
         "msm_sharded": msm24,
         "combine_ms_per_step": combine_ms,
-        "verified": bool(ok),
+        "verified": bool(ok), "worker_verify_ms_per_call_host": verify_ms,
     }
     # ---- CPU baseline (oracle port) on a bounded sample, rank 0 at N = 1 only
     if world == 1 and not args.no_cpu_baseline:
