@@ -70,3 +70,10 @@ def test_fq_inverse_binary_gcd(tmp_path):
             assert x * v % o.P == Rm * Rm % o.P, hex(x)
         n += 1
     assert n == 3001
+
+
+def test_host_pairing_fast_paths(tmp_path):
+    """csrc/host: complex Fq12 squaring, cyclotomic squaring and the endomorphism subgroup check agree with their
+    plain definitions (random Fq12 elements; curve points inside and outside the prime-order subgroup)."""
+    out = subprocess.check_output([build("pairing_host_test", tmp_path)]).decode().splitlines()
+    assert len(out) == 3 and all(line.split()[1] == "ok" for line in out), out

@@ -49,7 +49,34 @@ struct Fq12 {
         Fq6 r1 = (c0 + c1) * (o.c0 + o.c1) - t0 - t1;
         return {t0 + t1.mul_by_v(), r1};
     }
-    Fq12 sqr() const { return *this * *this; }
+    // (c0 + c1 w)^2 = (c0^2 + v c1^2) + 2 c0 c1 w with two Fq6 products: (c0 + c1)(c0 + v c1) = c0^2 + v c1^2 + (1 + v) c0 c1
+    Fq12 sqr() const {
+        Fq6 ab = c0 * c1;
+        Fq6 t = (c0 + c1) * (c0 + c1.mul_by_v());
+        return {t - ab - ab.mul_by_v(), ab + ab};
+    }
+    // Squaring in the cyclotomic subgroup (after the easy part of the final exponentiation): Granger-Scott, three
+    // Fq4 squarings = 9 Fq2 squarings instead of 12 Fq2 products.
+    static void fq4_square(const Fq2& a, const Fq2& b, Fq2& o0, Fq2& o1) {
+        Fq2 t0 = a.sqr(), t1 = b.sqr();
+        o0 = t1.mul_by_nonresidue() + t0;
+        o1 = (a + b).sqr() - t0 - t1;
+    }
+    Fq12 cyclotomic_sqr() const {
+        Fq2 z0 = c0.c0, z4 = c0.c1, z3 = c0.c2, z2 = c1.c0, z1 = c1.c1, z5 = c1.c2;
+        Fq2 t0, t1, t2, t3;
+        fq4_square(z0, z1, t0, t1);
+        z0 = (t0 - z0).dbl() + t0;
+        z1 = (t1 + z1).dbl() + t1;
+        fq4_square(z2, z3, t0, t1);
+        fq4_square(z4, z5, t2, t3);
+        z4 = (t0 - z4).dbl() + t0;
+        z5 = (t1 + z5).dbl() + t1;
+        t0 = t3.mul_by_nonresidue();
+        z2 = (t0 + z2).dbl() + t0;
+        z3 = (t2 - z3).dbl() + t2;
+        return {{z0, z4, z3}, {z2, z1, z5}};
+    }
     Fq12 conj() const { return {c0, c1.neg()}; }
     Fq12 inverse() const {
         Fq6 d = (c0 * c0 - (c1 * c1).mul_by_v()).inverse();
@@ -105,7 +132,7 @@ static const uint64_t BLS_X_ABS = 0xd201000000010000ull;  // |z|, z < 0
 inline Fq12 exp_by_z(const Fq12& f) {
     Fq12 acc = Fq12::one();
     for (int i = 63; i >= 0; i--) {
-        acc = acc.sqr();
+        acc = acc.cyclotomic_sqr();
         if ((BLS_X_ABS >> i) & 1) acc = acc * f;
     }
     return acc.conj();
@@ -120,7 +147,7 @@ inline Fq12 final_exponentiation(const Fq12& f) {
     Fq12 b = exp_by_z(a) * a.conj();          // t^((z-1)^2)
     Fq12 c = exp_by_z(b) * frobenius(b);      // ^(z+p)
     Fq12 d = exp_by_z(exp_by_z(c)) * frobenius(frobenius(c)) * c.conj();  // ^(z^2+p^2-1)
-    return d * t.sqr() * t;                   // * t^3
+    return d * t.cyclotomic_sqr() * t;        // * t^3
 }
 
 // Line coefficients of the Miller loop for a fixed Q on the twist (affine arithmetic).
