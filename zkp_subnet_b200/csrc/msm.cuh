@@ -91,6 +91,21 @@ inline uint32_t msm_window_bits(uint32_t n, bool precomp) {
     int c = precomp ? lg : lg - 4;
     if (c < 4) c = 4;
     if (c > (precomp ? 22 : 16)) c = precomp ? 22 : 16;
+    if (precomp && lg >= 18) {
+        // Large fixed-base MSMs: W = floor(255/c) + 1 only changes at a few widths (13 for c = 20 and 21, 12 for
+        // 22 and 23), so the width is chosen by cost (tools/window_sweep.py, B200): n W additions at 0.36 ns, plus
+        // a reduction that is latency-bound (~1.1 ms) up to 2^19 buckets and 2.1 ns per bucket beyond.  E.g.
+        // n = 2^21 takes c = 20, not 21 (same W, half the buckets: 11.96 vs 13.09 ms); 2^18 and 2^19 measured
+        // best at c = 16.
+        if (lg <= 19) return 16;
+        double best = 1e300;
+        for (int cc = lg - 3; cc <= 24; cc++) {
+            double tail = 2.1 * (double)(1ull << (cc - 1));
+            if (tail < 1.1e6) tail = 1.1e6;
+            double cost = 0.36 * (double)n * (255 / cc + 1) + tail;
+            if (cost < best * 0.999) { best = cost; c = cc; }
+        }
+    }
     return (uint32_t)c;
 }
 
