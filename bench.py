@@ -340,6 +340,36 @@ def main():
         for pb in polys2:
             pb.close()
 
+    # ---- the same 2^20 request stream through 3 contexts on 3 host threads (requests in flight overlap the
+    #      reduction tail and the upload of one with the accumulation of another); host buffers in, results out
+    pipelined = None
+    if not args.no_config2:
+        import concurrent.futures
+        nctx, per = 3, 6
+        ctxs = [native.Context(local) for _ in range(nctx)]
+        pins = []
+        for k, c3 in enumerate(ctxs):
+            c3.srs_generate(TAU_X, TAU_Y, log_n, log_m)
+            pins.append(native.PinnedBuffer(len(poly)).write(poly))
+            c3.worker_commit_open(row, pins[k], x)
+
+        def work3(k):
+            out = None
+            for _ in range(per):
+                out = ctxs[k].worker_commit_open(row, pins[k], x)
+            return out
+        with concurrent.futures.ThreadPoolExecutor(nctx) as ex:
+            list(ex.map(work3, range(nctx)))
+            t0 = time.perf_counter()
+            outs3 = list(ex.map(work3, range(nctx)))
+            thr3 = nctx * per / (time.perf_counter() - t0)
+        pipelined = {"contexts": nctx, "commit_open_per_s": thr3, "matches": all(o == (com, y, proof) for o in outs3),
+                     "note": "e2e (pinned host buffers in, results on host), per GPU; compare with e2e.value of this rank"}
+        for c3 in ctxs:
+            c3.close()
+        for pb in pins:
+            pb.close()
+
     imad_peak, fq_chain_peak = ctx.bench_peaks()
     ms_msm, _ = ctx.bench_msm(row, poly, 5, True)
     ms_kernel_alone = ctx.bench_last_kernel_ms()  # the dominant kernel with nothing else on the device
@@ -404,6 +434,7 @@ def main():
                 "frac_hbm": 64.0 * n / (ms_ntt * 1e-3) / 1e9 / hbm_peak,
                 "fr_mul_frac_of_imad_peak": (n / 2 * log_n) * 136 / (ms_ntt * 1e-3) / imad_peak},
         "config_2p16": cfg2,
+        "pipelined_2p20": pipelined,
         "msm_sharded": msm24,
         "combine_ms_per_step": combine_ms,
         "verified": bool(ok), "worker_verify_ms_per_call_host": verify_ms,
