@@ -60,6 +60,9 @@ int zkp_host_free(void* p);
  *      (Lagrange basis over the natural-order domains), plus [R_i(tau_y)]_1 per row and [tau_x]_2. */
 int zkp_srs_generate(zkp_ctx* ctx, const uint8_t tau_x_be[32], const uint8_t tau_y_be[32],
                      uint32_t log_n, uint32_t log_machines);
+/* the monomial SRS [tau_x^j]_1 as the single row (commitment from COEFFICIENTS; "path B" of BASELINE configs[2]:
+ * zkp_fft(inverse) then zkp_msm_g1 over this row equals zkp_worker_commit over the Lagrange row, byte for byte) */
+int zkp_srs_generate_monomial(zkp_ctx* ctx, const uint8_t tau_x_be[32], uint32_t log_n);
 /* point-range shard `shard` of 2^log_shards of the same SRS: rows hold points j in
  * [shard*n/S, (shard+1)*n/S); an MSM over the row with the matching scalar slice is one GPU's partial
  * commitment (MSM sharding by point range) */

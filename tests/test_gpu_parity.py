@@ -307,6 +307,25 @@ def test_full_size_trapdoor_identity(gpu_ctx, log_n):
     assert com == ref.g1_mul_gen(f_tau)
 
 
+@pytest.mark.parametrize("log_n", [4, 12, 20])
+def test_commit_path_a_equals_path_b(gpu_ctx, log_n, golden):
+    """BASELINE configs[2]: path A = MSM of the evaluations over the Lagrange SRS; path B = iNTT on the GPU, then
+    MSM of the coefficients over the monomial SRS [tau^j]_1.  Two SRS forms, two scalar vectors, identical bytes."""
+    n = 1 << log_n
+    evals = b"".join(o.b64_decode(s) for s in golden["test_poly"]) if log_n == 4 else gpu_ctx.random_poly(0xAB + log_n, n)
+    gpu_ctx.srs_generate(TAU_X, TAU_Y, log_n, 0)
+    path_a = gpu_ctx.worker_commit(0, evals)
+    coeffs = gpu_ctx.fft(evals, True, True)
+    gpu_ctx.srs_generate_monomial(TAU_X, log_n)
+    path_b = gpu_ctx.msm_g1(0, coeffs)
+    assert path_a == path_b
+    if log_n == 4:
+        assert path_a.hex() == golden["B_eval_form"]["commitment"]
+        # and the monomial row itself against the oracle, plus the coefficient-form golden vector A
+        assert gpu_ctx.srs_export_row(0, n) == ref.srs(n, TAU_X, "monomial")
+        assert gpu_ctx.msm_g1(0, evals).hex() == golden["A_coeff_form"]["commitment"]
+
+
 def test_sharded_commit_combines_to_full(gpu_ctx):
     # point-range sharding (SURVEY.md section 8e): partial commitments of the 4 shards sum to the commitment
     log_n, log_s = 12, 2

@@ -389,6 +389,48 @@ int zkp_srs_generate_shard(zkp_ctx* ctx, const uint8_t tau_x_be[32], const uint8
     return ZKP_OK;
 }
 
+// Monomial SRS [tau^j]_1, j < 2^log_n, as the single row of the context (BASELINE configs[2] "path B": iNTT of
+// the evaluations, then an MSM over the monomial basis, must give the bytes of the Lagrange-basis commitment).
+int zkp_srs_generate_monomial(zkp_ctx* ctx, const uint8_t tau_x_be[32], uint32_t log_n) {
+    if (!ctx || !tau_x_be) return fail(ZKP_ERR_ARG, "null argument");
+    Fr64 tx;
+    if (!Fr64::from_be(tx, tau_x_be)) return fail(ZKP_ERR_ENCODING, "trapdoor not canonical");
+    int rc = zkp_srs_set_shape(ctx, log_n, 0);
+    if (rc) return rc;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    DeviceGuard g(ctx->device);
+    rc = ensure_fixed_base(ctx);
+    if (rc) return rc;
+    const uint32_t n = 1u << log_n;
+    cudaStream_t st = ctx->stream;
+    std::vector<Fr64> tt(32);
+    tt[0] = tx;
+    for (size_t k = 1; k < tt.size(); k++) tt[k] = tt[k - 1].sqr();
+    ZKP_CUDA(ctx->partials.ensure(tt.size() * 32));
+    ZKP_CUDA(cudaMemcpyAsync(ctx->partials.p, tt.data(), tt.size() * 32, cudaMemcpyHostToDevice, st));
+    ZKP_CUDA(cudaStreamSynchronize(st));  // tt is a host stack object
+    ZKP_CUDA(ctx->fr_c.ensure((size_t)n * 32));
+    ZKP_CUDA(ctx->ws.buckets.ensure((size_t)n * sizeof(G1Xyzz)));
+    ZKP_CUDA(ctx->ws.pool.ensure((size_t)n * sizeof(Fq)));
+    k_power_scalars<<<((n + 7) / 8 + 127) / 128, 128, 0, st>>>(ctx->partials.as<Fr>(), n, ctx->fr_c.as<Fr>());
+    k_fixed_base_mul<<<(n + 127) / 128, 128, 0, st>>>(ctx->fr_c.as<Fr>(), n, ctx->fixed_base.as<G1Affine>(), ctx->ws.buckets.as<G1Xyzz>());
+    uint32_t EA = 16, ta = (n + EA - 1) / EA;
+    k_xyzz_to_affine<<<(ta + 127) / 128, 128, 0, st>>>(ctx->ws.buckets.as<G1Xyzz>(), n, EA, ctx->ws.pool.as<Fq>(), ctx->srs.as<G1Affine>());
+    ctx->launches += 3;
+    ZKP_CUDA(cudaStreamSynchronize(st));
+    ZKP_CUDA(cudaGetLastError());
+    ctx->scale_points[0] = host::g1_generator();
+    ctx->row_loaded[0] = 1;
+    Fr64 txc = tx.from_mont();
+    ctx->g2_tau = host::g2_generator().mul(txc.v, 4);
+    ctx->have_g2_tau = true;
+    ctx->have_g2_tau_y = false;
+    set_pairing_lines(ctx);
+    ctx->shard_domain_log = log_n;
+    ctx->shard_index = 0;
+    return ZKP_OK;
+}
+
 // sum of compressed G1 points (the only cross-GPU step of a sharded / Pianist commitment: N partial
 // points, 48 bytes each, combined on the host of rank 0)
 int zkp_g1_sum(const uint8_t* points48, size_t count, uint8_t out48[48]) {

@@ -92,6 +92,20 @@ __global__ void k_lagrange_scalars(const Fr* __restrict__ inv_d, uint32_t n, con
     }
 }
 
+// out[j] = tau^j (the scalars of the monomial SRS [tau^j]_1); tt[k] = tau^(2^k)
+__global__ void k_power_scalars(const Fr* __restrict__ tt, uint32_t n, Fr* __restrict__ out) {
+    constexpr uint32_t E = 8;
+    uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    uint64_t lo = (uint64_t)t * E;
+    if (lo >= n) return;
+    Fr a = pow_from_table(tt, lo);
+    const Fr tau = load_fr(tt);
+    for (uint32_t i = 0; i < E && lo + i < n; i++) {
+        store_fr(out + lo + i, a);
+        a = a * tau;
+    }
+}
+
 // [s]G for Montgomery-form scalars with the fixed-base table tab[w*256 + d] = [d * 256^w]G (affine)
 __global__ void __launch_bounds__(128)
 k_fixed_base_mul(const Fr* __restrict__ scalars, size_t n, const G1Affine* __restrict__ tab, G1Xyzz* __restrict__ out) {

@@ -40,6 +40,7 @@ _SIGNATURES = {
     "zkp_host_alloc": [ctypes.c_size_t, ctypes.POINTER(ctypes.c_void_p)],
     "zkp_host_free": [ctypes.c_void_p],
     "zkp_srs_generate": [_ctxp, _u8p, _u8p, ctypes.c_uint32, ctypes.c_uint32],
+    "zkp_srs_generate_monomial": [_ctxp, _u8p, ctypes.c_uint32],
     "zkp_srs_generate_shard": [_ctxp, _u8p, _u8p, ctypes.c_uint32, ctypes.c_uint32, ctypes.c_uint32, ctypes.c_uint32],
     "zkp_g1_sum": [_u8p, ctypes.c_size_t, _u8p],
     "zkp_g1_uncompress": [_u8p, _u8p],
@@ -186,6 +187,9 @@ class Context:
     # ---- SRS
     def srs_generate(self, tau_x: int, tau_y: int, log_n: int, log_machines: int) -> None:
         check(lib().zkp_srs_generate(self._h, tau_x.to_bytes(32, "big"), tau_y.to_bytes(32, "big"), log_n, log_machines))
+
+    def srs_generate_monomial(self, tau_x: int, log_n: int) -> None:
+        check(lib().zkp_srs_generate_monomial(self._h, tau_x.to_bytes(32, "big"), log_n))
 
     def srs_generate_shard(self, tau_x: int, tau_y: int, log_n: int, log_machines: int, shard: int, log_shards: int) -> None:
         check(lib().zkp_srs_generate_shard(self._h, tau_x.to_bytes(32, "big"), tau_y.to_bytes(32, "big"), log_n,
