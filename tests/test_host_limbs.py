@@ -77,3 +77,74 @@ def test_host_pairing_fast_paths(tmp_path):
     plain definitions (random Fq12 elements; curve points inside and outside the prime-order subgroup)."""
     out = subprocess.check_output([build("pairing_host_test", tmp_path)]).decode().splitlines()
     assert len(out) == 3 and all(line.split()[1] == "ok" for line in out), out
+
+
+def test_lazy_field_helpers_and_madd_lazy(tmp_path):
+    """The lazily reduced Fq helpers on WIDE operands (up to the ranges tools/lazy_bounds.py allows, edge values
+    included) against exact integer formulas -- an overflow of the even/odd accumulators would show up as a wrong
+    integer, not just a wrong residue -- and G1Xyzz::madd_lazy beside the fully reduced madd (doubling and
+    cancellation hit while the accumulator is loose; coordinate ranges checked after every step)."""
+    import random
+    exe = build("lazy_host_test", tmp_path)
+    p, M = o.P, 1 << 384
+    ninv = (-pow(p, -1, M)) % M
+    rng = random.Random(0xB200)
+
+    def wide(k_num, k_den=1):  # random value below k p, with edge values mixed in
+        top = p * k_num // k_den
+        c = rng.randrange(8)
+        if c == 0:
+            return max(0, min(top - 1, p * rng.randrange(0, k_num // k_den + 1) + rng.randrange(-2, 3)))
+        if c == 1:
+            return top - 1 - rng.randrange(3)
+        if c == 2:
+            return min(top - 1, int("".join(rng.choice(["00000000", "ffffffff"]) for _ in range(12)), 16))
+        return rng.randrange(top)
+
+    cases = []
+    for _ in range(300):
+        cases.append(("A", wide(16, 5), wide(16, 5)))       # both below 3.2 p: mul, sqr, add, mul2
+        cases.append(("B", wide(44, 5), wide(49, 5)))       # multiplicand below 8.8 p, multiplier below 9.8 p: mul
+        cases.append(("C", wide(2), wide(2)))               # differences with + 2p
+        cases.append(("D", wide(2), wide(6)))               # sub_fix
+    inp = "".join(f"{a:096x} {b:096x}\n" for _, a, b in cases).encode()
+    out = subprocess.run([exe], input=inp, stdout=subprocess.PIPE, check=True).stdout.decode().split("\n")
+    recs, cur = [], {}
+    for line in out:
+        if not line:
+            continue
+        k, v = line.split()
+        if k == "a" and cur:
+            recs.append(cur)
+            cur = {}
+        cur[k] = int(v, 16)
+    recs.append(cur)
+    assert len(recs) == len(cases)
+
+    def redc(t):
+        return (t + (t * ninv % M) * p) >> 384
+
+    n = 0
+    for (kind, a, b), r in zip(cases, recs):
+        assert (r["a"], r["b"]) == (a, b)
+        if kind in "AB":
+            assert r["mul"] == redc(a * b) < M, (kind, hex(a), hex(b))
+            n += 1
+        if kind == "A":
+            assert r["sqr"] == redc(a * a)
+            assert r["add"] == a + b
+            t = redc(2 * a * b)
+            assert r["mul2"] == (t - p if t >= p else t)
+            n += 3
+        if kind == "C":
+            assert r["subp2"] == a - b + 2 * p and r["rsubp2"] == 2 * p - b
+            n += 2
+        if kind == "D":
+            v = r["subfix"]
+            assert (v - (a - b)) % p == 0 and 0 <= v < max(a + 1, p + (p >> 24)), (hex(a), hex(b), hex(v))
+            if a >= b:
+                assert v == a - b
+            n += 1
+    assert n > 2000
+    res = subprocess.run([exe, "group"], stdout=subprocess.PIPE).stdout.decode().split()
+    assert res[0] == "ok" and int(res[1]) >= 400, res

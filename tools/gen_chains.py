@@ -323,6 +323,66 @@ def gen_extra(name, mod, n):
     return out
 
 
+def gen_lazy(name, mod, n):
+    """Unreduced helpers for the lazily reduced mixed addition (g1.cuh madd_lazy; ranges in tools/lazy_bounds.py):
+    all results are plain integers modulo 2^(32 n), the callers keep them below that."""
+    out = ""
+    m2 = limbs(2 * mod, n)
+
+    def chain(b, op0, opc, opl, dst, s1, s2):
+        for j in range(n):
+            op = op0 if j == 0 else (opc if j < n - 1 else opl)
+            b.emit(op, dst(j), s1(j), s2(j))
+
+    # ---- r = a + b
+    b = Block()
+    r = lambda j: b.operand(f"r{j}", "=r", f"r[{j}]")
+    aa = lambda j: b.operand(f"a{j}", "r", f"a[{j}]")
+    bb = lambda j: b.operand(f"b{j}", "r", f"b[{j}]")
+    for j in range(n):
+        r(j)
+    chain(b, "add.cc.u32", "addc.cc.u32", "addc.u32", r, aa, bb)
+    out += func(f"{name}_add_raw(uint32_t* r, const uint32_t* a, const uint32_t* b)", [b])
+
+    # ---- r = a - b, *bw = 0xffffffff when a < b (r is then a - b + 2^(32 n))
+    b = Block()
+    r = lambda j: b.operand(f"r{j}", "=r", f"r[{j}]")
+    aa = lambda j: b.operand(f"a{j}", "r", f"a[{j}]")
+    bb = lambda j: b.operand(f"b{j}", "r", f"b[{j}]")
+    for j in range(n):
+        r(j)
+    b.operand("mk", "=r", "mk")
+    chain(b, "sub.cc.u32", "subc.cc.u32", "subc.cc.u32", r, aa, bb)
+    b.emit("subc.u32", "mk", 0, 0)
+    out += func(f"{name}_sub_borrow(uint32_t* r, const uint32_t* a, const uint32_t* b, uint32_t* bw)",
+                ["    uint32_t mk;\n", b, "    *bw = mk;\n"])
+
+    # ---- r = a - b + 2p   (a - b + 2p must lie in [0, 2^(32 n)))
+    b = Block()
+    r = lambda j: b.operand(f"r{j}", "=r", f"r[{j}]")
+    aa = lambda j: b.operand(f"a{j}", "r", f"a[{j}]")
+    bb = lambda j: b.operand(f"b{j}", "r", f"b[{j}]")
+    for j in range(n):
+        r(j)
+    chain(b, "sub.cc.u32", "subc.cc.u32", "subc.u32", r, aa, bb)
+    b2 = Block()
+    r2 = lambda j: b2.operand(f"r{j}", "+r", f"r[{j}]")
+    for j in range(n):
+        r2(j)
+    chain(b2, "add.cc.u32", "addc.cc.u32", "addc.u32", r2, r2, lambda j: m2[j])
+    out += func(f"{name}_sub_p2(uint32_t* r, const uint32_t* a, const uint32_t* b)", [b, b2])
+
+    # ---- r = 2p - b   (b <= 2p)
+    b = Block()
+    r = lambda j: b.operand(f"r{j}", "=r", f"r[{j}]")
+    bb = lambda j: b.operand(f"b{j}", "r", f"b[{j}]")
+    for j in range(n):
+        r(j)
+    chain(b, "sub.cc.u32", "subc.cc.u32", "subc.u32", r, lambda j: m2[j], bb)
+    out += func(f"{name}_rsub_p2(uint32_t* r, const uint32_t* b)", [b])
+    return out
+
+
 hdr = """// GENERATED by tools/gen_chains.py -- do not edit.
 // One inline-asm statement per carry chain (see the generator's docstring).
 #pragma once
@@ -332,7 +392,7 @@ namespace zkp {
 namespace chains {
 
 """
-body = gen_field("fq", P, 12) + gen_extra("fq", P, 12) + gen_field("fr", R, 8)
+body = gen_field("fq", P, 12) + gen_extra("fq", P, 12) + gen_lazy("fq", P, 12) + gen_field("fr", R, 8)
 path = os.path.join(os.path.dirname(__file__), "..", "zkp_subnet_b200", "csrc", "mont_chains.cuh")
 open(path, "w").write(hdr + body + "}  // namespace chains\n}  // namespace zkp\n")
 print("wrote", os.path.abspath(path))

@@ -16,6 +16,19 @@
 
 namespace zkp {
 
+// limb i of k p (Fq), k < 8: the correction table of Fp::sub_fix and the constants of is_zero_mod_p_lt4
+ZKP_PARAM_HD constexpr uint32_t fq_kp_limb(uint32_t k, int i) {
+    uint64_t carry = 0;
+    uint32_t out = 0;
+    for (int j = 0; j <= i; j++) {
+        uint64_t t = (uint64_t)FqParams::mod(j) * k + carry;
+        out = (uint32_t)t;
+        carry = t >> 32;
+    }
+    return out;
+}
+constexpr int FQ_KP_ROWS = 8;
+
 template <class P>
 struct Fp {
     static constexpr int N = P::N;
@@ -84,7 +97,11 @@ struct Fp {
     // ---------------------------------------------------------------- Montgomery product
     // Row i adds a*b_i and m_i*p to the pair of accumulators and divides by 2^32; the accumulator
     // aligned on even limb positions and the one aligned on odd positions swap roles every row.
-    friend ZKP_HD Fp operator*(const Fp& a, const Fp& b) {
+    friend ZKP_HD Fp operator*(const Fp& a, const Fp& b) { return mul_t<true>(a, b); }
+    // REDUCE = false leaves out the final conditional subtraction: the result is (a b + m p) / 2^(32 N) < a b / 2^(32 N) + p
+    // (Fq only; operand ranges in tools/lazy_bounds.py)
+    template <bool REDUCE>
+    static ZKP_HD Fp mul_t(const Fp& a, const Fp& b) {
         uint32_t even[N], odd[N];
         Fp r;
         if constexpr (N == 12) {
@@ -140,7 +157,7 @@ struct Fp {
             }
 #endif
             chains::fq_merge(r.v, odd, even);
-            chains::fq_reduce_once(r.v, 0);
+            if (REDUCE) chains::fq_reduce_once(r.v, 0);
         } else {
             chains::fr_row_first(even, odd, a.v, b.v[0]);
             chains::fr_row(odd, even, a.v, b.v[1]);
@@ -157,7 +174,9 @@ struct Fp {
     // Dedicated squaring (Fq): row i multiplies a_i with (a_i, 2a_{i+1}, .., 2a_{N-1}) only -- N(N+1)/2 = 78
     // products instead of 144, plus the same 156 of the reduction: 234 wide multiply-accumulates instead of 300.
     // 2a < 2^382 fits the 12 limbs.  Fully unrolled (every row has its own shape).
-    ZKP_HD Fp sqr() const {
+    ZKP_HD Fp sqr() const { return sqr_t<true>(); }
+    template <bool REDUCE>
+    ZKP_HD Fp sqr_t() const {
         if constexpr (N == 12) {
             uint32_t even[N], odd[N], d[N];
 #pragma unroll
@@ -179,7 +198,7 @@ struct Fp {
             chains::fq_sqr_row_11(odd, even, v, d);
             Fp r;
             chains::fq_merge(r.v, odd, even);
-            chains::fq_reduce_once(r.v, 0);
+            if (REDUCE) chains::fq_reduce_once(r.v, 0);
             return r;
         } else {
             return *this * *this;
@@ -189,7 +208,9 @@ struct Fp {
     // 2*144 + 156 = 444 wide multiply-accumulates instead of 600 for two products, and no separate addition.
     // Inputs in [0, p); the accumulator stays below a + c + p < 3p and the result below 1.2p before the final
     // conditional subtraction.
-    static ZKP_HD Fp mul2(const Fp& a, const Fp& b, const Fp& c, const Fp& d) {
+    static ZKP_HD Fp mul2(const Fp& a, const Fp& b, const Fp& c, const Fp& d) { return mul2_t<true>(a, b, c, d); }
+    template <bool REDUCE>
+    static ZKP_HD Fp mul2_t(const Fp& a, const Fp& b, const Fp& c, const Fp& d) {
         if constexpr (N == 12) {
             uint32_t even[N], odd[N];
 #pragma unroll
@@ -214,11 +235,72 @@ struct Fp {
 #endif
             Fp r;
             chains::fq_merge(r.v, odd, even);
-            chains::fq_reduce_once(r.v, 0);
+            if (REDUCE) chains::fq_reduce_once(r.v, 0);
             return r;
         } else {
             return a * b + c * d;
         }
+    }
+
+    // ---------------------------------------------------------------- lazily reduced helpers (Fq)
+    // Plain 384-bit integers, not residues in [0, p): used by G1Xyzz::madd_lazy only, which keeps every value below
+    // 2^384 (tools/lazy_bounds.py) and hands canonical coordinates back through reduce_once().
+    static ZKP_HD Fp mul_lazy(const Fp& a, const Fp& b) { return mul_t<false>(a, b); }
+    ZKP_HD Fp sqr_lazy() const { return sqr_t<false>(); }
+    static ZKP_HD Fp add_raw(const Fp& a, const Fp& b) {
+        static_assert(N == 12, "Fq only");
+        Fp r;
+        chains::fq_add_raw(r.v, a.v, b.v);
+        return r;
+    }
+    // a - b + 2p (b < 2p)
+    static ZKP_HD Fp sub_p2(const Fp& a, const Fp& b) {
+        static_assert(N == 12, "Fq only");
+        Fp r;
+        chains::fq_sub_p2(r.v, a.v, b.v);
+        return r;
+    }
+    // 2p - a (a <= 2p)
+    ZKP_HD Fp rsub_p2() const {
+        static_assert(N == 12, "Fq only");
+        Fp r;
+        chains::fq_rsub_p2(r.v, v);
+        return r;
+    }
+    // a - b brought back into [0, max(a, p (1 + 2^-24))): when the difference is negative, k p is added with
+    // k = (2^32 - top limb) / (top limb of p) + 1, the smallest multiple that is certain to make it positive.
+    // kp = table of the limbs of k p, k < 8 (fq_kp_limb); |a - b| < 6 p.
+    static ZKP_HD Fp sub_fix(const Fp& a, const Fp& b, const uint32_t* kp) {
+        static_assert(N == 12, "Fq only");
+        Fp r;
+        uint32_t bw;
+        chains::fq_sub_borrow(r.v, a.v, b.v, &bw);
+        const uint32_t k = bw ? (0u - r.v[N - 1]) / P::mod(N - 1) + 1u : 0u;
+        Fp c;
+#pragma unroll
+        for (int i = 0; i < N; i++) c.v[i] = kp[k * N + i];
+        return add_raw(r, c);
+    }
+    // one conditional subtraction of p: [0, 2p) -> [0, p)
+    ZKP_HD Fp reduce_once() const {
+        static_assert(N == 12, "Fq only");
+        Fp r = *this;
+        chains::fq_reduce_once(r.v, 0);
+        return r;
+    }
+    // value in (0, 4p): is it a multiple of p?  (limb 0 of p, 2p, 3p first: almost never equal)
+    ZKP_HD bool is_zero_mod_p_lt4() const {
+        bool hit = false;
+#pragma unroll
+        for (uint32_t k = 1; k <= 3; k++) {
+            if (v[0] == fq_kp_limb(k, 0)) {
+                uint32_t acc = 0;
+#pragma unroll
+                for (int i = 0; i < N; i++) acc |= v[i] ^ fq_kp_limb(k, i);
+                hit |= acc == 0;
+            }
+        }
+        return hit;
     }
 
     // ---------------------------------------------------------------- Montgomery domain

@@ -102,6 +102,56 @@ struct G1Xyzz {
         madd(p.x, p.y, negate);
     }
 
+    // The same addition with LAZY reductions, for the bucket-accumulation kernel (msm.cuh k_accumulate<level0>), where
+    // one accumulator takes a run of additions and only the end of the run is stored.  Coordinates are plain
+    // 384-bit integers congruent to the true values: X < 2p, Y < 1.42p, ZZ < 1.26p, ZZZ < 1.2p (a box that the
+    // step maps into itself: tools/lazy_bounds.py checks it and every overflow condition with exact rationals).
+    //  * the seven single products skip their final conditional subtraction (result < ab/2^384 + p);
+    //  * the differences that feed products are a - b + 2p, unconditionally;
+    //  * X3 = R^2 - (PPP + 2Q) is the one value corrected on both sides (Fq::sub_fix: + k p with k read off the
+    //    top limb), Y3 keeps the single conditional subtraction of the fused product.
+    // About 170 add/sub/select instructions per addition instead of 460; the multiply count is unchanged.
+    // (px, py) canonical and not infinity.  kp = limbs of k p for k < 8 (shared memory on the device).
+    // normalize() returns canonical coordinates; infinity stays the all-zero record throughout.
+    ZKP_HD void madd_lazy(const Fq& px, const Fq& py, const uint32_t* kp) {
+        const int st = madd_lazy_core(px, py, kp);
+        if (st) madd_lazy_rare(st, px, py);
+    }
+    // The arithmetic of madd_lazy with the exceptional cases only DETECTED: returns 0 when the sum is in *this,
+    // 1 when the operands were equal (the sum is 2 (px, py)), 2 when they were opposite (the sum is infinity); in
+    // both cases *this is garbage and madd_lazy_rare finishes the job.  Keeping the test out of the way lets the
+    // products start before it resolves and lets the caller reload (px, py) in the rare case instead of holding
+    // them in registers through the whole addition.
+    ZKP_HD int madd_lazy_core(const Fq& px, const Fq& py, const uint32_t* kp) {
+        if (is_inf()) {
+            x = px; y = py; zz = Fq::one(); zzz = Fq::one();
+            return 0;
+        }
+        Fq u2 = Fq::mul_lazy(px, zz);
+        Fq s2 = Fq::mul_lazy(py, zzz);
+        Fq p = Fq::sub_p2(u2, x);   // in (0, 3.13p)
+        Fq r = Fq::sub_p2(s2, y);   // in (0, 3.13p)
+        const bool p_zero = p.is_zero_mod_p_lt4();
+        Fq pp = p.sqr_lazy();
+        Fq ppp = Fq::mul_lazy(p, pp);
+        Fq q = Fq::mul_lazy(x, pp);
+        Fq s = Fq::add_raw(Fq::add_raw(ppp, q), q);  // PPP + 2Q < 4.45p
+        Fq x3 = Fq::sub_fix(r.sqr_lazy(), s, kp);
+        y = Fq::mul2(r, Fq::sub_p2(q, x3), ppp, y.rsub_p2());  // < 2.42p before, < 1.42p after its conditional subtraction
+        x = x3;
+        zz = Fq::mul_lazy(zz, pp);
+        zzz = Fq::mul_lazy(zzz, ppp);
+        if (p_zero) return r.is_zero_mod_p_lt4() ? 1 : 2;
+        return 0;
+    }
+    ZKP_HD void madd_lazy_rare(int st, const Fq& px, const Fq& py) {
+        if (st == 1) *this = dbl_affine(px, py);  // P + P
+        else *this = infinity();                  // P + (-P)
+    }
+    ZKP_HD void normalize() {
+        x = x.reduce_once(); y = y.reduce_once(); zz = zz.reduce_once(); zzz = zzz.reduce_once();
+    }
+
     // this += o   (add-2008-s: 12M + 2S)
     ZKP_HD void add(const G1Xyzz& o) {
         if (o.is_inf()) return;

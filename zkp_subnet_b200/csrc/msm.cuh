@@ -263,6 +263,18 @@ __device__ __forceinline__ G1Affine load_affine(const G1Affine* src) {
     return p;
 }
 
+// a second read of the same record that the compiler cannot fold into the first one
+__device__ __forceinline__ G1Affine load_affine_again(const G1Affine* src) {
+    G1Affine p;
+    uint32_t* d = p.x.v;
+#pragma unroll
+    for (int i = 0; i < 6; i++)
+        asm volatile("ld.global.v4.u32 {%0, %1, %2, %3}, [%4];"
+                     : "=r"(d[4 * i]), "=r"(d[4 * i + 1]), "=r"(d[4 * i + 2]), "=r"(d[4 * i + 3])
+                     : "l"(reinterpret_cast<const uint4*>(src) + i));
+    return p;
+}
+
 // LEVEL0: items are (key, point index|sign) entries, points gathered from the affine SRS row.
 // else  : items are (key|flags, XYZZ) slots written by the previous level.
 template <bool LEVEL0, bool COOP = false>
@@ -278,6 +290,12 @@ k_accumulate(const uint32_t* __restrict__ keys, const uint32_t* __restrict__ val
     // multiplies).
     static_assert(!(LEVEL0 && COOP), "level 0 is one thread per slice");
     constexpr int LANES = COOP ? 4 : 1;
+    // level 0 adds with lazy reductions (G1Xyzz::madd_lazy); its correction table k p, k < 8, lives in shared memory
+    __shared__ uint32_t s_kp[LEVEL0 ? FQ_KP_ROWS * 12 : 1];
+    if (LEVEL0) {
+        if (threadIdx.x < FQ_KP_ROWS * 12) s_kp[threadIdx.x] = fq_kp_limb(threadIdx.x / 12, threadIdx.x % 12);
+        __syncthreads();
+    }
     size_t t = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) / LANES;
     const int lane_id = threadIdx.x & 31, gl = lane_id & (LANES - 1), gbase = lane_id - gl;
     const uint32_t gmask = COOP ? (0xfu << gbase) : 0u;
@@ -305,6 +323,7 @@ k_accumulate(const uint32_t* __restrict__ keys, const uint32_t* __restrict__ val
 
     // a finished run goes to the bucket array if it is wholly inside this slice, else to a slot
     auto flush = [&](bool continues_after) {
+        if (LEVEL0) acc.normalize();  // lazy coordinates -> canonical
         bool starts_before = is_first_run && cur == prev_key;
         if (last_level || (!starts_before && !continues_after)) {
             if (!acc.is_inf() && gl == 0) store_xyzz(buckets + cur, acc);
@@ -349,7 +368,14 @@ k_accumulate(const uint32_t* __restrict__ keys, const uint32_t* __restrict__ val
             }
             G1Affine p = load_affine(points + (v & 0x7fffffffu));
             if (v >> 31) p.y = p.y.neg();  // never taken with a negated table half (-(0, 0) stays the infinity marker)
-            acc.madd(p, 0);
+            if (!p.is_inf()) {
+                const int st = acc.madd_lazy_core(p.x, p.y, s_kp);
+                if (st) {  // equal or opposite operands: fetch the point again rather than keep it live
+                    p = load_affine_again(points + (v & 0x7fffffffu));
+                    if (v >> 31) p.y = p.y.neg();
+                    acc.madd_lazy_rare(st, p.x, p.y);
+                }
+            }
         } else if (!(raw & KEY_EMPTY_FLAG)) {
             G1Xyzz p = load_xyzz(slots_in + i);
             if (COOP) coop_add4(acc, p, gmask, gbase, gl);
