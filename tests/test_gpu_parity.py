@@ -307,6 +307,27 @@ def test_full_size_trapdoor_identity(gpu_ctx, log_n):
     assert com == ref.g1_mul_gen(f_tau)
 
 
+def test_commit_open_2p24_trapdoor_identity(gpu_ctx):
+    """BASELINE configs[3] and the north_star size: one SRS row of 2^24 points (1.5 GiB affine, 36 GiB of fixed-base
+    tables), commitment and opening proof checked through the trapdoor (commit == [sum f_j L_j(tau)]_1,
+    proof == [sum q_j L_j(tau)]_1 with q from the oracle's quotient), y against the oracle, pairing check on the
+    host.  The level-0 accumulation kernel runs its longest slices here."""
+    log_n = 24
+    n = 1 << log_n
+    gpu_ctx.srs_generate(TAU_X, TAU_Y, log_n, 0)
+    sc = gpu_ctx.random_poly(0xB200 + 4, n)
+    x = ref.random_scalars(77 + log_n, 1)
+    com, y, proof = gpu_ctx.worker_commit_open(0, sc, x)
+    ls = ref.lagrange_scalars(n, TAU_X)
+    assert com == ref.g1_mul_gen(ref.fr_dot(sc, ls))
+    assert com == gpu_ctx.worker_commit(0, sc)
+    ey, q = ref.quotient_evals(sc, x)
+    assert y == ey
+    assert proof == ref.g1_mul_gen(ref.fr_dot(q, ls))
+    assert gpu_ctx.worker_verify(0, proof, x, y, com)
+    gpu_ctx.srs_generate(TAU_X, TAU_Y, 4, 0)  # drop the 2^24 row and its tables before the next test
+
+
 @pytest.mark.parametrize("log_n", [4, 12, 20])
 def test_commit_path_a_equals_path_b(gpu_ctx, log_n, golden):
     """BASELINE configs[2]: path A = MSM of the evaluations over the Lagrange SRS; path B = iNTT on the GPU, then

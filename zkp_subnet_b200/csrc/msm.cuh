@@ -76,6 +76,9 @@ constexpr uint32_t REDUCE_DIRECT_MAX = 1024;
 #ifndef ZKP_ACC_MIN_BLOCKS
 #define ZKP_ACC_MIN_BLOCKS 3
 #endif
+#ifndef ZKP_ACC_THREADS
+#define ZKP_ACC_THREADS 128
+#endif
 #ifndef ZKP_SLOT_L1
 #define ZKP_SLOT_L1 8
 #endif
@@ -127,7 +130,7 @@ inline MsmPlan msm_make_plan(uint32_t n, int sm_count, uint32_t c, bool precomp,
     for (uint32_t r = 0; r < p.affine_rounds; r++) p.bound[r + 1] = (p.bound[r] + p.discard + 1) / 2;  // sum ceil(len/2) <= (N + buckets)/2
     p.acc_items = p.bound[p.affine_rounds];
     // level 0: slice length chosen so that the grid is a whole number of waves of resident threads
-    const size_t resident = (size_t)sm_count * 128 * ZKP_ACC_MIN_BLOCKS;
+    const size_t resident = (size_t)sm_count * ZKP_ACC_THREADS * ZKP_ACC_MIN_BLOCKS;
     // ~6 waves: long slices mean few slice-boundary partials for the slot levels, and because every
     // thread does the same work the last wave is as full as the first
 #ifndef ZKP_L0_TARGET
@@ -278,7 +281,7 @@ __device__ __forceinline__ G1Affine load_affine_again(const G1Affine* src) {
 // LEVEL0: items are (key, point index|sign) entries, points gathered from the affine SRS row.
 // else  : items are (key|flags, XYZZ) slots written by the previous level.
 template <bool LEVEL0, bool COOP = false>
-__global__ void __launch_bounds__(128, LEVEL0 ? ZKP_ACC_MIN_BLOCKS : 1)
+__global__ void __launch_bounds__(LEVEL0 ? ZKP_ACC_THREADS : 128, LEVEL0 ? ZKP_ACC_MIN_BLOCKS : 1)
 k_accumulate(const uint32_t* __restrict__ keys, const uint32_t* __restrict__ vals,
              const G1Affine* __restrict__ points, const G1Xyzz* __restrict__ slots_in, size_t items,
              uint32_t L, uint32_t discard, G1Xyzz* __restrict__ buckets, uint32_t* __restrict__ slot_keys,
@@ -293,7 +296,7 @@ k_accumulate(const uint32_t* __restrict__ keys, const uint32_t* __restrict__ val
     // level 0 adds with lazy reductions (G1Xyzz::madd_lazy); its correction table k p, k < 8, lives in shared memory
     __shared__ uint32_t s_kp[LEVEL0 ? FQ_KP_ROWS * 12 : 1];
     if (LEVEL0) {
-        if (threadIdx.x < FQ_KP_ROWS * 12) s_kp[threadIdx.x] = fq_kp_limb(threadIdx.x / 12, threadIdx.x % 12);
+        for (uint32_t i = threadIdx.x; i < FQ_KP_ROWS * 12; i += blockDim.x) s_kp[i] = fq_kp_limb(i / 12, i % 12);
         __syncthreads();
     }
     size_t t = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) / LANES;

@@ -132,8 +132,9 @@ inline int msm_enqueue_main(zkp_ctx* ctx, int lane, const MsmPlan& plan, const G
         const bool coop = l > 0 && lv.threads * 4 <= (size_t)ctx->sm_count * 512;
         unsigned blocks = (unsigned)((lv.threads * (coop ? 4 : 1) + 127) / 128);
         if (l == 0) {
+            blocks = (unsigned)((lv.threads + ZKP_ACC_THREADS - 1) / ZKP_ACC_THREADS);
             if (ctx->time_acc) cudaEventRecord(ev0, st);
-            k_accumulate<true><<<blocks, 128, 0, st>>>(acc_keys, acc_vals, acc_points, nullptr,
+            k_accumulate<true><<<blocks, ZKP_ACC_THREADS, 0, st>>>(acc_keys, acc_vals, acc_points, nullptr,
                                                        lv.items, lv.L, plan.discard, ws.buckets.as<G1Xyzz>(),
                                                        last ? nullptr : ws.slot_keys[0].as<uint32_t>(),
                                                        last ? nullptr : ws.slot_pts[0].as<G1Xyzz>(), last);
