@@ -148,3 +148,11 @@ def test_lazy_field_helpers_and_madd_lazy(tmp_path):
     assert n > 2000
     res = subprocess.run([exe, "group"], stdout=subprocess.PIPE).stdout.decode().split()
     assert res[0] == "ok" and int(res[1]) >= 400, res
+
+
+def test_lazy_range_proof_script():
+    """tools/lazy_bounds.py: the coordinate box of madd_lazy maps into itself and no accumulator of the even/odd
+    product rows can overflow (exact rationals; the script asserts, this test runs it)."""
+    out = subprocess.run(["python", os.path.join(ROOT, "tools", "lazy_bounds.py")], stdout=subprocess.PIPE, check=True,
+                         timeout=120).stdout.decode()
+    assert "invariant box" in out and "X < 1.99" in out, out

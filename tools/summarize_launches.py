@@ -11,9 +11,9 @@ for f in sys.argv[1:]:
         short = re.sub(r"\(.*", "", name)
         short = re.sub(r"^void ", "", short)
         if "k_accumulate" in short:
-            short = "zkp::k_accumulate<level0>" if ("<1>" in name or "<(bool)1>" in name) else "zkp::k_accumulate<slots>"
+            short = "zkp::k_accumulate<level0>" if re.search(r"k_accumulate<(\(bool\))?1\b", name) else "zkp::k_accumulate<slots>"
         elif "k_affine_round" in short:
-            short = "zkp::k_affine_round<first>" if ("<1>" in name or "<(bool)1>" in name) else "zkp::k_affine_round<next>"
+            short = "zkp::k_affine_round<first>" if re.search(r"k_affine_round<(\(bool\))?1\b", name) else "zkp::k_affine_round<next>"
         else:
             short = re.sub(r"<.*", "", short)
         v = float(r["Metric Value"].replace(",", ""))

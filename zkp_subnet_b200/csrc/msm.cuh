@@ -82,6 +82,9 @@ constexpr uint32_t REDUCE_DIRECT_MAX = 1024;
 #ifndef ZKP_SLOT_L1
 #define ZKP_SLOT_L1 8
 #endif
+#ifndef ZKP_SLOT_LN
+#define ZKP_SLOT_LN 8   // slice length of the slot levels after the first
+#endif
 
 inline uint32_t ilog2_floor(uint32_t n) {
     uint32_t lg = 0;
@@ -154,7 +157,7 @@ inline MsmPlan msm_make_plan(uint32_t n, int sm_count, uint32_t c, bool precomp,
         // shallow slot levels: every sequential addition costs ~17 us of latency.  For scalars that are not
         // adversarial almost every slot run is one (tail_t, head_t+1) pair, so the first slot level can be
         // made a single parallel addition per thread
-        L = lvl == 0 ? ZKP_SLOT_L1 : 8;
+        L = lvl == 0 ? ZKP_SLOT_L1 : ZKP_SLOT_LN;
     }
     // reduction plan
     if (p.B > REDUCE_DIRECT_MAX) {
