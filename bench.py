@@ -214,7 +214,7 @@ def main():
     e2e_pageable_ms = (time.perf_counter() - t0) * 1e3 / 3
     # ---- and through the reference-facing shim: fourier.Client.worker_commit_and_open(i, List[str], str) -- base64
     #      decode of 2^20 strings on the host + the call above + base64 of the results
-    client_ms = None
+    client_ms = client_two_calls_ms = None
     if rank == 0:
         import base64
         from zkp_subnet_b200.client import Client, encode_poly
@@ -227,6 +227,15 @@ def main():
             resp = cl.worker_commit_and_open(row, strs, xs)
         client_ms = (time.perf_counter() - t0) * 1e3 / 3
         assert resp.status_code == 200 and base64.b64decode(resp.json()["commitment"]) == com
+        # the UNMODIFIED reference miner makes two calls and ships the polynomial twice
+        # (neurons/miner.py:56-61: rpc_commit, then rpc_open)
+        t0 = time.perf_counter()
+        for _ in range(3):
+            r1 = cl.worker_commit(row, strs)
+            r2 = cl.worker_open(row, strs, xs)
+        client_two_calls_ms = (time.perf_counter() - t0) * 1e3 / 3
+        assert r1.status_code == 200 and base64.b64decode(r1.json()["commitment"]) == com
+        assert r2.status_code == 200 and base64.b64decode(r2.json()["proof"]) == proof
         cl.stop()
         del strs
 
@@ -414,7 +423,8 @@ def main():
                 "d2h_bytes_per_step": d2h_bytes, "ms_per_step": e2e_job / args.steps,
                 "api": "zkp_worker_commit_open (C ABI; polynomial in page-locked host memory from zkp_host_alloc -> results on host)",
                 "ms_per_step_pageable_input": e2e_pageable_ms,
-                "ms_per_call_via_fourier_Client_list_of_base64_str": client_ms},
+                "ms_per_call_via_fourier_Client_list_of_base64_str": client_ms,
+                "ms_via_fourier_Client_worker_commit_then_worker_open": client_two_calls_ms},
         "roofline": {"bound": "imad", "kernel": "k_accumulate<level0>", "achieved": achieved, "peak": peak,
                      "unit": "G Fq-mul/s", "frac": achieved / peak, "traffic": traffic,
                      "note": "bound is INT32 multiply issue (IMAD.WIDE.U32, fmaheavy pipe), neither HBM nor tensor: "

@@ -7,7 +7,7 @@ for f in sys.argv[1:]:
     for r in csv.DictReader(lines):
         if r.get("Metric Name") == "gpu__time_duration.sum":
             name = re.sub(r"\(.*", "", r["Kernel Name"])
-            name = re.sub(r"<.*", "", name) + ("<L0>" if "k_accumulate<1>" in r["Kernel Name"] or "k_accumulate<(bool)1>" in r["Kernel Name"] else "")
+            name = re.sub(r"<.*", "", name) + ("<L0>" if re.search(r"k_accumulate<(\(bool\))?1\b", r["Kernel Name"]) else "")
             val = float(r["Metric Value"].replace(",", ""))
             unit = r["Metric Unit"]
             val = val / 1e3 if unit == "ns" else (val * 1e3 if unit == "ms" else val)
