@@ -229,6 +229,8 @@ def main():
         assert resp.status_code == 200 and base64.b64decode(resp.json()["commitment"]) == com
         # the UNMODIFIED reference miner makes two calls and ships the polynomial twice
         # (neurons/miner.py:56-61: rpc_commit, then rpc_open)
+        cl.worker_commit(row, strs)
+        cl.worker_open(row, strs, xs)  # warm-up: allocates the second page-locked staging buffer (one-off)
         t0 = time.perf_counter()
         for _ in range(3):
             r1 = cl.worker_commit(row, strs)

@@ -106,6 +106,12 @@ int zkp_worker_commit(zkp_ctx* ctx, uint32_t i, const uint8_t* poly_be, size_t n
 /* Client.worker_open(i, poly, x)  (reference neurons/miner.py:47-54): y = f_i(x), proof = [q_i]_1 */
 int zkp_worker_open(zkp_ctx* ctx, uint32_t i, const uint8_t* poly_be, size_t n, const uint8_t x_be[32],
                     uint8_t eval_be[32], uint8_t proof48[48]);
+/* The second half of the reference's two-call flow (neurons/miner.py:56-61: rpc_commit(i, poly), then
+ * rpc_open(i, poly, alpha) with the SAME poly): opens the polynomial that the previous zkp_worker_commit /
+ * zkp_worker_open / zkp_worker_commit_open call on this context left on the device, without a second upload.
+ * ZKP_ERR_STATE when no polynomial of n elements is resident (any other call that stages scalars drops it). */
+int zkp_worker_open_resident(zkp_ctx* ctx, uint32_t i, size_t n, const uint8_t x_be[32], uint8_t eval_be[32],
+                             uint8_t proof48[48]);
 /* Miner.rpc_commit_and_open fused (reference neurons/miner.py:56-61): one upload, both MSMs */
 int zkp_worker_commit_open(zkp_ctx* ctx, uint32_t i, const uint8_t* poly_be, size_t n, const uint8_t x_be[32],
                            uint8_t commitment48[48], uint8_t eval_be[32], uint8_t proof48[48]);

@@ -247,3 +247,45 @@ def test_concurrent_forwards(client, golden):
     for i in range(4):
         assert base64.b64decode(out[i].commitment).hex() == rec[i]["commitment"]
         assert base64.b64decode(out[i].proof).hex() == rec[i]["proof"]
+
+
+def test_worker_open_after_worker_commit_reuses_the_resident_polynomial(client, golden):
+    """The reference's two-call flow (neurons/miner.py:56-61) through the shim: worker_open after worker_commit of the
+    same list takes the speculative path (resident polynomial, no second upload) and must give the bytes of a plain
+    worker_open; a different list of the same length, a list mutated in place, and a call that drops the resident
+    polynomial in between must all be noticed."""
+    import random
+    rng = random.Random(7)
+    n = 1 << (TEST_SCALE - TEST_MACHINES_SCALE)
+    enc = lambda v: base64.b64encode(v.to_bytes(32, "big")).decode().rstrip("=")
+    poly_a = [enc(rng.randrange(o.R)) for _ in range(n)]
+    poly_b = [enc(rng.randrange(o.R)) for _ in range(n)]
+    x = enc(rng.randrange(o.R))
+    fresh = Client(setup_path=client.setup_path)
+    fresh.start(scale=TEST_SCALE, machines_scale=TEST_MACHINES_SCALE)
+    try:
+        expect = {}
+        for name, p in (("a", poly_a), ("b", poly_b)):
+            expect[name] = fresh.worker_open(1, list(p), x).json()      # never preceded by a call on the same list
+            fresh.fft(poly_a, True, False)                              # drops the resident polynomial
+        assert client.worker_commit(1, poly_a).status_code == 200
+        assert client._resident_n == n
+        assert client.worker_open(1, poly_a, x).json() == expect["a"]   # speculative result accepted
+        assert client.worker_open(1, list(poly_a), x).json() == expect["a"]   # an equal COPY of the list as well
+        assert client.worker_open(1, poly_b, x).json() == expect["b"]   # same length, other polynomial: rejected, redone
+        assert client.worker_open(1, poly_b, x).json() == expect["b"]   # ... and poly_b is the resident one now
+        poly_b2 = list(poly_b)
+        poly_b2[5] = poly_a[5]                                          # "mutated in place"
+        want = fresh.worker_open(1, poly_b2, x).json()
+        assert client.worker_open(1, poly_b2, x).json() == want != expect["b"]
+        assert client.worker_commit(1, poly_a).status_code == 200
+        assert client.fft(poly_b, True, False).status_code == 200       # another call stages scalars on the device
+        assert client.worker_open(1, poly_a, x).json() == expect["a"]
+        # a malformed element is an error response whichever path is taken
+        assert client.worker_commit(1, poly_a).status_code == 200
+        bad = list(poly_a)
+        bad[3] = "!" * 43
+        assert client.worker_open(1, bad, x).status_code == 400
+        assert client.worker_open(1, poly_a, x).json() == expect["a"]
+    finally:
+        fresh.stop()

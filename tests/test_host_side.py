@@ -54,6 +54,27 @@ def test_wire_list_codec(golden):
     with pytest.raises(ValueError, match="element 15001"):
         native.wire_decode_list(lst)
     assert decode_poly(golden["test_poly"]) == b"".join(o.b64_decode(s) for s in golden["test_poly"])
+    # decode + compare in one pass (the speculative worker_open of the Client shim): same list, one changed element,
+    # a changed element behind a subclassed str (serial fallback path), malformed element
+    import ctypes
+    w = native.wire()
+    n = len(strs)
+    out, ref, same = ctypes.create_string_buffer(32 * n), ctypes.create_string_buffer(raw, 32 * n), ctypes.c_int(-1)
+    call = lambda lst: w.zkp_wire_decode_list_cmp(lst, ctypes.addressof(out), 32 * n, ctypes.addressof(ref), ctypes.byref(same))
+    assert call(strs) == n and same.value == 1 and out.raw == raw
+    lst = list(strs)
+    lst[12345] = strs[12344]
+    assert call(lst) == n and same.value == 0 and out.raw[32 * 12345:32 * 12346] == raw[32 * 12344:32 * 12345]
+
+    class S(str):
+        pass
+    lst = list(strs)
+    lst[3] = S(strs[3])
+    assert call(lst) == n and same.value == 1
+    lst[3] = S(strs[4])
+    assert call(lst) == n and same.value == 0
+    lst[3] = "?" * 43
+    assert call(lst) == -1 - 3
 
 
 def test_g1_sum(golden):

@@ -94,6 +94,8 @@ class Client:
         self.machines_scale = None
         self._ctx: Optional[native.Context] = None
         self._staging: Optional[native.PinnedBuffer] = None
+        self._staging_alt: Optional[native.PinnedBuffer] = None  # second buffer of the speculative worker_open
+        self._resident_n = 0  # > 0: self._staging holds the n x 32 bytes of the polynomial still resident on the GPU
         self._lock = threading.Lock()  # the staging buffer is shared: one prover call at a time, as in the library
         self._seed = seed if seed is not None else secrets.randbits(63)
         self._counter = 0
@@ -126,9 +128,11 @@ class Client:
     def stop(self) -> None:
         if getattr(self, "_attached", False):
             self._ctx = None
-        if self._staging is not None:
-            self._staging.close()
-            self._staging = None
+        self._resident_n = 0
+        for name in ("_staging", "_staging_alt"):
+            if getattr(self, name) is not None:
+                getattr(self, name).close()
+                setattr(self, name, None)
         if self._ctx is not None:
             self._ctx.close()
             self._ctx = None
@@ -136,6 +140,7 @@ class Client:
     def _decode(self, poly: Sequence[str]):
         """Decode a wire polynomial into the client's page-locked staging buffer (grown on demand)."""
         need = 32 * len(poly)
+        self._resident_n = 0  # the staging buffer is about to change
         if need == 0:
             return b""
         if self._staging is None or self._staging.capacity < need:
@@ -164,6 +169,7 @@ class Client:
         try:
             with self._lock:
                 com = self._need().worker_commit(int(i), self._decode(poly))
+                self._resident_n = len(poly)
             return Response(200, {"commitment": _b64_point(com)})
         except (ValueError, native.ZkpError) as e:
             return self._fail(e)
@@ -171,16 +177,75 @@ class Client:
     def worker_open(self, i: int, poly: Sequence[str], x: str) -> Response:
         try:
             with self._lock:
-                y, proof = self._need().worker_open(int(i), self._decode(poly), _decode_any(x, 32))
+                y, proof = self._open_locked(int(i), poly, _decode_any(x, 32))
             return Response(200, {"eval": _b64_fr(y), "proof": _b64_point(proof)})
         except (ValueError, TypeError, native.ZkpError) as e:
             return self._fail(e)
+
+    def _open_locked(self, i: int, poly: Sequence[str], xb: bytes):
+        """worker_open.  The reference miner calls worker_commit(i, poly) and then worker_open(i, poly, x) with the
+        same list (neurons/miner.py:56-61), i.e. it ships the polynomial twice.  When a polynomial of the same length
+        is still resident on the GPU, the opening of THAT polynomial starts at once while a helper thread decodes
+        the list that was actually given into the second staging buffer and compares it, element by element, with
+        the bytes of the resident one.  Equal (the reference flow): the result is already on its way
+        and neither the decode nor a second upload is on the critical path.  Different: the speculative result is
+        dropped and the regular path runs on the freshly decoded bytes."""
+        ctx = self._need()
+        n = len(poly)
+        if not (n and self._resident_n == n and self._staging is not None):
+            y, proof = ctx.worker_open(i, self._decode(poly), xb)
+            self._resident_n = n
+            return y, proof
+        if self._staging_alt is None or self._staging_alt.capacity < 32 * n:
+            if self._staging_alt is not None:
+                self._staging_alt.close()
+            self._staging_alt = native.PinnedBuffer(max(32 * n, self._staging.capacity))
+        # The list is decoded on a helper thread and the GPU call is made from THIS thread: the decoder keeps the
+        # GIL for its whole call (ctypes.PyDLL), the prover call releases it (ctypes.CDLL), so the helper gets
+        # going the moment this thread is inside the library.  The helper waits for `go`, which is set right before
+        # the prover call: started any earlier it would take the GIL first and the decode would run BEFORE the GPU
+        # work instead of beside it (measured at 2^20: 9.5 ms per call instead of 7.1).
+        dec = {}
+        go = threading.Event()
+
+        def run():
+            go.wait()
+            try:
+                dec["ok"] = native.wire_decode_list(poly, self._staging_alt, same_as=self._staging)
+            except Exception as e:
+                dec["err"] = e
+
+        t = threading.Thread(target=run)
+        t.start()
+        spec = err = None
+        try:
+            go.set()
+            spec = ctx.worker_open_resident(i, n, xb)
+        except native.ZkpError as e:  # resident polynomial dropped by another call on a shared context, bad x, ...
+            err = e
+        finally:
+            go.set()
+            t.join()
+        if "err" in dec:
+            raise dec["err"]
+        buf, same = dec["ok"]
+        if same and spec is not None:
+            return spec
+        if same and err is not None and err.code != native.ZKP_ERR_STATE:
+            raise err
+        # not the resident polynomial: the new bytes become the staged ones
+        self._resident_n = 0
+        self._staging, self._staging_alt = self._staging_alt, self._staging
+        y, proof = ctx.worker_open(i, buf, xb)
+        self._resident_n = n
+        return y, proof
 
     def worker_commit_and_open(self, i: int, poly: Sequence[str], x: str) -> Response:
         """Fused form of the reference's rpc_commit_and_open (neurons/miner.py:56-61): one decode, one upload."""
         try:
             with self._lock:
                 com, y, proof = self._need().worker_commit_open(int(i), self._decode(poly), _decode_any(x, 32))
+                self._resident_n = len(poly)
             return Response(200, {"commitment": _b64_point(com), "eval": _b64_fr(y), "proof": _b64_point(proof)})
         except (ValueError, TypeError, native.ZkpError) as e:
             return self._fail(e)

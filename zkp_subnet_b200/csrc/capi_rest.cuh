@@ -96,10 +96,15 @@ int open_device(zkp_ctx* ctx, cudaStream_t st, const Fr* d_f, uint32_t n, const 
 }
 
 // upload poly (big-endian), convert to Montgomery in fr_a; leaves the raw bytes in ctx->scalars
+int convert_poly(zkp_ctx* ctx, size_t n);
 int upload_poly(zkp_ctx* ctx, const uint8_t* poly_be, size_t n) {
     int rc = upload_scalars(ctx, poly_be, n, ctx->scalars);
     if (rc) return rc;
-    rc = ensure_small(ctx);
+    return convert_poly(ctx, n);
+}
+// raw big-endian bytes in ctx->scalars -> Montgomery form in fr_a (flags non-canonical elements)
+int convert_poly(zkp_ctx* ctx, size_t n) {
+    int rc = ensure_small(ctx);
     if (rc) return rc;
     ZKP_CUDA(ctx->fr_a.ensure(n * 32));
     ZKP_CUDA(cudaMemsetAsync(small_at<uint32_t>(ctx, SM_BAD), 0, 4, ctx->stream));
@@ -576,6 +581,21 @@ int zkp_worker_open(zkp_ctx* ctx, uint32_t i, const uint8_t* poly_be, size_t n, 
     DeviceGuard g(ctx->device);
     rc = upload_poly(ctx, poly_be, n);
     if (rc) return rc;
+    rc = commit_open_resident(ctx, i, n, x, nullptr, eval_be, proof48);
+    if (rc == ZKP_OK) ctx->resident_n = n;
+    return rc;
+}
+
+int zkp_worker_open_resident(zkp_ctx* ctx, uint32_t i, size_t n, const uint8_t x_be[32], uint8_t eval_be[32], uint8_t proof48[48]) {
+    Fr64 x;
+    int rc = open_checks(ctx, i, x_be /* any non-null pointer */, n, x_be, &x);
+    if (rc) return rc;
+    if (!eval_be || !proof48) return fail(ZKP_ERR_ARG, "null output");
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    DeviceGuard g(ctx->device);
+    if (ctx->resident_n != n) return fail(ZKP_ERR_STATE, "no polynomial of this size is resident on the device");
+    rc = convert_poly(ctx, n);
+    if (rc) return rc;
     return commit_open_resident(ctx, i, n, x, nullptr, eval_be, proof48);
 }
 
@@ -589,7 +609,9 @@ int zkp_worker_commit_open(zkp_ctx* ctx, uint32_t i, const uint8_t* poly_be, siz
     DeviceGuard g(ctx->device);
     rc = upload_poly(ctx, poly_be, n);
     if (rc) return rc;
-    return commit_open_resident(ctx, i, n, x, commitment48, eval_be, proof48);
+    rc = commit_open_resident(ctx, i, n, x, commitment48, eval_be, proof48);
+    if (rc == ZKP_OK) ctx->resident_n = n;
+    return rc;
 }
 
 // ---------------------------------------------------------------------------------------------- sharded open
@@ -1007,6 +1029,7 @@ int zkp_random_poly(zkp_ctx* ctx, uint64_t seed, uint8_t* out_be, size_t count) 
     if (!ctx || !out_be || !count) return fail(ZKP_ERR_ARG, "bad argument");
     std::lock_guard<std::mutex> lk(ctx->mu);
     DeviceGuard g(ctx->device);
+    ctx->resident_n = 0;
     ZKP_CUDA(ctx->scalars.ensure(count * 32));
     k_random_fr<<<(unsigned)((count + 255) / 256), 256, 0, ctx->stream>>>(seed, count, ctx->scalars.as<uint32_t>());
     ctx->launches++;
@@ -1207,6 +1230,7 @@ int zkp_bench_ntt(zkp_ctx* ctx, size_t n, int reps, int inverse, float* ms_per_n
     DeviceGuard g(ctx->device);
     ZKP_CUDA(ctx->fr_a.ensure(n * 32));
     ZKP_CUDA(ctx->fr_b.ensure(n * 32));
+    ctx->resident_n = 0;
     ZKP_CUDA(ctx->scalars.ensure(n * 32));
     k_random_fr<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(0xB200, n, ctx->scalars.as<uint32_t>());
     int rc = ensure_small(ctx);

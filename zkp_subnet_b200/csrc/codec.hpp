@@ -76,8 +76,9 @@ inline unsigned codec_threads(size_t count) {
 
 // runs fn(begin, end) over [0, count) on codec_threads(count) host threads
 template <class Fn>
-inline void parallel_ranges(size_t count, Fn fn) {
+inline void parallel_ranges(size_t count, Fn fn, unsigned max_threads = 0) {
     unsigned nt = codec_threads(count);
+    if (max_threads && nt > max_threads) nt = max_threads;
     if (nt <= 1) { fn((size_t)0, count); return; }
     std::vector<std::thread> th;
     th.reserve(nt - 1);

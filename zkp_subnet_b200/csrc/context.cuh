@@ -91,6 +91,9 @@ struct zkp_ctx {
     zkp::host::G2J g2_tau_y;                  // [tau_y]_2 (Pianist master verification only)
     // scratch
     zkp::DevBuf scalars, fr_a, fr_b, fr_c, flush;
+    // > 0: `scalars` still holds the n big-endian evaluations uploaded by the last worker_commit / worker_open /
+    // worker_commit_open call (zkp_worker_open_resident); every other writer of `scalars` clears it
+    size_t resident_n = 0;
     zkp::MsmWorkspace ws;                     // lane 0 workspace (runs on `stream`)
     // lane 1: second stream + workspace so that the two MSMs of a commit+open (and their
     // latency-bound reduction tails) overlap on the device

@@ -20,7 +20,15 @@ extern "C" {
 
 // list of str/bytes (43 or 44 chars each) -> out[32 * n].  Returns n, or -1 - i when element i is not a
 // valid field-element string, or a value <= -(1 << 40) for a wrong argument type / too small a buffer.
-long long zkp_wire_decode_list(PyObject* seq, uint8_t* out, size_t capacity) {
+// The compare variant runs BESIDE a prover call that is launching kernels from another thread of this process: it
+// takes half of the cores so that the launching thread is never waiting for a time slice.
+static unsigned cmp_threads() {
+    unsigned hw = std::thread::hardware_concurrency();
+    return hw >= 4 ? hw / 2 : 1;
+}
+// ref != nullptr: also compares every decoded element with ref[32 i ..] and reports *same (the fourier.Client
+// shim uses it to recognise the polynomial it was handed by the previous call, see client.py worker_open)
+static long long decode_list_impl(PyObject* seq, uint8_t* out, size_t capacity, const uint8_t* ref, int* same) {
     const long long BAD_ARG = -(1ll << 40);
     if (!seq || !out || !(PyList_Check(seq) || PyTuple_Check(seq))) return BAD_ARG;
     const Py_ssize_t n = PySequence_Fast_GET_SIZE(seq);
@@ -34,6 +42,7 @@ long long zkp_wire_decode_list(PyObject* seq, uint8_t* out, size_t capacity) {
     // uses the regular API with the GIL held.  (Measured on the 16-core GPU host at n = 2^20: a fourier.Client commit+open call went from 26.9 to 16.1 ms when the
     // walk moved from the calling thread to the workers.)
     std::atomic<size_t> first_bad((size_t)n), first_slow((size_t)n);
+    std::atomic<int> differs(0);
     auto lower = [](std::atomic<size_t>& a, size_t i) {
         size_t cur = a.load();
         while (i < cur && !a.compare_exchange_weak(cur, i)) {}
@@ -57,8 +66,9 @@ long long zkp_wire_decode_list(PyObject* seq, uint8_t* out, size_t capacity) {
                 lower(first_bad, i);
                 return;
             }
+            if (ref && memcmp(out + 32 * i, ref + 32 * i, 32) != 0) differs.store(1, std::memory_order_relaxed);
         }
-    });
+    }, ref ? cmp_threads() : 0u);
     // serial pass over the elements the workers skipped (none for the lists the reference sends)
     for (size_t i = first_slow.load(); i < (size_t)n && i < first_bad.load(); i++) {
         PyObject* it = items[i];
@@ -80,9 +90,18 @@ long long zkp_wire_decode_list(PyObject* seq, uint8_t* out, size_t capacity) {
             lower(first_bad, i);
             break;
         }
+        if (ref && memcmp(out + 32 * i, ref + 32 * i, 32) != 0) differs.store(1, std::memory_order_relaxed);
     }
+    if (same) *same = differs.load() ? 0 : 1;
     if (first_bad.load() != (size_t)n) return -1 - (long long)first_bad.load();
     return (long long)n;
+}
+long long zkp_wire_decode_list(PyObject* seq, uint8_t* out, size_t capacity) {
+    return decode_list_impl(seq, out, capacity, nullptr, nullptr);
+}
+long long zkp_wire_decode_list_cmp(PyObject* seq, uint8_t* out, size_t capacity, const uint8_t* ref, int* same) {
+    if (!ref || !same) return -(1ll << 40);
+    return decode_list_impl(seq, out, capacity, ref, same);
 }
 
 // in[32 * n] -> new list of n str (43 chars each, unpadded); nullptr with a Python error set on failure

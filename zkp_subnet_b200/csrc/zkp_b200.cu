@@ -49,6 +49,7 @@ const G1Affine* row_ptr(zkp_ctx* ctx, uint32_t row) { return ctx->srs.as<G1Affin
 
 // upload big-endian scalars and validate them (< r) on the device
 int upload_scalars(zkp_ctx* ctx, const uint8_t* be, size_t n, DevBuf& dst) {
+    ctx->resident_n = 0;
     ZKP_CUDA(dst.ensure(n * 32));
     ZKP_CUDA(cudaMemcpyAsync(dst.p, be, n * 32, cudaMemcpyHostToDevice, ctx->stream));
     return ZKP_OK;
@@ -337,7 +338,9 @@ int zkp_msm_g1(zkp_ctx* ctx, uint32_t row, const uint8_t* scalars_be, size_t n, 
     DeviceGuard g(ctx->device);
     rc = upload_scalars(ctx, scalars_be, n, ctx->scalars);
     if (rc) return rc;
-    return msm_device(ctx, row, ctx->scalars.as<uint32_t>(), SCALAR_BE, n, out48);
+    rc = msm_device(ctx, row, ctx->scalars.as<uint32_t>(), SCALAR_BE, n, out48);
+    if (rc == ZKP_OK) ctx->resident_n = n;  // canonical (the MSM validated every scalar) and still on the device
+    return rc;
 }
 
 int zkp_worker_commit(zkp_ctx* ctx, uint32_t i, const uint8_t* poly_be, size_t n, uint8_t commitment48[48]) {

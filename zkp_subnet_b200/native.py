@@ -60,6 +60,7 @@ _SIGNATURES = {
     "zkp_srs_shape": [_ctxp, ctypes.POINTER(ctypes.c_uint32), ctypes.POINTER(ctypes.c_uint32)],
     "zkp_worker_commit": [_ctxp, ctypes.c_uint32, _u8p, ctypes.c_size_t, _u8p],
     "zkp_worker_open": [_ctxp, ctypes.c_uint32, _u8p, ctypes.c_size_t, _u8p, _u8p, _u8p],
+    "zkp_worker_open_resident": [_ctxp, ctypes.c_uint32, ctypes.c_size_t, _u8p, _u8p, _u8p],
     "zkp_worker_commit_open": [_ctxp, ctypes.c_uint32, _u8p, ctypes.c_size_t, _u8p, _u8p, _u8p, _u8p],
     "zkp_worker_verify": [_ctxp, ctypes.c_uint32, _u8p, _u8p, _u8p, _u8p, ctypes.POINTER(ctypes.c_int)],
     "zkp_worker_verify_batch": [_ctxp, ctypes.c_size_t, ctypes.POINTER(ctypes.c_uint32), _u8p, _u8p, _u8p, _u8p, ctypes.POINTER(ctypes.c_int)],
@@ -235,6 +236,14 @@ class Context:
         check(lib().zkp_worker_open(self._h, i, _arg(poly_be), len(poly_be) // 32, x_be, y, proof))
         return y.raw, proof.raw
 
+    def worker_open_resident(self, i: int, n: int, x_be: bytes) -> Tuple[bytes, bytes]:
+        """Opening of the polynomial the previous worker_commit / worker_open / worker_commit_open call left on the
+        device (no upload); ZkpError(ZKP_ERR_STATE) when none of n elements is resident."""
+        y = ctypes.create_string_buffer(32)
+        proof = ctypes.create_string_buffer(48)
+        check(lib().zkp_worker_open_resident(self._h, i, n, x_be, y, proof))
+        return y.raw, proof.raw
+
     def worker_commit_open(self, i: int, poly_be: bytes, x_be: bytes) -> Tuple[bytes, bytes, bytes]:
         com = ctypes.create_string_buffer(48)
         y = ctypes.create_string_buffer(32)
@@ -400,18 +409,31 @@ def wire() -> ctypes.PyDLL:
         h = ctypes.PyDLL(WIRE_PATH)
         h.zkp_wire_decode_list.argtypes = [ctypes.py_object, ctypes.c_void_p, ctypes.c_size_t]
         h.zkp_wire_decode_list.restype = ctypes.c_longlong
+        h.zkp_wire_decode_list_cmp.argtypes = [ctypes.py_object, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p,
+                                               ctypes.POINTER(ctypes.c_int)]
+        h.zkp_wire_decode_list_cmp.restype = ctypes.c_longlong
         h.zkp_wire_encode_list.argtypes = [ctypes.c_char_p, ctypes.c_size_t]
         h.zkp_wire_encode_list.restype = ctypes.py_object
         _wire = h
     return _wire
 
 
-def wire_decode_list(strs, out: Optional[PinnedBuffer] = None):
-    """List[str] (43/44-char base64 field elements) -> n x 32 bytes, into `out` (returned) when given."""
+def wire_decode_list(strs, out: Optional[PinnedBuffer] = None, same_as: Optional[PinnedBuffer] = None):
+    """List[str] (43/44-char base64 field elements) -> n x 32 bytes, into `out` (returned) when given.
+    With `same_as` (a buffer holding n x 32 bytes) the result is the pair (out, decoded bytes == same_as)."""
     if not isinstance(strs, (list, tuple)):
         strs = list(strs)
     n = len(strs)
-    if out is not None:
+    if same_as is not None:
+        if out is None or out.capacity < 32 * n or same_as.capacity < 32 * n:
+            raise ValueError("PinnedBuffer too small")
+        same = ctypes.c_int(0)
+        rc = wire().zkp_wire_decode_list_cmp(strs, ctypes.addressof(out.buf), out.capacity, ctypes.addressof(same_as.buf),
+                                             ctypes.byref(same))
+        if rc == n:
+            out.used = 32 * n
+            return out, bool(same.value)
+    elif out is not None:
         if out.capacity < 32 * n:
             raise ValueError("PinnedBuffer too small")
         rc = wire().zkp_wire_decode_list(strs, ctypes.addressof(out.buf), out.capacity)
