@@ -131,3 +131,36 @@ def test_pairing_check_kzg_equation(golden):
 def test_response_contract():
     with Response(200, {"commitment": "x"}) as r:
         assert r.status_code == 200 and r.json().get("commitment") == "x"
+
+
+def test_wire_decoder_every_byte_at_every_position():
+    """The list decoder (AVX2 on x86-64, table-driven otherwise) against Python's base64 for every byte value at
+    every one of the 43 positions: accepted exactly when the byte is in the standard alphabet (and, in the last
+    position, carries no trailing bits), and then decoded to the same 32 bytes."""
+    import random
+    alphabet = b"ABCDEFGHIJKLMNOPQRSTUVWXYZabcdefghijklmnopqrstuvwxyz0123456789+/"
+    rng = random.Random(43)
+    base = base64.b64encode(bytes(rng.randrange(256) for _ in range(32)))[:43]
+    checked = 0
+    for pos in range(43):
+        for c in range(256):
+            s = base[:pos] + bytes([c]) + base[pos + 1:]
+            ok = c in alphabet and (pos != 42 or alphabet.index(c) % 4 == 0)
+            for item in (s, s + b"="):
+                if ok:
+                    assert native.wire_decode_list([item]) == base64.b64decode(s + b"="), (pos, c)
+                else:
+                    with pytest.raises(ValueError):
+                        native.wire_decode_list([item])
+            if c < 128:  # the same through a str
+                if ok:
+                    assert native.wire_decode_list([s.decode()]) == base64.b64decode(s + b"=")
+                else:
+                    with pytest.raises(ValueError):
+                        native.wire_decode_list([s.decode()])
+            checked += 1
+    assert checked == 43 * 256
+    # random valid elements in bulk
+    raw = bytes(rng.randrange(256) for _ in range(32 * 5000))
+    strs = [base64.b64encode(raw[32 * i:32 * i + 32]).decode().rstrip("=") for i in range(5000)]
+    assert native.wire_decode_list(strs) == raw

@@ -55,6 +55,64 @@ inline bool b64_decode32(const char* s, uint8_t out[32]) {
     return !(bad & B64Tables::BAD) && !(v & 0xc0u);
 }
 
+#if defined(__x86_64__) && defined(__GNUC__)
+#define ZKP_CODEC_AVX2 1
+}  // namespace codec
+}  // namespace zkp
+#include <immintrin.h>
+namespace zkp {
+namespace codec {
+inline bool have_avx2() {
+    static const bool v = __builtin_cpu_supports("avx2");
+    return v;
+}
+// 32 base64 characters -> 24 bytes in the low 192 bits; *bad accumulates a non-zero byte for every invalid character.
+// Validity and value come from the two nibbles of a character c: hi = c >> 4 selects one bit, lo = c & 15 selects the
+// set of hi values for which (hi, lo) is in the alphabet ('A'-'O' 4x, 'P'-'Z' 5x, 'a'-'o' 6x, 'p'-'z' 7x, '0'-'9' 3x,
+// '+' 2B, '/' 2F); the 6-bit value is c plus an offset that depends on hi only, except for '/'.
+__attribute__((target("avx2"))) inline __m256i b64_decode_32chars(__m256i in, __m256i* bad) {
+    const __m256i lo_sets = _mm256_setr_epi8(
+        (char)0xa8, (char)0xf8, (char)0xf8, (char)0xf8, (char)0xf8, (char)0xf8, (char)0xf8, (char)0xf8,
+        (char)0xf8, (char)0xf8, (char)0xf0, (char)0x54, (char)0x50, (char)0x50, (char)0x50, (char)0x54,
+        (char)0xa8, (char)0xf8, (char)0xf8, (char)0xf8, (char)0xf8, (char)0xf8, (char)0xf8, (char)0xf8,
+        (char)0xf8, (char)0xf8, (char)0xf0, (char)0x54, (char)0x50, (char)0x50, (char)0x50, (char)0x54);
+    const __m256i hi_bit = _mm256_setr_epi8(1, 2, 4, 8, 16, 32, 64, (char)128, 0, 0, 0, 0, 0, 0, 0, 0,
+                                            1, 2, 4, 8, 16, 32, 64, (char)128, 0, 0, 0, 0, 0, 0, 0, 0);
+    const __m256i offset = _mm256_setr_epi8(0, 0, 19, 4, -65, -65, -71, -71, 0, 0, 0, 0, 0, 0, 0, 0,
+                                            0, 0, 19, 4, -65, -65, -71, -71, 0, 0, 0, 0, 0, 0, 0, 0);
+    const __m256i nib = _mm256_set1_epi8(0x0f);
+    const __m256i hi = _mm256_and_si256(_mm256_srli_epi32(in, 4), nib);
+    const __m256i lo = _mm256_and_si256(in, nib);
+    const __m256i ok = _mm256_and_si256(_mm256_shuffle_epi8(lo_sets, lo), _mm256_shuffle_epi8(hi_bit, hi));
+    *bad = _mm256_or_si256(*bad, _mm256_cmpeq_epi8(ok, _mm256_setzero_si256()));
+    const __m256i is_slash = _mm256_cmpeq_epi8(in, _mm256_set1_epi8(0x2f));
+    const __m256i off = _mm256_blendv_epi8(_mm256_shuffle_epi8(offset, hi), _mm256_set1_epi8(16), is_slash);
+    const __m256i v = _mm256_add_epi8(in, off);
+    // four 6-bit values -> one 24-bit group, then the three bytes of every group in stream order
+    const __m256i t = _mm256_maddubs_epi16(v, _mm256_set1_epi32(0x01400140));
+    const __m256i g = _mm256_madd_epi16(t, _mm256_set1_epi32(0x00011000));
+    const __m256i bytes = _mm256_shuffle_epi8(g, _mm256_setr_epi8(2, 1, 0, 6, 5, 4, 10, 9, 8, 14, 13, 12, -1, -1, -1, -1,
+                                                                 2, 1, 0, 6, 5, 4, 10, 9, 8, 14, 13, 12, -1, -1, -1, -1));
+    return _mm256_permutevar8x32_epi32(bytes, _mm256_setr_epi32(0, 1, 2, 4, 5, 6, 3, 7));
+}
+// b64_decode32 with two overlapping 32-character blocks: characters 0..31 give bytes 0..23, characters 12..43 (the
+// 44th replaced by 'A') give bytes 9..32, and byte 32 holds exactly the two trailing bits that have to be zero.
+// READS s[43]: the caller guarantees 44 readable bytes (a Python str / bytes object always has its terminator).
+__attribute__((target("avx2"))) inline bool b64_decode32_avx2(const char* s, uint8_t out[32]) {
+    __m256i bad = _mm256_setzero_si256();
+    const __m256i a = _mm256_loadu_si256(reinterpret_cast<const __m256i*>(s));
+    __m256i b = _mm256_loadu_si256(reinterpret_cast<const __m256i*>(s + 12));
+    b = _mm256_blendv_epi8(b, _mm256_set1_epi8('A'), _mm256_setr_epi8(0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0,
+                                                                       0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, -1));
+    alignas(32) uint8_t t0[32], t1[32];
+    _mm256_store_si256(reinterpret_cast<__m256i*>(t0), b64_decode_32chars(a, &bad));
+    _mm256_store_si256(reinterpret_cast<__m256i*>(t1), b64_decode_32chars(b, &bad));
+    memcpy(out, t0, 16);
+    memcpy(out + 16, t1 + 7, 16);
+    return _mm256_testz_si256(bad, bad) && t1[23] == 0;
+}
+#endif
+
 inline void b64_encode32(const uint8_t in[32], char out[43]) {
     static const char* a = "ABCDEFGHIJKLMNOPQRSTUVWXYZabcdefghijklmnopqrstuvwxyz0123456789+/";
     int o = 0;

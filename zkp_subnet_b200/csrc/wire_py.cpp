@@ -28,6 +28,14 @@ static unsigned cmp_threads() {
 }
 // ref != nullptr: also compares every decoded element with ref[32 i ..] and reports *same (the fourier.Client
 // shim uses it to recognise the polynomial it was handed by the previous call, see client.py worker_open)
+// one element whose buffer has at least 44 readable bytes (str and bytes objects keep a terminator)
+static inline bool decode_one(const char* p, uint8_t* out, bool avx2) {
+#ifdef ZKP_CODEC_AVX2
+    if (avx2) return codec::b64_decode32_avx2(p, out);
+#endif
+    (void)avx2;
+    return codec::b64_decode32(p, out);
+}
 static long long decode_list_impl(PyObject* seq, uint8_t* out, size_t capacity, const uint8_t* ref, int* same) {
     const long long BAD_ARG = -(1ll << 40);
     if (!seq || !out || !(PyList_Check(seq) || PyTuple_Check(seq))) return BAD_ARG;
@@ -43,6 +51,11 @@ static long long decode_list_impl(PyObject* seq, uint8_t* out, size_t capacity, 
     // walk moved from the calling thread to the workers.)
     std::atomic<size_t> first_bad((size_t)n), first_slow((size_t)n);
     std::atomic<int> differs(0);
+#ifdef ZKP_CODEC_AVX2
+    const bool avx2 = codec::have_avx2();
+#else
+    const bool avx2 = false;
+#endif
     auto lower = [](std::atomic<size_t>& a, size_t i) {
         size_t cur = a.load();
         while (i < cur && !a.compare_exchange_weak(cur, i)) {}
@@ -62,7 +75,7 @@ static long long decode_list_impl(PyObject* seq, uint8_t* out, size_t capacity, 
                 lower(first_slow, i);
                 continue;
             }
-            if (!(len == 43 || (len == 44 && p[43] == '=')) || !codec::b64_decode32(p, out + 32 * i)) {
+            if (!(len == 43 || (len == 44 && p[43] == '=')) || !decode_one(p, out + 32 * i, avx2)) {
                 lower(first_bad, i);
                 return;
             }
@@ -86,7 +99,7 @@ static long long decode_list_impl(PyObject* seq, uint8_t* out, size_t capacity, 
             lower(first_bad, i);
             break;
         }
-        if (!(len == 43 || (len == 44 && p[43] == '=')) || !codec::b64_decode32(p, out + 32 * i)) {
+        if (!(len == 43 || (len == 44 && p[43] == '=')) || !decode_one(p, out + 32 * i, avx2)) {
             lower(first_bad, i);
             break;
         }
