@@ -56,6 +56,33 @@ def test_msm_special_points(gpu_ctx):
         assert gpu_ctx.msm_g1(0, sc) == ref.msm(raw, sc, 1)
 
 
+@pytest.mark.parametrize("tables", [True, False])
+def test_msm_exceptional_additions_on_a_loose_accumulator(gpu_ctx, tables):
+    """The level-0 accumulation adds with lazy reductions (G1Xyzz::madd_lazy): its test for equal / opposite
+    operands has to work on unreduced coordinates.  Rows built so that, with every scalar equal (one bucket per
+    window, entries in index order), the running sum meets a point EQUAL to itself after a few additions (doubling
+    branch), later its NEGATIVE (the sum becomes infinity), and then carries on from infinity."""
+    g = o.G1_GEN
+    ks = [3, 5, 11]                      # acc = 19 G after three additions ...
+    ks += [19]                           # ... + 19 G: doubling while the accumulator is loose -> 38 G
+    ks += [7, 2]                         # 47 G
+    ks += [-47, 13]                      # cancellation -> infinity, restart from infinity (end of the first 8-entry slice)
+    ks += [13, 13, 26, -52, 9]           # next slice: 13 G + 13 G (doubling from an affine start), + 26 G (doubling again), - 52 G, + 9 G
+    ks += [k + 100 for k in range(64 - len(ks))]
+    pts = [o.g1_mul(g, k) if k > 0 else o.g1_neg(o.g1_mul(g, -k)) for k in ks]
+    raw = b"".join(p[0].to_bytes(48, "big") + p[1].to_bytes(48, "big") for p in pts)
+    gpu_ctx.set_msm_mode(tables)
+    try:
+        gpu_ctx.srs_set_shape(6, 0)
+        gpu_ctx.srs_import_row(0, raw)
+        for sc in (ref.join32([1] * 64), ref.join32([0x1234567] * 64), ref.join32([R - 2] * 64),
+                   ref.join32([1] * 12 + [0] * 52), ref.random_scalars(11, 64)):
+            assert gpu_ctx.msm_g1(0, sc) == ref.msm(raw, sc, 1)
+    finally:
+        gpu_ctx.set_msm_mode(True)
+        gpu_ctx.set_msm_window(0)
+
+
 @pytest.mark.parametrize("rounds", [1, 2, 3, 6])
 def test_batched_affine_rounds_vs_oracle(gpu_ctx, rounds):
     """Batched-affine pairwise rounds in front of the XYZZ accumulation (msm_affine.cuh): forced on at small
