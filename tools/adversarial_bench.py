@@ -4,10 +4,12 @@ polynomial that alternates between two values."""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from zkp_subnet_b200 import native
-tag = os.path.basename(os.environ.get("ZKP_B200_LIB", "default"))
+tag = os.path.basename(os.environ.get("ZKP_B200_LIB", "default")) + ":" + os.environ.get("ZKP_SORT", "bucket")
 for lg in (16, 20):
     n = 1 << lg
     ctx = native.Context(0)
+    if os.environ.get('ZKP_SORT') == 'cub':
+        ctx.set_msm_sort(False)
     ctx.srs_generate(1927409816240961209460912649124, 0x1234567890ABCDEF1234567890ABCDEF, lg, 0)
     rnd = ctx.random_poly(0xB200 + 3, n)
     a, b = rnd[:32], rnd[32:64]

@@ -2,10 +2,12 @@
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from zkp_subnet_b200 import native
-tag = os.path.basename(os.environ.get("ZKP_B200_LIB", "default"))
+tag = os.path.basename(os.environ.get("ZKP_B200_LIB", "default")) + ":" + os.environ.get("ZKP_SORT", "bucket")
 ref = {}
 for lg in (16, 20):
     ctx = native.Context(0)
+    if os.environ.get('ZKP_SORT') == 'cub':
+        ctx.set_msm_sort(False)
     ctx.srs_generate(1927409816240961209460912649124, 0x1234567890ABCDEF1234567890ABCDEF, lg, 0)
     poly = ctx.random_poly(0xB200 + 3, 1 << lg)
     x = ctx.random_point(0xA1FA)

@@ -50,6 +50,7 @@ struct DevBuf {
 
 struct MsmWorkspace {
     DevBuf keys_a, keys_b, vals_a, vals_b, cub_temp, buckets, next_a, next_b, pool, sums_a, sums_b, sums_out, bad;
+    DevBuf sort_counters, sort_chunks;  // bucket sort: one cursor per key (+ padding to whole chunks), one start per chunk
     std::vector<DevBuf> slot_keys, slot_pts;
     // batched-affine rounds: per-round bucket starts, scan input, ping-pong point lists, keys of the last list,
     // prefix-product scratch
@@ -60,7 +61,8 @@ struct MsmWorkspace {
     void release() {
         if (h_bad) cudaFreeHost(h_bad);
         h_bad = nullptr;
-        for (DevBuf* b : {&keys_a, &keys_b, &vals_a, &vals_b, &cub_temp, &buckets, &next_a, &next_b, &pool, &sums_a, &sums_b, &sums_out, &bad})
+        for (DevBuf* b : {&keys_a, &keys_b, &vals_a, &vals_b, &cub_temp, &buckets, &next_a, &next_b, &pool, &sums_a, &sums_b, &sums_out, &bad,
+                          &sort_counters, &sort_chunks})
             b->release();
         for (auto& b : slot_keys) b.release();
         for (auto& b : slot_pts) b.release();
@@ -102,6 +104,7 @@ struct zkp_ctx {
     cudaEvent_t ev_ready = nullptr;           // polynomial uploaded + converted (lane 0 -> lane 1)
     cudaEvent_t ev_acc2_0 = nullptr, ev_acc2_1 = nullptr;
     uint32_t c_override = 0;
+    bool bucket_sort = true;                  // hand-written counting sort of the digits (false: cub::DeviceRadixSort)
     int affine_rounds_override = -1;          // <= 0: off (default, see plan_for); 1..6: rounds of batched-affine additions
     // fixed-base tables: per SRS row, [2^(c w)] P_i for w < W (slice w at w * 2^log_n); built lazily
     struct Precomp { zkp::DevBuf table; uint32_t c = 0, W = 0; };

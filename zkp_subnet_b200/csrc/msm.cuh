@@ -184,9 +184,16 @@ inline MsmPlan msm_make_plan(uint32_t n, int sm_count, uint32_t c, bool precomp,
 enum { SCALAR_LE = 0, SCALAR_BE = 1, SCALAR_MONT = 2 };
 // precomp: every digit position shares the bucket set (key = |digit| - 1) and val indexes the table
 // [2^(c w)] P_i at w * win_stride + i.
+// MODE 0 (DIGITS_WRITE): keys/vals written in window-major order (entry w n + i) for the library radix sort.
+// MODE 1 (DIGITS_COUNT) and 2 (DIGITS_SCATTER): the two passes of the hand-written bucket sort (section 2 below) --
+// the digits are recomputed in the second pass instead of being stored unsorted, written once, and read back.
+enum { DIGITS_WRITE = 0, DIGITS_COUNT = 1, DIGITS_SCATTER = 2 };
+constexpr uint32_t SORT_CHUNK_LOG = 10, SORT_CHUNK = 1u << SORT_CHUNK_LOG;  // keys per chunk of the two-level scan
+template <int MODE>
 __global__ void k_decompose(const uint32_t* __restrict__ scalars, uint32_t n, uint32_t c, uint32_t W,
                             uint32_t B, uint32_t discard, int fmt, int precomp, uint32_t win_stride, uint32_t neg_offset,
-                            uint32_t* __restrict__ keys, uint32_t* __restrict__ vals, uint32_t* __restrict__ bad) {
+                            uint32_t* __restrict__ keys, uint32_t* __restrict__ vals, uint32_t* __restrict__ bad,
+                            uint32_t* __restrict__ counters, const uint32_t* __restrict__ chunk_base) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     uint32_t s[9];
@@ -207,7 +214,7 @@ __global__ void k_decompose(const uint32_t* __restrict__ scalars, uint32_t n, ui
         m = m.from_mont();
 #pragma unroll
         for (int k = 0; k < 8; k++) s[k] = m.v[k];
-    } else {
+    } else if (MODE != DIGITS_SCATTER) {
         bool lt = false, decided = false;
 #pragma unroll
         for (int k = 7; k >= 0; k--) {
@@ -219,6 +226,7 @@ __global__ void k_decompose(const uint32_t* __restrict__ scalars, uint32_t n, ui
     s[8] = 0;
     uint32_t carry = 0;
     const uint32_t half = 1u << (c - 1), mask = (1u << c) - 1;
+    const uint32_t lane = threadIdx.x & 31, lanes_below = (1u << lane) - 1;
     for (uint32_t w = 0; w < W; w++) {
         uint32_t bit = w * c, limb = bit >> 5, off = bit & 31;
         uint32_t raw = 0;
@@ -230,10 +238,102 @@ __global__ void k_decompose(const uint32_t* __restrict__ scalars, uint32_t n, ui
         uint32_t neg = raw > half;
         uint32_t mag = neg ? (1u << c) - raw : raw;
         carry = neg;
-        size_t o = (size_t)w * n + i;
-        keys[o] = mag ? (precomp ? 0u : w * B) + mag - 1 : discard;
+        const uint32_t key = mag ? (precomp ? 0u : w * B) + mag - 1 : discard;
         // with a negated table half the sign selects the half and no kernel ever negates a y-coordinate
-        vals[o] = neg_offset ? w * win_stride + i + (neg ? neg_offset : 0u) : ((precomp ? w * win_stride + i : i) | (neg << 31));
+        const uint32_t val = neg_offset ? w * win_stride + i + (neg ? neg_offset : 0u) : ((precomp ? w * win_stride + i : i) | (neg << 31));
+        if (MODE == DIGITS_WRITE) {
+            size_t o = (size_t)w * n + i;
+            keys[o] = key;
+            vals[o] = val;
+        } else {
+            // lanes of the warp that hold the same key act as one: a constant polynomial puts all 32 lanes (and every
+            // warp of the grid) on ONE counter per window, and must not turn into n serialised atomics
+            const uint32_t peers = __match_any_sync(__activemask(), key);
+            const uint32_t leader = __ffs(peers) - 1, rank = __popc(peers & lanes_below);
+            if (MODE == DIGITS_COUNT) {
+                if (lane == leader) atomicAdd(counters + key, (uint32_t)__popc(peers));
+            } else {
+                uint32_t first = 0;
+                if (lane == leader) first = atomicAdd(counters + key, (uint32_t)__popc(peers));
+                first = __shfl_sync(peers, first, leader);
+                // one 8-byte store per entry: the scatter is bound by the number of L2 transactions (an atomic and the
+                // stores of an entry go to unrelated sectors), not by bytes
+                const size_t o = (size_t)chunk_base[key >> SORT_CHUNK_LOG] + first + rank;
+                reinterpret_cast<uint2*>(keys)[o] = make_uint2(key, val);
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// 2. bucket sort (hand-written; the library radix sort stays selectable for A/B runs)
+// ------------------------------------------------------------------------------------------------
+// The accumulation needs the entries GROUPED by key, in key order; the order inside a group is irrelevant (a
+// bucket is a sum).  That is a counting sort: k_decompose<COUNT> histograms the keys, two small kernels turn the
+// histogram into start positions (an exclusive scan kept as "position inside a chunk of 1024 keys" + "start of the
+// chunk", so that no third pass has to add the two), k_decompose<SCATTER> recomputes the digits and places every
+// entry with one atomicAdd on its key's cursor.  Traffic: the 32-byte scalars twice and the sorted (key, value)
+// arrays once, against four reads and three writes of the 8-byte pairs for a 3-pass LSD radix sort.
+// counters[chunk * 1024 ..] -> exclusive prefix inside the chunk (in place), chunk_sum[chunk] = total of the chunk
+__global__ void __launch_bounds__(SORT_CHUNK) k_sort_scan_chunks(uint32_t* __restrict__ counters, uint32_t m, uint32_t* __restrict__ chunk_sum) {
+    __shared__ uint32_t warp_tot[32];
+    const uint32_t idx = blockIdx.x * SORT_CHUNK + threadIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t v = idx < m ? counters[idx] : 0u;
+    uint32_t incl = v;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        uint32_t t = __shfl_up_sync(0xffffffffu, incl, d);
+        if ((int)lane >= d) incl += t;
+    }
+    if (lane == 31) warp_tot[warp] = incl;
+    __syncthreads();
+    if (warp == 0) {
+        uint32_t t = warp_tot[lane], ti = t;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            uint32_t u = __shfl_up_sync(0xffffffffu, ti, d);
+            if ((int)lane >= d) ti += u;
+        }
+        warp_tot[lane] = ti - t;  // exclusive
+        if (lane == 31) chunk_sum[blockIdx.x] = ti;
+    }
+    __syncthreads();
+    if (idx < m) counters[idx] = warp_tot[warp] + incl - v;
+}
+// chunk_sum[0..chunks) -> exclusive prefix in place (one block; chunks <= a few thousand)
+__global__ void __launch_bounds__(1024) k_sort_scan_sums(uint32_t* __restrict__ chunk_sum, uint32_t chunks) {
+    __shared__ uint32_t warp_tot[32];
+    __shared__ uint32_t running;
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (threadIdx.x == 0) running = 0;
+    __syncthreads();
+    for (uint32_t base = 0; base < chunks; base += 1024) {
+        const uint32_t idx = base + threadIdx.x;
+        const uint32_t v = idx < chunks ? chunk_sum[idx] : 0u;
+        uint32_t incl = v;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            uint32_t t = __shfl_up_sync(0xffffffffu, incl, d);
+            if ((int)lane >= d) incl += t;
+        }
+        if (lane == 31) warp_tot[warp] = incl;
+        __syncthreads();
+        uint32_t block_total = 0;
+        if (warp == 0) {
+            uint32_t t = warp_tot[lane], ti = t;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                uint32_t u = __shfl_up_sync(0xffffffffu, ti, d);
+                if ((int)lane >= d) ti += u;
+            }
+            warp_tot[lane] = ti - t;
+            block_total = __shfl_sync(0xffffffffu, ti, 31);
+        }
+        __syncthreads();
+        if (idx < chunks) chunk_sum[idx] = running + warp_tot[warp] + incl - v;
+        __syncthreads();
+        if (threadIdx.x == 0) running += block_total;
+        __syncthreads();
     }
 }
 
@@ -288,7 +388,9 @@ __global__ void __launch_bounds__(LEVEL0 ? ZKP_ACC_THREADS : 128, LEVEL0 ? ZKP_A
 k_accumulate(const uint32_t* __restrict__ keys, const uint32_t* __restrict__ vals,
              const G1Affine* __restrict__ points, const G1Xyzz* __restrict__ slots_in, size_t items,
              uint32_t L, uint32_t discard, G1Xyzz* __restrict__ buckets, uint32_t* __restrict__ slot_keys,
-             G1Xyzz* __restrict__ slot_pts, int last_level) {
+             G1Xyzz* __restrict__ slot_pts, int last_level, uint32_t S = 1) {
+    // S: stride of the level-0 entry arrays in words -- 1 for separate key / value arrays (library sort, batched-affine
+    // output), 2 for the interleaved (key, value) pairs written by the bucket sort (vals == keys + 1)
     // Level 0: one thread per slice.  Small slot levels (COOP): FOUR lanes per slice -- they run the same control flow
     // on the same slice and share every point addition (coop_add4), because these levels are pure latency: a few
     // dependent additions per slice and far fewer slices than the machine has lanes.  A slot level with more slices
@@ -314,7 +416,7 @@ k_accumulate(const uint32_t* __restrict__ keys, const uint32_t* __restrict__ val
     size_t end = (t + 1) * L + shift < items ? (t + 1) * L + shift : items;
 
     auto key_at = [&](size_t i) -> uint32_t {
-        uint32_t k = keys[i];
+        uint32_t k = keys[LEVEL0 ? i * S : i];
         if (!LEVEL0 && k != KEY_NONE) k &= ~KEY_EMPTY_FLAG;
         return k;
     };
@@ -343,7 +445,7 @@ k_accumulate(const uint32_t* __restrict__ keys, const uint32_t* __restrict__ val
     };
 
     for (size_t i = start; i < end; i++) {
-        uint32_t raw = keys[i];
+        uint32_t raw = keys[LEVEL0 ? i * S : i];
         uint32_t k = raw;
         if (LEVEL0) {
             if (k >= discard) break;  // zero digits sort last: nothing further in this slice
@@ -364,11 +466,11 @@ k_accumulate(const uint32_t* __restrict__ keys, const uint32_t* __restrict__ val
         last_key = k;
         if (LEVEL0) {
             // vals == nullptr: the items ARE the points (output of the batched-affine rounds), in list order
-            uint32_t v = vals ? vals[i] : (uint32_t)i;
+            uint32_t v = vals ? vals[i * S] : (uint32_t)i;
             if (vals && i + 1 < end) {
                 // the gather is a 96-byte random read of a table far larger than L2: pull the NEXT point
                 // towards L2 while this one is being added (no registers held, unlike a software pipeline)
-                const char* nx = reinterpret_cast<const char*>(points + (vals[i + 1] & 0x7fffffffu));
+                const char* nx = reinterpret_cast<const char*>(points + (vals[(i + 1) * S] & 0x7fffffffu));
                 asm volatile("prefetch.global.L2 [%0];" ::"l"(nx));
                 asm volatile("prefetch.global.L2 [%0];" ::"l"(nx + 64));
             }

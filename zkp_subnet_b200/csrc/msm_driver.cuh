@@ -16,6 +16,9 @@ inline uint64_t msm_fq_muls(const MsmPlan& p) {
 // front halves (digits + sort) of BOTH lanes before either bucket accumulation: an accumulation grid keeps every
 // SM busy for milliseconds and starves whatever small kernels another stream launches after it.
 // Front half: workspaces, signed digits, radix sort.
+// the bucket sort writes interleaved pairs, which the batched-affine rounds (separate key / value arrays) do not read
+inline bool msm_uses_bucket_sort(const zkp_ctx* ctx, const MsmPlan& plan) { return ctx->bucket_sort && plan.affine_rounds == 0; }
+
 inline int msm_enqueue_prep(zkp_ctx* ctx, int lane, const MsmPlan& plan, const uint32_t* d_scalars, int fmt) {
     MsmWorkspace& ws = lane ? ctx->ws2 : ctx->ws;
     cudaStream_t st = lane ? ctx->stream2 : ctx->stream;
@@ -46,20 +49,43 @@ inline int msm_enqueue_prep(zkp_ctx* ctx, int lane, const MsmPlan& plan, const u
     trace_mark(ctx, lane, st, "msm_begin");
     ZKP_CUDA(ws.bad.ensure(8));
     ZKP_CUDA(cudaMemsetAsync(ws.bad.p, 0, 4, st));
-    k_decompose<<<(plan.n + 255) / 256, 256, 0, st>>>(d_scalars, plan.n, plan.c, plan.W, plan.B, plan.discard, fmt,
-                                                      plan.precomp ? 1 : 0, plan.win_stride, plan.neg_offset, ws.keys_a.as<uint32_t>(),
-                                                      ws.vals_a.as<uint32_t>(), ws.bad.as<uint32_t>());
-    ctx->launches++;
-    trace_mark(ctx, lane, st, "decompose");
-    // 2. sort by (window, bucket)
-    size_t temp_bytes = 0;
-    ZKP_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, temp_bytes, ws.keys_a.as<uint32_t>(), ws.keys_b.as<uint32_t>(),
-                                             ws.vals_a.as<uint32_t>(), ws.vals_b.as<uint32_t>(), (int64_t)N, 0,
-                                             (int)plan.key_bits, st));
-    ZKP_CUDA(ws.cub_temp.ensure(temp_bytes));
-    ZKP_CUDA(cub::DeviceRadixSort::SortPairs(ws.cub_temp.p, temp_bytes, ws.keys_a.as<uint32_t>(), ws.keys_b.as<uint32_t>(),
-                                             ws.vals_a.as<uint32_t>(), ws.vals_b.as<uint32_t>(), (int64_t)N, 0,
-                                             (int)plan.key_bits, st));
+    if (!msm_uses_bucket_sort(ctx, plan)) {
+        k_decompose<DIGITS_WRITE><<<(plan.n + 255) / 256, 256, 0, st>>>(d_scalars, plan.n, plan.c, plan.W, plan.B, plan.discard, fmt,
+                                                                        plan.precomp ? 1 : 0, plan.win_stride, plan.neg_offset,
+                                                                        ws.keys_a.as<uint32_t>(), ws.vals_a.as<uint32_t>(),
+                                                                        ws.bad.as<uint32_t>(), nullptr, nullptr);
+        ctx->launches++;
+        trace_mark(ctx, lane, st, "decompose");
+        // 2. sort by (window, bucket): library radix sort
+        size_t temp_bytes = 0;
+        ZKP_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, temp_bytes, ws.keys_a.as<uint32_t>(), ws.keys_b.as<uint32_t>(),
+                                                 ws.vals_a.as<uint32_t>(), ws.vals_b.as<uint32_t>(), (int64_t)N, 0,
+                                                 (int)plan.key_bits, st));
+        ZKP_CUDA(ws.cub_temp.ensure(temp_bytes));
+        ZKP_CUDA(cub::DeviceRadixSort::SortPairs(ws.cub_temp.p, temp_bytes, ws.keys_a.as<uint32_t>(), ws.keys_b.as<uint32_t>(),
+                                                 ws.vals_a.as<uint32_t>(), ws.vals_b.as<uint32_t>(), (int64_t)N, 0,
+                                                 (int)plan.key_bits, st));
+    } else {
+        // 1 + 2. hand-written bucket sort: count, scan, scatter (msm.cuh section 2)
+        const uint32_t m = plan.discard + 1, chunks = (m + SORT_CHUNK - 1) / SORT_CHUNK;
+        ZKP_CUDA(ws.sort_counters.ensure((size_t)chunks * SORT_CHUNK * 4));
+        ZKP_CUDA(ws.sort_chunks.ensure((size_t)chunks * 4));
+        ZKP_CUDA(ws.keys_b.ensure(N * 8));  // interleaved (key, value) pairs
+        ZKP_CUDA(cudaMemsetAsync(ws.sort_counters.p, 0, (size_t)chunks * SORT_CHUNK * 4, st));
+        k_decompose<DIGITS_COUNT><<<(plan.n + 255) / 256, 256, 0, st>>>(d_scalars, plan.n, plan.c, plan.W, plan.B, plan.discard, fmt,
+                                                                        plan.precomp ? 1 : 0, plan.win_stride, plan.neg_offset, nullptr,
+                                                                        nullptr, ws.bad.as<uint32_t>(), ws.sort_counters.as<uint32_t>(),
+                                                                        nullptr);
+        trace_mark(ctx, lane, st, "decompose");
+        k_sort_scan_chunks<<<chunks, SORT_CHUNK, 0, st>>>(ws.sort_counters.as<uint32_t>(), m, ws.sort_chunks.as<uint32_t>());
+        k_sort_scan_sums<<<1, 1024, 0, st>>>(ws.sort_chunks.as<uint32_t>(), chunks);
+        k_decompose<DIGITS_SCATTER><<<(plan.n + 255) / 256, 256, 0, st>>>(d_scalars, plan.n, plan.c, plan.W, plan.B, plan.discard, fmt,
+                                                                          plan.precomp ? 1 : 0, plan.win_stride, plan.neg_offset,
+                                                                          ws.keys_b.as<uint32_t>(), nullptr,
+                                                                          ws.bad.as<uint32_t>(), ws.sort_counters.as<uint32_t>(),
+                                                                          ws.sort_chunks.as<uint32_t>());
+        ctx->launches += 4;
+    }
     trace_mark(ctx, lane, st, "sort");
     return ZKP_OK;
 }
@@ -75,8 +101,9 @@ inline int msm_enqueue_main(zkp_ctx* ctx, int lane, const MsmPlan& plan, const G
     const size_t out_records = (size_t)plan.Wb * plan.out_per_window;
     const size_t temp_bytes = ws.cub_temp.cap;
     // 2b. batched-affine rounds: pairwise additions inside every bucket, 6 Fq products each instead of 10
+    const bool packed = msm_uses_bucket_sort(ctx, plan);
     const uint32_t* acc_keys = ws.keys_b.as<uint32_t>();
-    const uint32_t* acc_vals = ws.vals_b.as<uint32_t>();
+    const uint32_t* acc_vals = packed ? acc_keys + 1 : ws.vals_b.as<uint32_t>();
     const G1Affine* acc_points = d_points;
     if (plan.affine_rounds) {
         const uint32_t nbk = plan.discard, R = plan.affine_rounds;
@@ -137,7 +164,7 @@ inline int msm_enqueue_main(zkp_ctx* ctx, int lane, const MsmPlan& plan, const G
             k_accumulate<true><<<blocks, ZKP_ACC_THREADS, 0, st>>>(acc_keys, acc_vals, acc_points, nullptr,
                                                        lv.items, lv.L, plan.discard, ws.buckets.as<G1Xyzz>(),
                                                        last ? nullptr : ws.slot_keys[0].as<uint32_t>(),
-                                                       last ? nullptr : ws.slot_pts[0].as<G1Xyzz>(), last);
+                                                       last ? nullptr : ws.slot_pts[0].as<G1Xyzz>(), last, packed ? 2u : 1u);
             if (ctx->time_acc) cudaEventRecord(ev1, st);
             trace_mark(ctx, lane, st, "accumulate_l0");
         } else if (coop) {

@@ -237,6 +237,13 @@ int zkp_set_msm_window(zkp_ctx* ctx, uint32_t c) {
     return ZKP_OK;
 }
 
+int zkp_set_msm_sort(zkp_ctx* ctx, int bucket_sort) {
+    if (!ctx) return fail(ZKP_ERR_ARG, "null context");
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    ctx->bucket_sort = bucket_sort != 0;
+    return ZKP_OK;
+}
+
 int zkp_set_msm_mode(zkp_ctx* ctx, int fixed_base_tables) {
     if (!ctx) return fail(ZKP_ERR_ARG, "null context");
     std::lock_guard<std::mutex> lk(ctx->mu);

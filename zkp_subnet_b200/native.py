@@ -83,6 +83,7 @@ _SIGNATURES = {
     "zkp_bench_peaks": [_ctxp, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_double)],
     "zkp_set_msm_mode": [_ctxp, ctypes.c_int],
     "zkp_set_msm_window": [_ctxp, ctypes.c_uint32],
+    "zkp_set_msm_sort": [_ctxp, ctypes.c_int],
     "zkp_set_msm_affine_rounds": [_ctxp, ctypes.c_int],
     "zkp_msm_info": [_ctxp, ctypes.c_size_t, ctypes.POINTER(ctypes.c_uint32), ctypes.POINTER(ctypes.c_uint32),
                      ctypes.POINTER(ctypes.c_uint64)],
@@ -322,6 +323,9 @@ class Context:
     # ---- bench / tuning
     def set_msm_window(self, c: int) -> None:
         check(lib().zkp_set_msm_window(self._h, c))
+
+    def set_msm_sort(self, bucket_sort: bool) -> None:
+        check(lib().zkp_set_msm_sort(self._h, int(bucket_sort)))
 
     def set_msm_mode(self, fixed_base_tables: bool) -> None:
         check(lib().zkp_set_msm_mode(self._h, int(fixed_base_tables)))
