@@ -178,8 +178,9 @@ int zkp_bench_ntt(zkp_ctx* ctx, size_t n, int reps, int inverse, float* ms_per_n
 int zkp_bench_peaks(zkp_ctx* ctx, double* imad_wide_per_s, double* fq_mul_per_s);
 /* MSM tuning knobs: window bits (0 = automatic) */
 int zkp_set_msm_window(zkp_ctx* ctx, uint32_t c);
-/* 1 (default): group the (bucket, point) entries with the library's own counting sort (histogram, scan, scatter: the
- * order inside a bucket is irrelevant); 0: cub::DeviceRadixSort.  Results are identical either way. */
+/* How the (bucket, point) entries of an MSM are grouped: 1 = this library's counting sort (histogram, scan, scatter;
+ * the order inside a bucket is irrelevant), 0 = cub::DeviceRadixSort, 2 (default) = by size (the counting sort
+ * while its scattered output stays cache-resident).  Results are identical for every setting. */
 int zkp_set_msm_sort(zkp_ctx* ctx, int bucket_sort);
 /* 1 (default): keep per-row fixed-base tables [2^(c w)] P_i in HBM (W x the row) so that all digit positions
  * share one bucket set; 0: classic per-window buckets.  Results are identical either way. */

@@ -12,7 +12,7 @@ for f in sys.argv[1:]:
             unit = r["Metric Unit"]
             val = val / 1e3 if unit == "ns" else (val * 1e3 if unit == "ms" else val)
             rows.append((name[:48], val))
-    idx = [i for i, r in enumerate(rows) if "k_decompose" in r[0]]
+    idx = [i for i, r in enumerate(rows) if "k_decompose" in r[0] and (i == 0 or "k_sort_scan" not in rows[i - 1][0])]
     last = rows[idx[-1]:] if idx else rows
     tot = sum(v for _, v in last)
     print(f"{f}: {len(rows)} launches; last MSM = {len(last)} launches, {tot:.1f} us")

@@ -104,7 +104,7 @@ struct zkp_ctx {
     cudaEvent_t ev_ready = nullptr;           // polynomial uploaded + converted (lane 0 -> lane 1)
     cudaEvent_t ev_acc2_0 = nullptr, ev_acc2_1 = nullptr;
     uint32_t c_override = 0;
-    bool bucket_sort = true;                  // hand-written counting sort of the digits (false: cub::DeviceRadixSort)
+    int bucket_sort = 2;                      // digits grouped by the hand-written counting sort (1), cub::DeviceRadixSort (0), by size (2)
     int affine_rounds_override = -1;          // <= 0: off (default, see plan_for); 1..6: rounds of batched-affine additions
     // fixed-base tables: per SRS row, [2^(c w)] P_i for w < W (slice w at w * 2^log_n); built lazily
     struct Precomp { zkp::DevBuf table; uint32_t c = 0, W = 0; };

@@ -17,7 +17,18 @@ inline uint64_t msm_fq_muls(const MsmPlan& p) {
 // SM busy for milliseconds and starves whatever small kernels another stream launches after it.
 // Front half: workspaces, signed digits, radix sort.
 // the bucket sort writes interleaved pairs, which the batched-affine rounds (separate key / value arrays) do not read
-inline bool msm_uses_bucket_sort(const zkp_ctx* ctx, const MsmPlan& plan) { return ctx->bucket_sort && plan.affine_rounds == 0; }
+// Measured on B200 (tools/sort_ab.py, lone MSMs): the two sorts are within 0.3% of each other from 2^14 to 2^23 points
+// (<= 109 M entries); at 2^24 (201 M entries, 1.6 GB of scattered pairs, 2 M cursors) the library's radix sort is 4%
+// faster (79.3 vs 82.7 ms).  Inside a commit+open, where the sort of one lane runs beside the other lane's kernels, the
+// counting sort is the faster one (12.0 vs 12.5 ms at 2^20, 1.49 vs 1.71 ms at 2^16): it is bound by L2 transactions
+// and leaves the SMs' registers to whatever else is resident.
+#ifndef ZKP_BUCKET_SORT_MAX_ENTRIES
+#define ZKP_BUCKET_SORT_MAX_ENTRIES (1ull << 27)
+#endif
+inline bool msm_uses_bucket_sort(const zkp_ctx* ctx, const MsmPlan& plan) {
+    if (plan.affine_rounds != 0 || ctx->bucket_sort == 0) return false;
+    return ctx->bucket_sort == 1 || plan.N <= ZKP_BUCKET_SORT_MAX_ENTRIES;
+}
 
 inline int msm_enqueue_prep(zkp_ctx* ctx, int lane, const MsmPlan& plan, const uint32_t* d_scalars, int fmt) {
     MsmWorkspace& ws = lane ? ctx->ws2 : ctx->ws;

@@ -240,7 +240,7 @@ int zkp_set_msm_window(zkp_ctx* ctx, uint32_t c) {
 int zkp_set_msm_sort(zkp_ctx* ctx, int bucket_sort) {
     if (!ctx) return fail(ZKP_ERR_ARG, "null context");
     std::lock_guard<std::mutex> lk(ctx->mu);
-    ctx->bucket_sort = bucket_sort != 0;
+    ctx->bucket_sort = bucket_sort < 0 || bucket_sort > 2 ? 2 : bucket_sort;
     return ZKP_OK;
 }
 

@@ -324,8 +324,9 @@ class Context:
     def set_msm_window(self, c: int) -> None:
         check(lib().zkp_set_msm_window(self._h, c))
 
-    def set_msm_sort(self, bucket_sort: bool) -> None:
-        check(lib().zkp_set_msm_sort(self._h, int(bucket_sort)))
+    def set_msm_sort(self, mode) -> None:
+        """0 / False: cub::DeviceRadixSort, 1 / True: hand-written bucket sort, 2: by size (default)"""
+        check(lib().zkp_set_msm_sort(self._h, int(mode)))
 
     def set_msm_mode(self, fixed_base_tables: bool) -> None:
         check(lib().zkp_set_msm_mode(self._h, int(fixed_base_tables)))
