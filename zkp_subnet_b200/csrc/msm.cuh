@@ -57,7 +57,7 @@ struct MsmPlan {
     uint32_t W = 0;        // digit positions per scalar
     uint32_t Wb = 0;       // bucket windows: W (classic) or 1 (fixed-base tables, shared buckets)
     uint32_t B = 0;        // buckets per bucket window = 2^(c-1)
-    uint32_t key_bits = 0; // radix-sort bits
+    uint32_t key_bits = 0; // key bits (library radix-sort path)
     uint32_t discard = 0;  // key of zero digits
     bool precomp = false;  // vals index the table [2^(c w)] P_i at w * win_stride + i
     uint32_t win_stride = 0;

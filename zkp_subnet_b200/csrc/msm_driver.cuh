@@ -15,7 +15,7 @@ inline uint64_t msm_fq_muls(const MsmPlan& p) {
 // The device pipeline of one MSM on a lane's stream, in two halves so that a commit+open can enqueue the cheap
 // front halves (digits + sort) of BOTH lanes before either bucket accumulation: an accumulation grid keeps every
 // SM busy for milliseconds and starves whatever small kernels another stream launches after it.
-// Front half: workspaces, signed digits, radix sort.
+// Front half: workspaces, signed digits grouped by bucket (bucket sort, or the library radix sort -- see below).
 // the bucket sort writes interleaved pairs, which the batched-affine rounds (separate key / value arrays) do not read
 // Measured on B200 (tools/sort_ab.py, lone MSMs): the two sorts are within 0.3% of each other from 2^14 to 2^23 points
 // (<= 109 M entries); at 2^24 (201 M entries, 1.6 GB of scattered pairs, 2 M cursors) the library's radix sort is 4%
@@ -34,10 +34,14 @@ inline int msm_enqueue_prep(zkp_ctx* ctx, int lane, const MsmPlan& plan, const u
     MsmWorkspace& ws = lane ? ctx->ws2 : ctx->ws;
     cudaStream_t st = lane ? ctx->stream2 : ctx->stream;
     const size_t N = plan.N;
-    ZKP_CUDA(ws.keys_a.ensure(N * 4));
-    ZKP_CUDA(ws.keys_b.ensure(N * 4));
-    ZKP_CUDA(ws.vals_a.ensure(N * 4));
-    ZKP_CUDA(ws.vals_b.ensure(N * 4));
+    if (msm_uses_bucket_sort(ctx, plan)) {
+        ZKP_CUDA(ws.keys_b.ensure(N * 8));  // interleaved (key, value) pairs in bucket order
+    } else {
+        ZKP_CUDA(ws.keys_a.ensure(N * 4));
+        ZKP_CUDA(ws.keys_b.ensure(N * 4));
+        ZKP_CUDA(ws.vals_a.ensure(N * 4));
+        ZKP_CUDA(ws.vals_b.ensure(N * 4));
+    }
     const size_t nb = (size_t)plan.Wb * plan.B;
     ZKP_CUDA(ws.buckets.ensure(nb * sizeof(G1Xyzz)));
     if (ws.slot_keys.size() < plan.levels.size()) {
@@ -81,7 +85,6 @@ inline int msm_enqueue_prep(zkp_ctx* ctx, int lane, const MsmPlan& plan, const u
         const uint32_t m = plan.discard + 1, chunks = (m + SORT_CHUNK - 1) / SORT_CHUNK;
         ZKP_CUDA(ws.sort_counters.ensure((size_t)chunks * SORT_CHUNK * 4));
         ZKP_CUDA(ws.sort_chunks.ensure((size_t)chunks * 4));
-        ZKP_CUDA(ws.keys_b.ensure(N * 8));  // interleaved (key, value) pairs
         ZKP_CUDA(cudaMemsetAsync(ws.sort_counters.p, 0, (size_t)chunks * SORT_CHUNK * 4, st));
         k_decompose<DIGITS_COUNT><<<(plan.n + 255) / 256, 256, 0, st>>>(d_scalars, plan.n, plan.c, plan.W, plan.B, plan.discard, fmt,
                                                                         plan.precomp ? 1 : 0, plan.win_stride, plan.neg_offset, nullptr,
