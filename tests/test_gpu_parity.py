@@ -355,6 +355,37 @@ def test_commit_open_2p24_trapdoor_identity(gpu_ctx):
     gpu_ctx.srs_generate(TAU_X, TAU_Y, 4, 0)  # drop the 2^24 row and its tables before the next test
 
 
+def test_msm_sort_paths_and_linearity_full_size(gpu_ctx):
+    """Size-independent properties at 2^20 (BASELINE configs[2]): the hand-written bucket sort, the library radix sort
+    and the classic per-window buckets give the same bytes for uniform, constant and sparse scalars; the commitment is
+    linear: commit(f + g) = commit(f) + commit(g) (field addition on the CPU, group addition through zkp_g1_sum)."""
+    log_n = 20
+    n = 1 << log_n
+    gpu_ctx.srs_generate(TAU_X, TAU_Y, log_n, 0)
+    f = gpu_ctx.random_poly(0xF00D, n)
+    g = gpu_ctx.random_poly(0xBEEF, n)
+    const = f[:32] * n
+    sparse = b"".join(f[32 * i:32 * i + 32] if i % 97 == 0 else bytes(32) for i in range(n))
+    try:
+        for sc in (f, const, sparse):
+            gpu_ctx.set_msm_sort(1)
+            a = gpu_ctx.msm_g1(0, sc)
+            gpu_ctx.set_msm_sort(0)
+            assert gpu_ctx.msm_g1(0, sc) == a
+        gpu_ctx.set_msm_mode(False)
+        gpu_ctx.set_msm_sort(1)
+        classic = gpu_ctx.msm_g1(0, f)
+        gpu_ctx.set_msm_mode(True)
+        cf, cg = gpu_ctx.msm_g1(0, f), gpu_ctx.msm_g1(0, g)
+        assert classic == cf
+        fi, gi = ref.split32(f), ref.split32(g)
+        s = ref.join32([(x + y) % R for x, y in zip(fi, gi)])
+        assert gpu_ctx.msm_g1(0, s) == native.g1_sum(cf + cg)
+    finally:
+        gpu_ctx.set_msm_sort(2)
+        gpu_ctx.set_msm_mode(True)
+
+
 @pytest.mark.parametrize("log_n", [4, 12, 20])
 def test_commit_path_a_equals_path_b(gpu_ctx, log_n, golden):
     """BASELINE configs[2]: path A = MSM of the evaluations over the Lagrange SRS; path B = iNTT on the GPU, then
