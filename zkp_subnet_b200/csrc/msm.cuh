@@ -257,7 +257,10 @@ __global__ void k_decompose(const uint32_t* __restrict__ scalars, uint32_t n, ui
             // lanes of the warp that hold the same key act as one: a constant polynomial puts all 32 lanes (and every
             // warp of the grid) on ONE counter per window, and must not turn into n serialised atomics
             // (measured: no aggregation makes a lone 2^20 MSM 0.05 ms faster on uniform scalars and 42% slower on a
-            // constant polynomial; aggregating only the all-equal warp loses 25% on a two-valued polynomial)
+            // constant polynomial; aggregating only the all-equal warp loses 25% on a two-valued polynomial; issuing
+            // the matches and atomics of 8 digit positions back to back before using any result is SLOWER -- count
+            // 112 -> 119 us, scatter 238 -> 290 us: the passes are bound by L2 transaction throughput, not by the
+            // latency a thread sees)
             const uint32_t peers = __match_any_sync(__activemask(), key);
             const uint32_t leader = __ffs(peers) - 1, rank = __popc(peers & lanes_below);
             if (MODE == DIGITS_COUNT) {
