@@ -111,6 +111,23 @@ __attribute__((target("avx2"))) inline bool b64_decode32_avx2(const char* s, uin
     memcpy(out + 16, t1 + 7, 16);
     return _mm256_testz_si256(bad, bad) && t1[23] == 0;
 }
+// The same with non-temporal stores (out 16-byte aligned; the caller issues _mm_sfence() when its range is done): a
+// polynomial decoded into page-locked memory is read next by the GPU's DMA engine, not by a core, and a host->device
+// copy of 32 MiB that sixteen cores have just left dirty in their caches was measured 0.9 ms slower than the same
+// copy of data at rest.
+__attribute__((target("avx2"))) inline bool b64_decode32_avx2_stream(const char* s, uint8_t out[32]) {
+    __m256i bad = _mm256_setzero_si256();
+    const __m256i a = _mm256_loadu_si256(reinterpret_cast<const __m256i*>(s));
+    __m256i b = _mm256_loadu_si256(reinterpret_cast<const __m256i*>(s + 12));
+    b = _mm256_blendv_epi8(b, _mm256_set1_epi8('A'), _mm256_setr_epi8(0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0,
+                                                                       0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, -1));
+    alignas(32) uint8_t t1[32];
+    const __m256i d0 = b64_decode_32chars(a, &bad);
+    _mm256_store_si256(reinterpret_cast<__m256i*>(t1), b64_decode_32chars(b, &bad));
+    _mm_stream_si128(reinterpret_cast<__m128i*>(out), _mm256_castsi256_si128(d0));
+    _mm_stream_si128(reinterpret_cast<__m128i*>(out + 16), _mm_loadu_si128(reinterpret_cast<const __m128i*>(t1 + 7)));
+    return _mm256_testz_si256(bad, bad) && t1[23] == 0;
+}
 #endif
 
 inline void b64_encode32(const uint8_t in[32], char out[43]) {

@@ -29,11 +29,12 @@ static unsigned cmp_threads() {
 // ref != nullptr: also compares every decoded element with ref[32 i ..] and reports *same (the fourier.Client
 // shim uses it to recognise the polynomial it was handed by the previous call, see client.py worker_open)
 // one element whose buffer has at least 44 readable bytes (str and bytes objects keep a terminator)
-static inline bool decode_one(const char* p, uint8_t* out, bool avx2) {
+static inline bool decode_one(const char* p, uint8_t* out, bool avx2, bool stream = false) {
 #ifdef ZKP_CODEC_AVX2
-    if (avx2) return codec::b64_decode32_avx2(p, out);
+    if (avx2) return stream ? codec::b64_decode32_avx2_stream(p, out) : codec::b64_decode32_avx2(p, out);
 #endif
     (void)avx2;
+    (void)stream;
     return codec::b64_decode32(p, out);
 }
 static long long decode_list_impl(PyObject* seq, uint8_t* out, size_t capacity, const uint8_t* ref, int* same) {
@@ -56,6 +57,8 @@ static long long decode_list_impl(PyObject* seq, uint8_t* out, size_t capacity, 
 #else
     const bool avx2 = false;
 #endif
+    // non-temporal stores for a large result that nobody on the host reads back (not the compare variant)
+    const bool stream = avx2 && !ref && n >= 4096 && (reinterpret_cast<uintptr_t>(out) & 15) == 0;
     auto lower = [](std::atomic<size_t>& a, size_t i) {
         size_t cur = a.load();
         while (i < cur && !a.compare_exchange_weak(cur, i)) {}
@@ -75,12 +78,15 @@ static long long decode_list_impl(PyObject* seq, uint8_t* out, size_t capacity, 
                 lower(first_slow, i);
                 continue;
             }
-            if (!(len == 43 || (len == 44 && p[43] == '=')) || !decode_one(p, out + 32 * i, avx2)) {
+            if (!(len == 43 || (len == 44 && p[43] == '=')) || !decode_one(p, out + 32 * i, avx2, stream)) {
                 lower(first_bad, i);
-                return;
+                break;
             }
             if (ref && memcmp(out + 32 * i, ref + 32 * i, 32) != 0) differs.store(1, std::memory_order_relaxed);
         }
+#ifdef ZKP_CODEC_AVX2
+        if (stream) _mm_sfence();
+#endif
     }, ref ? cmp_threads() : 0u);
     // serial pass over the elements the workers skipped (none for the lists the reference sends)
     for (size_t i = first_slow.load(); i < (size_t)n && i < first_bad.load(); i++) {
