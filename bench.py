@@ -417,7 +417,7 @@ def main():
                                f"N>1 = Pianist split, one sub-polynomial per GPU, 96-byte gather per step",
                    "log_n": log_n, "msm_window_bits": c, "msm_windows": W, "rows": 1 << log_m,
                    "l2": "flushed (256 MiB memset) before every timed iteration of `value`; e2e working set "
-                         "(fixed-base tables 2.4 GiB gathered at random + sorted entry pairs 104 MiB + buckets 96 MiB) exceeds the 126 MB L2",
+                         "(fixed-base tables 3.25 GiB gathered at random + sorted entry pairs 104 MiB + buckets 96 MiB) exceeds the 126 MB L2",
                    "seed": "0xB200+3"},
         "gpu_launches": int(launches) * args.steps,
         "clocks": clocks,

@@ -335,7 +335,7 @@ def test_full_size_trapdoor_identity(gpu_ctx, log_n):
 
 
 def test_commit_open_2p24_trapdoor_identity(gpu_ctx):
-    """BASELINE configs[3] and the north_star size: one SRS row of 2^24 points (1.5 GiB affine, 36 GiB of fixed-base
+    """BASELINE configs[3] and the north_star size: one SRS row of 2^24 points (1.5 GiB affine, 48 GiB of fixed-base
     tables), commitment and opening proof checked through the trapdoor (commit == [sum f_j L_j(tau)]_1,
     proof == [sum q_j L_j(tau)]_1 with q from the oracle's quotient), y against the oracle, pairing check on the
     host.  The level-0 accumulation kernel runs its longest slices here."""

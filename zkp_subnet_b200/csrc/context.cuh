@@ -110,7 +110,7 @@ struct zkp_ctx {
     struct Precomp { zkp::DevBuf table; uint32_t c = 0, W = 0; };
     std::vector<Precomp> precomp;
     bool use_precomp = true;
-    zkp::DevBuf scratch_xyzz, scratch_fq;
+    zkp::DevBuf scratch_xyzz, scratch_fq, scratch_aff;
     uint32_t shard_domain_log = 0;            // log2 of the full domain when the rows are point-range shards
     uint32_t shard_index = 0;                 // which slice [shard * 2^log_n, (shard+1) * 2^log_n) of that domain
     uint64_t launches = 0;                    // kernels launched by this context (bench accounting)

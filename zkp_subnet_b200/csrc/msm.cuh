@@ -48,6 +48,7 @@
 
 namespace zkp {
 
+constexpr uint32_t TABLE_STRIDE = 128;       // bytes per record of a fixed-base table (96 used, padded to one L2 line)
 constexpr uint32_t KEY_NONE = 0xffffffffu;   // slot of a thread that had no entries
 constexpr uint32_t KEY_EMPTY_FLAG = 0x80000000u;  // slot carries a key but no point
 
@@ -401,7 +402,10 @@ __global__ void __launch_bounds__(LEVEL0 ? ZKP_ACC_THREADS : 128, LEVEL0 ? ZKP_A
 k_accumulate(const uint32_t* __restrict__ keys, const uint32_t* __restrict__ vals,
              const G1Affine* __restrict__ points, const G1Xyzz* __restrict__ slots_in, size_t items,
              uint32_t L, uint32_t discard, G1Xyzz* __restrict__ buckets, uint32_t* __restrict__ slot_keys,
-             G1Xyzz* __restrict__ slot_pts, int last_level, uint32_t S = 1) {
+             G1Xyzz* __restrict__ slot_pts, int last_level, uint32_t S = 1, uint32_t pstride = sizeof(G1Affine)) {
+    // pstride: bytes between consecutive records of `points` -- 96 for an SRS row or a list of the batched-affine
+    // rounds, TABLE_STRIDE (128) for a fixed-base table, whose records are padded so that a gather touches ONE
+    // 128-byte line instead of 1.75 on average
     // S: stride of the level-0 entry arrays in words -- 1 for separate key / value arrays (library sort, batched-affine
     // output), 2 for the interleaved (key, value) pairs written by the bucket sort (vals == keys + 1)
     // Level 0: one thread per slice.  Small slot levels (COOP): FOUR lanes per slice -- they run the same control flow
@@ -483,16 +487,17 @@ k_accumulate(const uint32_t* __restrict__ keys, const uint32_t* __restrict__ val
             if (vals && i + 1 < end) {
                 // the gather is a 96-byte random read of a table far larger than L2: pull the NEXT point
                 // towards L2 while this one is being added (no registers held, unlike a software pipeline)
-                const char* nx = reinterpret_cast<const char*>(points + (vals[(i + 1) * S] & 0x7fffffffu));
+                const char* nx = reinterpret_cast<const char*>(points) + (size_t)(vals[(i + 1) * S] & 0x7fffffffu) * pstride;
                 asm volatile("prefetch.global.L2 [%0];" ::"l"(nx));
                 asm volatile("prefetch.global.L2 [%0];" ::"l"(nx + 64));
             }
-            G1Affine p = load_affine(points + (v & 0x7fffffffu));
+            const G1Affine* pp = reinterpret_cast<const G1Affine*>(reinterpret_cast<const char*>(points) + (size_t)(v & 0x7fffffffu) * pstride);
+            G1Affine p = load_affine(pp);
             if (v >> 31) p.y = p.y.neg();  // never taken with a negated table half (-(0, 0) stays the infinity marker)
             if (!p.is_inf()) {
                 const int st = acc.madd_lazy_core(p.x, p.y, s_kp);
                 if (st) {  // equal or opposite operands: fetch the point again rather than keep it live
-                    p = load_affine_again(points + (v & 0x7fffffffu));
+                    p = load_affine_again(pp);
                     if (v >> 31) p.y = p.y.neg();
                     acc.madd_lazy_rare(st, p.x, p.y);
                 }

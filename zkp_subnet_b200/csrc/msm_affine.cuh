@@ -114,7 +114,8 @@ template <bool FIRST>
 __global__ void __launch_bounds__(128, ZKP_AFF_MIN_BLOCKS)
 k_affine_round(const uint32_t* __restrict__ start_in, const uint32_t* __restrict__ start_out, uint32_t nb,
                const uint32_t* __restrict__ vals, const G1Affine* __restrict__ in_pts, G1Affine* __restrict__ out_pts,
-               uint32_t* __restrict__ out_keys, uint32_t K, Fq* __restrict__ scratch, uint32_t total_threads, uint32_t sm_count) {
+               uint32_t* __restrict__ out_keys, uint32_t K, Fq* __restrict__ scratch, uint32_t total_threads, uint32_t sm_count,
+               uint32_t first_stride = sizeof(G1Affine)) {
     const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
     const uint32_t n_out = start_out[nb];
     const uint64_t o_begin64 = (uint64_t)t * K;
@@ -140,7 +141,11 @@ k_affine_round(const uint32_t* __restrict__ start_in, const uint32_t* __restrict
     // otherwise) and of the second operand, or PAIR_NONE when the output is a plain copy
     constexpr uint32_t PAIR_NONE = 0xffffffffu;
     uint32_t ia[AFF_KB], ib[AFF_KB];
-    auto point_of = [&](uint32_t v) -> const G1Affine* { return in_pts + (FIRST ? (v & 0x7fffffffu) : v); };
+    // FIRST: records of the SRS row (96 bytes) or of a fixed-base table (TABLE_STRIDE bytes)
+    auto point_of = [&](uint32_t v) -> const G1Affine* {
+        if (FIRST) return reinterpret_cast<const G1Affine*>(reinterpret_cast<const char*>(in_pts) + (size_t)(v & 0x7fffffffu) * first_stride);
+        return in_pts + v;
+    };
     auto load_x = [&](uint32_t v) -> Fq { return load_fq_ldg(&point_of(v)->x); };
     auto load_y = [&](uint32_t v) -> Fq {
         Fq y = load_fq_ldg(&point_of(v)->y);

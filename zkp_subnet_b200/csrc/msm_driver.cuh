@@ -119,6 +119,7 @@ inline int msm_enqueue_main(zkp_ctx* ctx, int lane, const MsmPlan& plan, const G
     const uint32_t* acc_keys = ws.keys_b.as<uint32_t>();
     const uint32_t* acc_vals = packed ? acc_keys + 1 : ws.vals_b.as<uint32_t>();
     const G1Affine* acc_points = d_points;
+    uint32_t acc_stride = plan.precomp ? TABLE_STRIDE : (uint32_t)sizeof(G1Affine);  // records of d_points
     if (plan.affine_rounds) {
         const uint32_t nbk = plan.discard, R = plan.affine_rounds;
         for (uint32_t r = 0; r <= R; r++) ZKP_CUDA(ws.aff_start[r].ensure(((size_t)nbk + 1) * 4));
@@ -152,7 +153,7 @@ inline int msm_enqueue_main(zkp_ctx* ctx, int lane, const MsmPlan& plan, const G
             if (r == 0)
                 k_affine_round<true><<<blocks, 128, 0, st>>>(ws.aff_start[0].as<uint32_t>(), ws.aff_start[1].as<uint32_t>(), nbk,
                                                              ws.vals_b.as<uint32_t>(), d_points, ws.aff_pts[0].as<G1Affine>(), out_keys, K,
-                                                             ws.aff_scratch.as<Fq>(), total_threads, (uint32_t)ctx->sm_count);
+                                                             ws.aff_scratch.as<Fq>(), total_threads, (uint32_t)ctx->sm_count, acc_stride);
             else
                 k_affine_round<false><<<blocks, 128, 0, st>>>(ws.aff_start[r].as<uint32_t>(), ws.aff_start[r + 1].as<uint32_t>(), nbk, nullptr,
                                                               ws.aff_pts[(r - 1) & 1].as<G1Affine>(), ws.aff_pts[r & 1].as<G1Affine>(), out_keys,
@@ -162,6 +163,7 @@ inline int msm_enqueue_main(zkp_ctx* ctx, int lane, const MsmPlan& plan, const G
         acc_keys = ws.aff_keys.as<uint32_t>();
         acc_vals = nullptr;
         acc_points = ws.aff_pts[(R - 1) & 1].as<G1Affine>();
+        acc_stride = (uint32_t)sizeof(G1Affine);
         trace_mark(ctx, lane, st, "affine_rounds");
     }
     // 3. balanced accumulation, level by level
@@ -178,7 +180,8 @@ inline int msm_enqueue_main(zkp_ctx* ctx, int lane, const MsmPlan& plan, const G
             k_accumulate<true><<<blocks, ZKP_ACC_THREADS, 0, st>>>(acc_keys, acc_vals, acc_points, nullptr,
                                                        lv.items, lv.L, plan.discard, ws.buckets.as<G1Xyzz>(),
                                                        last ? nullptr : ws.slot_keys[0].as<uint32_t>(),
-                                                       last ? nullptr : ws.slot_pts[0].as<G1Xyzz>(), last, packed ? 2u : 1u);
+                                                       last ? nullptr : ws.slot_pts[0].as<G1Xyzz>(), last, packed ? 2u : 1u,
+                                                                   acc_stride);
             if (ctx->time_acc) cudaEventRecord(ev1, st);
             trace_mark(ctx, lane, st, "accumulate_l0");
         } else if (coop) {

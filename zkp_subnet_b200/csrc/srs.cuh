@@ -125,10 +125,10 @@ k_fixed_base_mul(const Fr* __restrict__ scalars, size_t n, const G1Affine* __res
 
 // fixed-base table step: out[i] = [2^c] in[i]
 __global__ void __launch_bounds__(128)
-k_table_next(const G1Affine* __restrict__ in, size_t n, uint32_t c, G1Xyzz* __restrict__ out) {
+k_table_next(const char* __restrict__ in /* TABLE_STRIDE-byte records */, size_t n, uint32_t c, G1Xyzz* __restrict__ out) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    G1Affine p = in[i];
+    G1Affine p = *reinterpret_cast<const G1Affine*>(in + i * TABLE_STRIDE);
     G1Xyzz acc = G1Xyzz::infinity();
     if (!p.is_inf()) {
         acc = G1Xyzz::dbl_affine(p.x, p.y);
@@ -138,12 +138,18 @@ k_table_next(const G1Affine* __restrict__ in, size_t n, uint32_t c, G1Xyzz* __re
 }
 
 // out[i] = -in[i] (the negated half of a fixed-base table; the infinity marker (0, 0) maps to itself)
-__global__ void k_negate_points(const G1Affine* __restrict__ in, size_t n, G1Affine* __restrict__ out) {
+__global__ void k_negate_points(const char* __restrict__ in, size_t n, char* __restrict__ out) {  // TABLE_STRIDE-byte records
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    G1Affine p = in[i];
+    G1Affine p = *reinterpret_cast<const G1Affine*>(in + i * TABLE_STRIDE);
     p.y = p.y.neg();
-    out[i] = p;
+    *reinterpret_cast<G1Affine*>(out + i * TABLE_STRIDE) = p;
+}
+// 96-byte points -> TABLE_STRIDE-byte records (a slice of a fixed-base table)
+__global__ void k_pad_points(const G1Affine* __restrict__ in, size_t n, char* __restrict__ out) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    *reinterpret_cast<G1Affine*>(out + i * TABLE_STRIDE) = in[i];
 }
 
 // XYZZ -> affine with one inversion per run of E points (prefix products parked in scratch)

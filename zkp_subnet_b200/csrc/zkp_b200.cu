@@ -71,7 +71,7 @@ int ensure_precomp(zkp_ctx* ctx, uint32_t row, uint32_t c, bool* ok) {
     if (pc.table.p && pc.c == c && pc.W == W) { *ok = true; return ZKP_OK; }
     const size_t n_row = (size_t)1 << ctx->log_n;
     // W slices [2^(c w)] P_i followed by the same W slices negated: the sign of a digit picks the half
-    const size_t bytes = 2 * (size_t)W * n_row * sizeof(G1Affine);
+    const size_t bytes = 2 * (size_t)W * n_row * TABLE_STRIDE;
     pc.table.release();
     pc.c = 0;
     size_t free_b = 0, total_b = 0;
@@ -81,17 +81,25 @@ int ensure_precomp(zkp_ctx* ctx, uint32_t row, uint32_t c, bool* ok) {
     ZKP_CUDA(ctx->scratch_xyzz.ensure(n_row * sizeof(G1Xyzz)));
     ZKP_CUDA(ctx->scratch_fq.ensure(n_row * sizeof(Fq)));
     cudaStream_t st = ctx->stream;
-    G1Affine* tab = pc.table.as<G1Affine>();
-    ZKP_CUDA(cudaMemcpyAsync(tab, row_ptr(ctx, row), n_row * sizeof(G1Affine), cudaMemcpyDeviceToDevice, st));
+    // records padded to TABLE_STRIDE bytes (msm.cuh); every slice is converted to affine in a 96-byte-stride
+    // scratch slice and then placed
+    char* tab = pc.table.as<char>();
+    const size_t slice = n_row * TABLE_STRIDE;
+    ZKP_CUDA(ctx->scratch_aff.ensure(n_row * sizeof(G1Affine)));
+    ZKP_CUDA(cudaMemsetAsync(tab, 0, bytes, st));
+    const unsigned gp = (unsigned)((n_row + 255) / 256);
+    k_pad_points<<<gp, 256, 0, st>>>(row_ptr(ctx, row), n_row, tab);
+    ctx->launches++;
     const uint32_t EA = 16;
     const unsigned ta = (unsigned)((n_row + EA - 1) / EA);
     for (uint32_t w = 1; w < W; w++) {
-        k_table_next<<<(unsigned)((n_row + 127) / 128), 128, 0, st>>>(tab + (size_t)(w - 1) * n_row, n_row, c, ctx->scratch_xyzz.as<G1Xyzz>());
+        k_table_next<<<(unsigned)((n_row + 127) / 128), 128, 0, st>>>(tab + (size_t)(w - 1) * slice, n_row, c, ctx->scratch_xyzz.as<G1Xyzz>());
         k_xyzz_to_affine<<<(ta + 127) / 128, 128, 0, st>>>(ctx->scratch_xyzz.as<G1Xyzz>(), n_row, EA, ctx->scratch_fq.as<Fq>(),
-                                                           tab + (size_t)w * n_row);
-        ctx->launches += 2;
+                                                           ctx->scratch_aff.as<G1Affine>());
+        k_pad_points<<<gp, 256, 0, st>>>(ctx->scratch_aff.as<G1Affine>(), n_row, tab + (size_t)w * slice);
+        ctx->launches += 3;
     }
-    k_negate_points<<<(unsigned)(((size_t)W * n_row + 255) / 256), 256, 0, st>>>(tab, (size_t)W * n_row, tab + (size_t)W * n_row);
+    k_negate_points<<<(unsigned)(((size_t)W * n_row + 255) / 256), 256, 0, st>>>(tab, (size_t)W * n_row, tab + (size_t)W * slice);
     ctx->launches++;
     ZKP_CUDA(cudaStreamSynchronize(st));
     ZKP_CUDA(cudaGetLastError());
@@ -219,6 +227,7 @@ void zkp_ctx_destroy(zkp_ctx* ctx) {
         drop_precomp(ctx, -1);
         ctx->scratch_xyzz.release();
         ctx->scratch_fq.release();
+        ctx->scratch_aff.release();
         for (DevBuf* b : {&ctx->srs, &ctx->scalars, &ctx->fr_a, &ctx->fr_b, &ctx->fr_c, &ctx->flush, &ctx->small, &ctx->partials,
                           &ctx->ntt_tmp, &ctx->fixed_base})
             b->release();
