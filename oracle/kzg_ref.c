@@ -578,16 +578,42 @@ static void* srs_worker(void* arg) {
         g1j_add(&base, &t[w][15], &base);
     }
     (void)tab;
-    for (size_t i = j->lo; i < j->hi; i++) {
-        fr k; fr_from_mont(&k, &j->k[i]);
-        g1j acc; g1j_set_inf(&acc);
-        for (int w = 0; w < 64; w++) {
-            unsigned d = (unsigned)((k.v[w >> 4] >> ((w & 15) * 4)) & 15);
-            if (d) g1j_add(&acc, &acc, &t[w][d]);
+    /* chunks of CH points share one field inversion (Montgomery's trick on the Z coordinates) */
+    enum { CH = 256 };
+    g1j* pts = (g1j*)malloc(sizeof(g1j) * CH);
+    fq* pre = (fq*)malloc(sizeof(fq) * CH);
+    for (size_t lo = j->lo; lo < j->hi; lo += CH) {
+        size_t cnt = j->hi - lo < CH ? j->hi - lo : CH;
+        for (size_t c = 0; c < cnt; c++) {
+            fr k; fr_from_mont(&k, &j->k[lo + c]);
+            g1j acc; g1j_set_inf(&acc);
+            for (int w = 0; w < 64; w++) {
+                unsigned d = (unsigned)((k.v[w >> 4] >> ((w & 15) * 4)) & 15);
+                if (d) g1j_add(&acc, &acc, &t[w][d]);
+            }
+            pts[c] = acc;
         }
-        g1a a; g1j_to_affine(&a, &acc);
-        g1_serialize96(j->out + 96 * i, &a);
+        fq run; memset(&run, 0, sizeof(run));
+        { fq one = {{1, 0, 0, 0, 0, 0}}; fq_to_mont(&run, &one); }
+        for (size_t c = 0; c < cnt; c++) {
+            pre[c] = run;
+            if (!g1j_is_inf(&pts[c])) fq_mul(&run, &run, &pts[c].z);
+        }
+        fq inv; fq_inv(&inv, &run);
+        for (size_t c = cnt; c-- > 0;) {
+            g1a a;
+            if (g1j_is_inf(&pts[c])) { memset(&a, 0, sizeof(a)); a.inf = 1; }
+            else {
+                fq zi, zi2, zi3;
+                fq_mul(&zi, &inv, &pre[c]);
+                fq_mul(&inv, &inv, &pts[c].z);
+                fq_sqr(&zi2, &zi); fq_mul(&zi3, &zi2, &zi);
+                fq_mul(&a.x, &pts[c].x, &zi2); fq_mul(&a.y, &pts[c].y, &zi3); a.inf = 0;
+            }
+            g1_serialize96(j->out + 96 * (lo + c), &a);
+        }
     }
+    free(pts); free(pre);
     free(t);
     return NULL;
 }
@@ -612,12 +638,25 @@ int ref_srs(const uint8_t* tau_be, const uint8_t* scale_be, size_t n, int kind, 
         fr_from_u64(&ninv, (u64)n); fr_inv(&ninv, &ninv);
         fr_mul(&zn, &zn, &ninv);
         fr_mul(&zn, &zn, scale);
+        /* one inversion for all the denominators (Montgomery's trick): pre[j] = d_0 .. d_(j-1) */
+        fr* d = (fr*)malloc(sizeof(fr) * (n ? n : 1));
+        fr* pre = (fr*)malloc(sizeof(fr) * (n ? n : 1));
+        fr run = one;
         wj = one;
         for (size_t j = 0; j < n; j++) {
-            fr d; fr_sub(&d, tau, &wj); fr_inv(&d, &d);
-            fr_mul(&k[j], &zn, &wj); fr_mul(&k[j], &k[j], &d);
+            fr_sub(&d[j], tau, &wj);
+            fr_mul(&k[j], &zn, &wj);
+            pre[j] = run;
+            fr_mul(&run, &run, &d[j]);
             fr_mul(&wj, &wj, &w);
         }
+        fr inv; fr_inv(&inv, &run);
+        for (size_t j = n; j-- > 0;) {
+            fr dj; fr_mul(&dj, &inv, &pre[j]);
+            fr_mul(&inv, &inv, &d[j]);
+            fr_mul(&k[j], &k[j], &dj);
+        }
+        free(d); free(pre);
     }
     if (threads < 1) threads = 1;
     if ((size_t)threads > n) threads = n ? (int)n : 1;
@@ -682,6 +721,30 @@ int ref_lagrange_scalars(const uint8_t* tau_be, const uint8_t* scale_be, size_t 
     }
     free(d); free(pre); free(tau); free(scale);
     return ok1 && ok2 ? 0 : -2;
+}
+/* Elements [first, first + n) of the COUNTER-BASED stream the product's device generator produces (zkp_random_poly /
+ * zkp_random_poly_range, kzg.cuh k_random_fr): candidate `attempt` of element i is four SplitMix64 outputs from the
+ * state seed + GOLDEN * (4 (64 i + attempt) + 1), little-endian 64-bit words, top bit cleared, first candidate < r
+ * wins.  Restated here so that the tests and the benchmark can compute expected commitments of device-generated
+ * inputs without copying them back. */
+void ref_random_scalars_ctr(uint64_t seed, uint64_t first, size_t n, uint8_t* out_be) {
+    for (size_t t = 0; t < n; t++) {
+        const u64 i = first + t;
+        fr v;
+        for (u64 attempt = 0;; attempt++) {
+            u64 s = seed + 0x9e3779b97f4a7c15ull * (4 * (i * 64 + attempt) + 1);
+            for (int k = 0; k < RL; k++) {
+                s += 0x9e3779b97f4a7c15ull;
+                u64 z = s;
+                z = (z ^ (z >> 30)) * 0xbf58476d1ce4e5b9ull;
+                z = (z ^ (z >> 27)) * 0x94d049bb133111ebull;
+                v.v[k] = z ^ (z >> 31);
+            }
+            v.v[RL - 1] &= 0x7fffffffffffffffull;
+            if (!ge_n(v.v, R_MOD, RL)) break;
+        }
+        fr_to_be(out_be + 32 * t, &v);
+    }
 }
 /* uniform-ish test scalars: SplitMix64 stream -> 256 bits -> top bit cleared twice -> < r by rejection */
 void ref_random_scalars(uint64_t seed, size_t n, uint8_t* out_be) {

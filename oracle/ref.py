@@ -37,6 +37,8 @@ def lib() -> ctypes.CDLL:
         _lib.ref_lagrange_scalars.argtypes = [c.c_char_p, c.c_char_p, c.c_size_t, c.c_char_p]
         _lib.ref_random_scalars.argtypes = [c.c_uint64, c.c_size_t, c.c_char_p]
         _lib.ref_random_scalars.restype = None
+        _lib.ref_random_scalars_ctr.argtypes = [c.c_uint64, c.c_uint64, c.c_size_t, c.c_char_p]
+        _lib.ref_random_scalars_ctr.restype = None
     return _lib
 
 
@@ -113,6 +115,13 @@ def lagrange_scalars(n: int, tau: int, scale: int = 1) -> bytes:
 def random_scalars(seed: int, n: int) -> bytes:
     out = ctypes.create_string_buffer(32 * n)
     lib().ref_random_scalars(seed, n, out)
+    return out.raw
+
+
+def random_scalars_ctr(seed: int, first: int, n: int) -> bytes:
+    """elements [first, first + n) of the counter-based stream of the product's device generator (zkp_random_poly)"""
+    out = ctypes.create_string_buffer(32 * n)
+    lib().ref_random_scalars_ctr(seed, first, n, out)
     return out.raw
 
 

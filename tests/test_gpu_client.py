@@ -21,8 +21,11 @@ TEST_MACHINE_COUNT = 2
 @pytest.fixture(scope="module")
 def client(tmp_path_factory):
     path = str(tmp_path_factory.mktemp("srs") / "test_setup.compressed")
-    c = Client(port=1337, bin="./test_prover", uncompressed=False, setup_path=path, precompute_path=path + ".pre")
+    # no SRS file exists at `path`: the throw-away test SRS has to be asked for explicitly, and nothing is written
+    c = Client(port=1337, bin="./test_prover", uncompressed=False, setup_path=path, precompute_path=path + ".pre", test_srs=True)
     c.start(scale=TEST_SCALE, machines_scale=TEST_MACHINES_SCALE)
+    import os
+    assert c.srs_source == "test-trapdoor" and not os.path.exists(path)
     yield c
     c.stop()
 
@@ -261,7 +264,7 @@ def test_worker_open_after_worker_commit_reuses_the_resident_polynomial(client, 
     poly_a = [enc(rng.randrange(o.R)) for _ in range(n)]
     poly_b = [enc(rng.randrange(o.R)) for _ in range(n)]
     x = enc(rng.randrange(o.R))
-    fresh = Client(setup_path=client.setup_path)
+    fresh = Client(test_srs=True)
     fresh.start(scale=TEST_SCALE, machines_scale=TEST_MACHINES_SCALE)
     try:
         expect = {}
@@ -269,7 +272,7 @@ def test_worker_open_after_worker_commit_reuses_the_resident_polynomial(client, 
             expect[name] = fresh.worker_open(1, list(p), x).json()      # never preceded by a call on the same list
             fresh.fft(poly_a, True, False)                              # drops the resident polynomial
         assert client.worker_commit(1, poly_a).status_code == 200
-        assert client._resident_n == n
+        assert client._free.queue[-1].resident_n == n  # the slot that served the call (the pool is last-in first-out)
         assert client.worker_open(1, poly_a, x).json() == expect["a"]   # speculative result accepted
         assert client.worker_open(1, list(poly_a), x).json() == expect["a"]   # an equal COPY of the list as well
         assert client.worker_open(1, poly_b, x).json() == expect["b"]   # same length, other polynomial: rejected, redone

@@ -10,19 +10,29 @@ CPU fallback: `start()` raises if the library or a GPU is missing.
 Wire format (reference base/protocol.py:35-60, tests/test_miner.py:33-55): field elements are
 unpadded standard base64 of 32 big-endian bytes; G1 points are base64 of the 48-byte ZCash
 compressed encoding.
+
+Concurrency (reference base/miner.py:66-70 hands `forward` to the axon's threads): the client keeps a POOL of
+contexts -- `contexts` per device, all sharing one resident SRS and one set of fixed-base tables per device
+(zkp_ctx_fork) -- and every call borrows one, so concurrent requests overlap on the GPU instead of queueing on a lock.
+With `devices=[...]` the pool spans several GPUs (each holds the SRS); `multi_gpu="split"` instead splits EVERY
+request by point range over the GPUs (zkp_mgpu_commit_open).
 """
 from __future__ import annotations
 
 import base64
 import os
+import queue
 import secrets
+import sys
 import threading
 from typing import Any, Dict, List, Optional, Sequence
 
-from . import native
+from . import native, srsfile
 
-# Public test trapdoors used when no SRS file exists (the reference's tests also generate a
-# throw-away SRS: tests/conftest.py:50-65).  A production deployment loads the ceremony SRS file.
+# Public test trapdoors for a throw-away SRS (the reference's tests also generate one: tests/conftest.py:50-65).
+# Anyone can forge openings against an SRS whose trapdoor is known, so it is only ever used behind an explicit
+# opt-in (Client(test_srs=True) or ZKP_B200_TEST_SRS=1), it is announced on stderr, and it is never written to
+# `setup_path`.  A deployment loads the ceremony files.
 TEST_TAU_X = 1927409816240961209460912649124
 TEST_TAU_Y = 0x1234567890ABCDEF1234567890ABCDEF
 
@@ -72,33 +82,101 @@ def encode_poly(raw: bytes) -> List[str]:
     return native.wire_encode_list(raw)
 
 
+def _bitrev(i: int, bits: int) -> int:
+    r = 0
+    for _ in range(bits):
+        r = (r << 1) | (i & 1)
+        i >>= 1
+    return r
+
+
+def _truthy(v) -> bool:
+    # the reference declares --uncompressed with type=bool, so `--uncompressed true` arrives as a non-empty string
+    # (utils/config.py:131-136); accept both
+    if isinstance(v, str):
+        return v.strip().lower() not in ("", "0", "false", "no", "off")
+    return bool(v)
+
+
+class _Slot:
+    """One pooled context with its page-locked staging buffers and what it remembers about the resident polynomial."""
+
+    def __init__(self, ctx):
+        self.ctx = ctx
+        self.staging: Optional[native.PinnedBuffer] = None
+        self.staging_alt: Optional[native.PinnedBuffer] = None  # second buffer of the speculative worker_open
+        self.resident_n = 0      # > 0: self.staging holds the n x 32 bytes of the polynomial this slot uploaded last
+        self.resident_gen = -1   # ... and this is the library's generation of that upload
+
+    def close(self, close_ctx: bool = True):
+        self.resident_n = 0
+        for name in ("staging", "staging_alt"):
+            if getattr(self, name) is not None:
+                getattr(self, name).close()
+                setattr(self, name, None)
+        if close_ctx and self.ctx is not None:
+            self.ctx.close()
+        self.ctx = None
+
+
 class Client:
-    """`Client(port=..., bin=..., uncompressed=..., setup_path=..., precompute_path=...)`.
+    """`Client(port=..., bin=..., uncompressed=..., setup_path=..., precompute_path=...)` (reference base/miner.py:75-81).
 
     `port` and `bin` are accepted for signature compatibility and ignored (there is no prover process).
-    `setup_path` names the SRS file: if it exists it is loaded, otherwise an SRS is generated on the GPU
-    from the public test trapdoor and saved there.  `precompute_path` / `uncompressed` are accepted and
-    ignored: the Lagrange ("precompute") rows live in the same file.
+    `setup_path` / `precompute_path` / `uncompressed` name the SRS files exactly as the reference's flags do
+    (Makefile:64-74): see zkp_subnet_b200/srsfile.py for the formats read.  A missing file is an ERROR unless the
+    throw-away test SRS has been asked for explicitly (`test_srs=True` or ZKP_B200_TEST_SRS=1).
+
+    Extensions (keyword-only in spirit; the reference never passes them):
+      device / devices   GPU(s) to use; with several devices every one holds the SRS
+      contexts           pooled contexts per device (concurrent requests overlap on the GPU)
+      precompute         "eager": build the fixed-base tables in start(); "lazy": inside the first request of a row
+      multi_gpu          "requests": each request runs on one GPU of the pool; "split": every request is split by
+                         point range over all GPUs (zkp_mgpu_commit_open)
+      poly_form          "evals" (default) or "coeffs": what the `poly` of worker_commit / worker_open holds
+                         (reference neurons/validator.py:67 says "coefficients", its own flow
+                         implies evaluations)
+      row_order          "natural" (default) or "bitrev": which SRS row worker index i uses, R_i or R_bitrev(i)
     """
 
     def __init__(self, port: int = 1337, bin: Optional[str] = None, uncompressed: bool = False,
                  setup_path: Optional[str] = None, precompute_path: Optional[str] = None, device: int = 0,
-                 seed: Optional[int] = None):
+                 seed: Optional[int] = None, devices: Optional[Sequence[int]] = None, contexts: int = 2,
+                 precompute: str = "eager", multi_gpu: str = "requests", poly_form: str = "evals",
+                 row_order: str = "natural", test_srs: Optional[bool] = None):
+        if precompute not in ("eager", "lazy"):
+            raise ValueError("precompute must be 'eager' or 'lazy'")
+        if multi_gpu not in ("requests", "split"):
+            raise ValueError("multi_gpu must be 'requests' or 'split'")
+        if poly_form not in ("evals", "coeffs"):
+            raise ValueError("poly_form must be 'evals' or 'coeffs'")
+        if row_order not in ("natural", "bitrev"):
+            raise ValueError("row_order must be 'natural' or 'bitrev'")
         self.port = port
         self.bin = bin
-        self.uncompressed = uncompressed
+        self.uncompressed = _truthy(uncompressed)
         self.setup_path = setup_path
         self.precompute_path = precompute_path
-        self.device = device
+        self.devices = list(devices) if devices else [device]
+        self.device = self.devices[0]
+        self.contexts = max(1, int(contexts))
+        self.precompute = precompute
+        self.multi_gpu = multi_gpu
+        self.poly_form = poly_form
+        self.row_order = row_order
+        self.test_srs = test_srs
         self.scale = None
         self.machines_scale = None
-        self._ctx: Optional[native.Context] = None
-        self._staging: Optional[native.PinnedBuffer] = None
-        self._staging_alt: Optional[native.PinnedBuffer] = None  # second buffer of the speculative worker_open
-        self._resident_n = 0  # > 0: self._staging holds the n x 32 bytes of the polynomial still resident on the GPU
-        self._lock = threading.Lock()  # the staging buffer is shared: one prover call at a time, as in the library
+        self.srs_source = None     # "file:<format>" or "test-trapdoor" once started
+        self._roots: List[native.Context] = []   # one per device: owns the SRS
+        self._slots: List[_Slot] = []
+        self._free: "queue.LifoQueue[_Slot]" = queue.LifoQueue()
+        self._mg: Optional[native.MultiContext] = None
+        self._mg_lock = threading.Lock()
+        self._attached = False
         self._seed = seed if seed is not None else secrets.randbits(63)
         self._counter = 0
+        self._counter_lock = threading.Lock()
 
     # ---- lifecycle (reference base/miner.py:82-84,155,181)
     def start(self, scale: int = 18, machines_scale: int = 8) -> None:
@@ -106,53 +184,131 @@ class Client:
             raise ValueError("machines_scale must not exceed scale")
         self.scale, self.machines_scale = int(scale), int(machines_scale)
         log_n = self.scale - self.machines_scale
-        self._ctx = native.Context(self.device)
-        path = self.setup_path
-        if path and os.path.exists(path):
-            self._ctx.srs_load(path)
-            if self._ctx.srs_shape() != (log_n, self.machines_scale):
-                raise native.ZkpError(native.ZKP_ERR_STATE, f"SRS file {path} has shape {self._ctx.srs_shape()}, "
-                                      f"expected {(log_n, self.machines_scale)}")
+        source = srsfile.find_source(self.setup_path, self.precompute_path, self.uncompressed, self.scale, self.machines_scale)
+        if source is None:
+            opted = self.test_srs if self.test_srs is not None else os.environ.get("ZKP_B200_TEST_SRS", "") not in ("", "0")
+            if not opted:
+                raise native.ZkpError(native.ZKP_ERR_IO,
+                                      f"SRS file {self.setup_path!r} (precompute {self.precompute_path!r}) not found.  Generate the "
+                                      f"files with `python -m zkp_subnet_b200.setup` or download the ceremony files; a throw-away "
+                                      f"SRS from a PUBLIC trapdoor is only generated when asked for explicitly "
+                                      f"(Client(test_srs=True) or ZKP_B200_TEST_SRS=1)")
+            print("zkp_b200: WARNING: using a TEST SRS generated from a PUBLIC trapdoor -- openings can be forged by anyone; "
+                  "never use this on a live network (nothing is written to setup_path)", file=sys.stderr, flush=True)
+        if self.multi_gpu == "split" and len(self.devices) > 1:
+            self._mg = native.MultiContext(self.devices)
+            if source is None:
+                self._mg.srs_generate(TEST_TAU_X, TEST_TAU_Y, log_n, self.machines_scale, native.LAYOUT_POINT_RANGE)
+            else:
+                srsfile.load_into_multi(self._mg, source, log_n, self.machines_scale, native.LAYOUT_POINT_RANGE)
+            if self.precompute == "eager":
+                self._mg.prebuild_tables()
+            roots = [self._mg.ctx(0)]  # verify / fft / eval / rng run on device 0
         else:
-            self._ctx.srs_generate(TEST_TAU_X, TEST_TAU_Y, log_n, self.machines_scale)
-            if path:
-                self._ctx.srs_save(path)
+            roots = []
+            for dev in self.devices:
+                ctx = native.Context(dev)
+                roots.append(ctx)
+                if source is None:
+                    ctx.srs_generate(TEST_TAU_X, TEST_TAU_Y, log_n, self.machines_scale)
+                else:
+                    srsfile.load_into(ctx, source)
+                    if ctx.srs_shape() != (log_n, self.machines_scale):
+                        raise native.ZkpError(native.ZKP_ERR_STATE, f"SRS files hold shape {ctx.srs_shape()}, "
+                                              f"expected {(log_n, self.machines_scale)}")
+                if self.precompute == "eager":
+                    ctx.prebuild_tables()
+        self.srs_source = "test-trapdoor" if source is None else f"file:{source.kind}"
+        self._roots = roots
+        for ctx in roots:
+            ctx.set_poly_form(self.poly_form == "coeffs")
+        for ctx in roots:
+            self._add_slot(ctx)
+            for _ in range(self.contexts - 1):
+                self._add_slot(ctx.fork())
+
+    def _add_slot(self, ctx) -> None:
+        s = _Slot(ctx)
+        self._slots.append(s)
+        self._free.put(s)
 
     def attach(self, ctx: native.Context, scale: int, machines_scale: int) -> "Client":
         """Use an existing context (its SRS already resident) instead of start(); for benchmarks and tests that
         share one GPU context between the raw C-ABI calls and this wire-level shim."""
-        self._ctx, self.scale, self.machines_scale = ctx, int(scale), int(machines_scale)
+        self.scale, self.machines_scale = int(scale), int(machines_scale)
         self._attached = True
+        self._roots = [ctx]
+        self._add_slot(ctx)
         return self
 
     def stop(self) -> None:
-        if getattr(self, "_attached", False):
-            self._ctx = None
-        self._resident_n = 0
-        for name in ("_staging", "_staging_alt"):
-            if getattr(self, name) is not None:
-                getattr(self, name).close()
-                setattr(self, name, None)
-        if self._ctx is not None:
-            self._ctx.close()
-            self._ctx = None
+        slots, self._slots = self._slots, []
+        self._free = queue.LifoQueue()
+        roots = set(id(r) for r in self._roots)
+        # forks first, then the contexts that own the SRS
+        for s in slots:
+            if id(s.ctx) not in roots:
+                s.close()
+        for s in slots:
+            if s.ctx is not None:
+                s.close(close_ctx=not self._attached)
+        self._roots = []
+        if self._mg is not None:
+            self._mg.close()
+            self._mg = None
 
-    def _decode(self, poly: Sequence[str]):
-        """Decode a wire polynomial into the client's page-locked staging buffer (grown on demand)."""
-        need = 32 * len(poly)
-        self._resident_n = 0  # the staging buffer is about to change
-        if need == 0:
-            return b""
-        if self._staging is None or self._staging.capacity < need:
-            if self._staging is not None:
-                self._staging.close()
-            self._staging = native.PinnedBuffer(max(need, 32 << (self.scale - self.machines_scale)))
-        return decode_poly(poly, self._staging)
+    # ---- pool
+    class _Lease:
+        def __init__(self, client: "Client"):
+            self.client = client
+            self.slot: Optional[_Slot] = None
+
+        def __enter__(self) -> _Slot:
+            c = self.client
+            if not c._slots:
+                raise native.ZkpError(native.ZKP_ERR_STATE, "Client.start() has not been called")
+            self.slot = c._free.get()
+            return self.slot
+
+        def __exit__(self, *exc) -> bool:
+            self.client._free.put(self.slot)
+            return False
+
+    def _lease(self) -> "Client._Lease":
+        return Client._Lease(self)
 
     def _need(self) -> native.Context:
-        if self._ctx is None:
+        if not self._roots:
             raise native.ZkpError(native.ZKP_ERR_STATE, "Client.start() has not been called")
-        return self._ctx
+        return self._roots[0]
+
+    def _row(self, i: int) -> int:
+        i = int(i)
+        if self.row_order == "bitrev" and self.machines_scale:
+            if not 0 <= i < (1 << self.machines_scale):
+                raise ValueError("worker index out of range")
+            return _bitrev(i, self.machines_scale)
+        return i
+
+    def _decode(self, slot: _Slot, poly: Sequence[str]):
+        """Decode a wire polynomial into the slot's page-locked staging buffer (grown on demand)."""
+        need = 32 * len(poly)
+        slot.resident_n = 0  # the staging buffer is about to change
+        if need == 0:
+            return b""
+        if slot.staging is None or slot.staging.capacity < need:
+            if slot.staging is not None:
+                slot.staging.close()
+            slot.staging = native.PinnedBuffer(max(need, 32 << (self.scale - self.machines_scale)))
+        return decode_poly(poly, slot.staging)
+
+    @staticmethod
+    def _mark_resident(slot: _Slot, n: int) -> None:
+        try:
+            gen, rn = slot.ctx.resident_generation()
+        except native.ZkpError:
+            gen, rn = -1, 0
+        slot.resident_n, slot.resident_gen = (n, gen) if rn == n else (0, -1)
 
     @staticmethod
     def _fail(e: Exception) -> Response:
@@ -161,45 +317,60 @@ class Client:
         return Response(code, {"error": str(e)})
 
     def _next_seed(self) -> int:
-        self._counter += 1
-        return (self._seed + 0x9E3779B97F4A7C15 * self._counter) & 0xFFFFFFFFFFFFFFFF
+        with self._counter_lock:
+            self._counter += 1
+            return (self._seed + 0x9E3779B97F4A7C15 * self._counter) & 0xFFFFFFFFFFFFFFFF
 
     # ---- prover calls
     def worker_commit(self, i: int, poly: Sequence[str]) -> Response:
         try:
-            with self._lock:
-                com = self._need().worker_commit(int(i), self._decode(poly))
-                self._resident_n = len(poly)
+            row = self._row(i)
+            with self._lease() as slot:
+                buf = self._decode(slot, poly)
+                if self._mg is not None:
+                    with self._mg_lock:
+                        com = self._mg.msm_g1(row, buf)
+                else:
+                    com = slot.ctx.worker_commit(row, buf)
+                    self._mark_resident(slot, len(poly))
             return Response(200, {"commitment": _b64_point(com)})
         except (ValueError, native.ZkpError) as e:
             return self._fail(e)
 
     def worker_open(self, i: int, poly: Sequence[str], x: str) -> Response:
         try:
-            with self._lock:
-                y, proof = self._open_locked(int(i), poly, _decode_any(x, 32))
+            row, xb = self._row(i), _decode_any(x, 32)
+            with self._lease() as slot:
+                if self._mg is not None:
+                    buf = self._decode(slot, poly)
+                    with self._mg_lock:
+                        _, y, proof = self._mg.commit_open(row, buf, xb)
+                else:
+                    y, proof = self._open_on(slot, row, poly, xb)
             return Response(200, {"eval": _b64_fr(y), "proof": _b64_point(proof)})
         except (ValueError, TypeError, native.ZkpError) as e:
             return self._fail(e)
 
-    def _open_locked(self, i: int, poly: Sequence[str], xb: bytes):
+    def _open_on(self, slot: _Slot, i: int, poly: Sequence[str], xb: bytes):
         """worker_open.  The reference miner calls worker_commit(i, poly) and then worker_open(i, poly, x) with the
-        same list (neurons/miner.py:56-61), i.e. it ships the polynomial twice.  When a polynomial of the same length
-        is still resident on the GPU, the opening of THAT polynomial starts at once while a helper thread decodes
-        the list that was actually given into the second staging buffer and compares it, element by element, with
-        the bytes of the resident one.  Equal (the reference flow): the result is already on its way
-        and neither the decode nor a second upload is on the critical path.  Different: the speculative result is
-        dropped and the regular path runs on the freshly decoded bytes."""
-        ctx = self._need()
+        same list (neurons/miner.py:56-61), i.e. it ships the polynomial twice.  When the polynomial THIS slot uploaded
+        last is still resident on the GPU, its opening starts at once while a helper thread decodes the list that
+        was actually given into the second staging buffer and compares it, element by element, with the bytes of the
+        resident one.  Equal (the reference flow): the result is already on its way and neither the decode nor a
+        second upload is on the critical path.  Different: the speculative result is dropped and the regular path
+        runs on the freshly decoded bytes.  The speculative call names the upload by its generation
+        (zkp_worker_open_resident_gen): if anything else -- another client of a shared context, a raw call -- has
+        rewritten the staged polynomial since, the library refuses and the regular path runs."""
+        ctx = slot.ctx
         n = len(poly)
-        if not (n and self._resident_n == n and self._staging is not None):
-            y, proof = ctx.worker_open(i, self._decode(poly), xb)
-            self._resident_n = n
+        if not (n and slot.resident_n == n and slot.staging is not None):
+            y, proof = ctx.worker_open(i, self._decode(slot, poly), xb)
+            self._mark_resident(slot, n)
             return y, proof
-        if self._staging_alt is None or self._staging_alt.capacity < 32 * n:
-            if self._staging_alt is not None:
-                self._staging_alt.close()
-            self._staging_alt = native.PinnedBuffer(max(32 * n, self._staging.capacity))
+        if slot.staging_alt is None or slot.staging_alt.capacity < 32 * n:
+            if slot.staging_alt is not None:
+                slot.staging_alt.close()
+            slot.staging_alt = native.PinnedBuffer(max(32 * n, slot.staging.capacity))
         # The list is decoded on a helper thread and the GPU call is made from THIS thread: the decoder keeps the
         # GIL for its whole call (ctypes.PyDLL), the prover call releases it (ctypes.CDLL), so the helper gets
         # going the moment this thread is inside the library.  The helper waits for `go`, which is set right before
@@ -211,7 +382,7 @@ class Client:
         def run():
             go.wait()
             try:
-                dec["ok"] = native.wire_decode_list(poly, self._staging_alt, same_as=self._staging)
+                dec["ok"] = native.wire_decode_list(poly, slot.staging_alt, same_as=slot.staging)
             except Exception as e:
                 dec["err"] = e
 
@@ -220,8 +391,8 @@ class Client:
         spec = err = None
         try:
             go.set()
-            spec = ctx.worker_open_resident(i, n, xb)
-        except native.ZkpError as e:  # resident polynomial dropped by another call on a shared context, bad x, ...
+            spec = ctx.worker_open_resident_gen(i, n, slot.resident_gen, xb)
+        except native.ZkpError as e:  # resident polynomial replaced by another call on a shared context, bad x, ...
             err = e
         finally:
             go.set()
@@ -234,19 +405,69 @@ class Client:
         if same and err is not None and err.code != native.ZKP_ERR_STATE:
             raise err
         # not the resident polynomial: the new bytes become the staged ones
-        self._resident_n = 0
-        self._staging, self._staging_alt = self._staging_alt, self._staging
+        slot.resident_n = 0
+        slot.staging, slot.staging_alt = slot.staging_alt, slot.staging
         y, proof = ctx.worker_open(i, buf, xb)
-        self._resident_n = n
+        self._mark_resident(slot, n)
         return y, proof
 
     def worker_commit_and_open(self, i: int, poly: Sequence[str], x: str) -> Response:
         """Fused form of the reference's rpc_commit_and_open (neurons/miner.py:56-61): one decode, one upload."""
         try:
-            with self._lock:
-                com, y, proof = self._need().worker_commit_open(int(i), self._decode(poly), _decode_any(x, 32))
-                self._resident_n = len(poly)
+            row, xb = self._row(i), _decode_any(x, 32)
+            with self._lease() as slot:
+                buf = self._decode(slot, poly)
+                if self._mg is not None:
+                    with self._mg_lock:
+                        com, y, proof = self._mg.commit_open(row, buf, xb)
+                else:
+                    com, y, proof = slot.ctx.worker_commit_open(row, buf, xb)
+                    self._mark_resident(slot, len(poly))
             return Response(200, {"commitment": _b64_point(com), "eval": _b64_fr(y), "proof": _b64_point(proof)})
+        except (ValueError, TypeError, native.ZkpError) as e:
+            return self._fail(e)
+
+    def worker_commit_and_open_batch(self, items: Sequence[Dict[str, Any]]) -> Response:
+        """Several requests ({"i", "poly", "alpha"}) in ONE launch set (zkp_worker_commit_open_batch): what a miner
+        serving several validators at once wants at the mainnet row size.  Answers {"results": [...]} with one
+        {"commitment", "eval", "proof"} or {"error"} per item, in order.  Not part of the reference's Client."""
+        try:
+            if self._mg is not None:
+                raise native.ZkpError(native.ZKP_ERR_STATE, "batches are not available with multi_gpu='split'")
+            with self._lease() as slot:
+                slot.resident_n = 0
+                rows, bufs, xs, errs = [], [], [], {}
+                n = 1 << (self.scale - self.machines_scale)
+                stage = native.PinnedBuffer(32 * n * max(1, len(items)))
+                try:
+                    for k, it in enumerate(items):
+                        try:
+                            if len(it["poly"]) != n:
+                                raise ValueError(f"polynomial must have {n} elements")
+                            raw = native.wire_decode_list(it["poly"])
+                            xb = _decode_any(it["alpha"], 32)
+                            row = self._row(it["i"])
+                        except (ValueError, TypeError, KeyError) as e:
+                            errs[k] = str(e)
+                            continue
+                        stage.write(raw, 32 * n * len(rows))
+                        rows.append(row)
+                        xs.append(xb)
+                        bufs.append(k)
+                    out = []
+                    if rows:
+                        views = [(ctypes_view(stage, 32 * n * j, 32 * n)) for j in range(len(rows))]
+                        out = slot.ctx.worker_commit_open_batch(rows, views, b"".join(xs))
+                finally:
+                    stage.close()
+                results: List[Dict[str, Any]] = [None] * len(items)  # type: ignore
+                for j, k in enumerate(bufs):
+                    st, com, y, proof = out[j]
+                    results[k] = ({"commitment": _b64_point(com), "eval": _b64_fr(y), "proof": _b64_point(proof)} if st == 0
+                                  else {"error": f"zkp_b200 error {st}: malformed field element"})
+                for k, msg in errs.items():
+                    results[k] = {"error": msg}
+            return Response(200, {"results": results})
         except (ValueError, TypeError, native.ZkpError) as e:
             return self._fail(e)
 
@@ -258,8 +479,8 @@ class Client:
         except (ValueError, TypeError):
             return Response(200, {"valid": False})
         try:
-            return Response(200, {"valid": self._need().worker_verify(int(i), *args)})
-        except native.ZkpError as e:
+            return Response(200, {"valid": self._need().worker_verify(self._row(i), *args)})
+        except (ValueError, native.ZkpError) as e:
             return self._fail(e)
 
     def worker_verify_batch(self, items: Sequence[Dict[str, Any]], alpha: str) -> Response:
@@ -270,7 +491,7 @@ class Client:
             zero48, zero32 = b"\xff" * 48, b"\xff" * 32  # placeholders that fail to decode -> valid = False
             idx, proofs, evals, coms = [], [], [], []
             for it in items:
-                idx.append(int(it["i"]))
+                idx.append(self._row(it["i"]))
                 try:
                     p, e, c = _decode_any(it["proof"], 48), _decode_any(it["eval"], 32), _decode_any(it["commitment"], 48)
                 except (ValueError, TypeError, KeyError):
@@ -283,25 +504,35 @@ class Client:
             if not idx:
                 return Response(200, {"valid": []})
             return Response(200, {"valid": self._need().worker_verify_batch(idx, b"".join(proofs), a, b"".join(evals), b"".join(coms))})
-        except native.ZkpError as e:
+        except (ValueError, native.ZkpError) as e:
             return self._fail(e)
 
     # ---- Pianist master node.  Not part of the reference's Client yet ("multi-miner proofs ... not yet
     #      implemented", reference neurons/validator.py:198; roadmap README.md:38); named after the worker_* calls.
+    #      The points come from OTHER parties (the workers), so every one is subgroup-checked before it is added.
     def master_commit(self, commitments: Sequence[str]) -> Response:
         """com = sum_i com_i over the workers' commitments."""
         try:
             raw = b"".join(_decode_any(c, 48) for c in commitments)
-            return Response(200, {"commitment": _b64_point(native.g1_sum(raw))})
+            return Response(200, {"commitment": _b64_point(native.g1_sum_checked(raw))})
         except (ValueError, TypeError, native.ZkpError) as e:
             return self._fail(e)
+
+    def _worker_order(self, vals: Sequence[str]) -> List[str]:
+        """values indexed by worker -> indexed by SRS row (identity in natural order)"""
+        if self.row_order != "bitrev":
+            return list(vals)
+        out: List[Any] = [None] * len(vals)
+        for i, v in enumerate(vals):
+            out[self._row(i)] = v
+        return out
 
     def master_open(self, evals: Sequence[str], proofs: Sequence[str], beta: str) -> Response:
         """From the workers' (eval, proof) answers at a common alpha: pi_X = sum_i pi_i, z = f(alpha, beta) and the
         Y-direction proof pi_Y."""
         try:
-            pix = native.g1_sum(b"".join(_decode_any(p, 48) for p in proofs))
-            z, piy = self._need().master_open_y(b"".join(_decode_any(e, 32) for e in evals), _decode_any(beta, 32))
+            pix = native.g1_sum_checked(b"".join(_decode_any(p, 48) for p in proofs))
+            z, piy = self._need().master_open_y(b"".join(_decode_any(e, 32) for e in self._worker_order(evals)), _decode_any(beta, 32))
             return Response(200, {"eval": _b64_fr(z), "proof_x": _b64_point(pix), "proof_y": _b64_point(piy)})
         except (ValueError, TypeError, native.ZkpError) as e:
             return self._fail(e)
@@ -319,16 +550,16 @@ class Client:
 
     def fft(self, poly: Sequence[str], left: bool = True, inverse: bool = False) -> Response:
         try:
-            with self._lock:
-                out = self._need().fft(self._decode(poly), bool(left), bool(inverse))
+            with self._lease() as slot:
+                out = slot.ctx.fft(self._decode(slot, poly), bool(left), bool(inverse))
             return Response(200, {"poly": encode_poly(out)})
         except (ValueError, native.ZkpError) as e:
             return self._fail(e)
 
     def eval(self, poly: Sequence[str], x: str) -> Response:
         try:
-            with self._lock:
-                y = self._need().eval(self._decode(poly), _decode_any(x, 32))
+            with self._lease() as slot:
+                y = slot.ctx.eval(self._decode(slot, poly), _decode_any(x, 32))
             return Response(200, {"y": _b64_fr(y)})
         except (ValueError, TypeError, native.ZkpError) as e:
             return self._fail(e)
@@ -340,9 +571,9 @@ class Client:
             rows = len(polys)
             if rows == 0 or any(len(p) != len(polys[0]) for p in polys):
                 raise ValueError("rows of equal, non-zero length expected")
-            with self._lock:
+            with self._lease() as slot:
                 flat = [s for p in polys for s in p]
-                raw = self._need().challenge_evals(self._decode(flat), rows, _decode_any(x, 32))
+                raw = slot.ctx.challenge_evals(self._decode(slot, flat), rows, _decode_any(x, 32))
             return Response(200, {"evals": [_b64_fr(raw[32 * i:32 * i + 32]) for i in range(rows)]})
         except (ValueError, TypeError, native.ZkpError) as e:
             return self._fail(e)
@@ -351,9 +582,10 @@ class Client:
         """Random bivariate polynomial as 2^machines_scale rows of 2^(scale-machines_scale) evaluations
         (reference neurons/validator.py:67-75)."""
         try:
-            ctx = self._need()
             rows, n = 1 << self.machines_scale, 1 << (self.scale - self.machines_scale)
-            raw = ctx.random_poly(self._next_seed(), rows * n)
+            with self._lease() as slot:
+                slot.resident_n = 0
+                raw = slot.ctx.random_poly(self._next_seed(), rows * n)
             flat = encode_poly(raw)
             return Response(200, {"poly": [flat[r * n:(r + 1) * n] for r in range(rows)]})
         except native.ZkpError as e:
@@ -361,6 +593,14 @@ class Client:
 
     def random_point(self) -> Response:
         try:
-            return Response(200, {"point": _b64_fr(self._need().random_point(self._next_seed()))})
+            with self._lease() as slot:
+                slot.resident_n = 0
+                return Response(200, {"point": _b64_fr(slot.ctx.random_point(self._next_seed()))})
         except native.ZkpError as e:
             return self._fail(e)
+
+
+def ctypes_view(buf: native.PinnedBuffer, offset: int, nbytes: int):
+    """a ctypes char array over a slice of a page-locked buffer (no copy)"""
+    import ctypes
+    return (ctypes.c_char * nbytes).from_address(ctypes.addressof(buf.buf) + offset)

@@ -3,6 +3,7 @@
 #pragma once
 #include <chrono>
 #include <random>
+#include <thread>
 
 namespace {
 
@@ -28,6 +29,8 @@ Fr to_dev(const Fr64& a) {
 int get_domain(zkp_ctx* ctx, uint32_t log_n, bool need_tw, zkp_ctx::Domain** out) {
     if (log_n >= ctx->domains.size()) return fail(ZKP_ERR_ARG, "domain too large");
     zkp_ctx::Domain& d = ctx->domains[log_n];
+    if (d.ready && (!need_tw || d.have_tw || log_n < 1)) { *out = &d; return ZKP_OK; }  // tables are immutable once built
+    std::lock_guard<std::recursive_mutex> lk(ctx->S.mu);  // shared with the forks of this context
     if (!d.ready) {
         d.w = fr_root_of_unity(log_n);
         d.w_inv = d.w.inverse();
@@ -46,14 +49,14 @@ int get_domain(zkp_ctx* ctx, uint32_t log_n, bool need_tw, zkp_ctx::Domain** out
         uint32_t threads = (half + 15) / 16;
         k_build_twiddles<<<(threads + 127) / 128, 128, 0, ctx->stream>>>(d.tw.as<Fr>(), half, d.wt.as<Fr>());
         ctx->launches++;
+        ZKP_CUDA(cudaStreamSynchronize(ctx->stream));  // other contexts of the store use the table from their own streams
         d.have_tw = true;
     }
     *out = &d;
     return ZKP_OK;
 }
 
-// small device scratch layout (ctx->small): [0] bad flag, [4] hit, [32] y, [64] s1, [96] s2, [128] eval
-constexpr size_t SM_BAD = 0, SM_HIT = 4, SM_Y = 32, SM_S1 = 64, SM_S2 = 96, SM_EVAL = 128, SM_BYTES = 256;
+// small device scratch layout (ctx->small): one request record, see kzg.cuh (SM_BAD, SM_HIT, SM_Y, SM_S1, SM_S2, SM_EVAL)
 
 int ensure_small(zkp_ctx* ctx) {
     ZKP_CUDA(ctx->small.ensure(SM_BYTES));
@@ -61,48 +64,61 @@ int ensure_small(zkp_ctx* ctx) {
 }
 template <class T> T* small_at(zkp_ctx* ctx, size_t off) { return reinterpret_cast<T*>(ctx->small.as<uint8_t>() + off); }
 
-// ---- opening on device: f (Montgomery, n elements) -> y (device, SM_Y) and q (Montgomery, fr_c)
-int open_device(zkp_ctx* ctx, cudaStream_t st, const Fr* d_f, uint32_t n, const Fr64& x) {
+// ---- opening on device: `count` polynomials f (Montgomery, n elements each, back to back) -> per request y (record
+// r of `records`, offset SM_Y) and q (Montgomery, fr_c).  Evaluation points: x by value (count == 1) or d_xs[r].
+int open_buffers(zkp_ctx* ctx, uint32_t n, uint32_t count) {
+    ZKP_CUDA(ctx->fr_b.ensure((size_t)n * count * 32));
+    ZKP_CUDA(ctx->fr_c.ensure((size_t)n * count * 32));
+    return ZKP_OK;
+}
+int open_device(zkp_ctx* ctx, cudaStream_t st, const Fr* d_f, uint32_t n, const Fr64& x, uint32_t count = 1, const Fr* d_xs = nullptr,
+                uint8_t* records = nullptr) {
     uint32_t log_n = ilog2(n);
     zkp_ctx::Domain* dom;
     int rc = get_domain(ctx, log_n, false, &dom);
     if (rc) return rc;
-    ZKP_CUDA(ctx->fr_b.ensure((size_t)n * 32));
-    ZKP_CUDA(ctx->fr_c.ensure((size_t)n * 32));
+    rc = open_buffers(ctx, n, count);
+    if (rc) return rc;
+    if (!records) records = ctx->small.as<uint8_t>();
+    auto rec = [&](size_t off) { return records + off; };
     // elements per thread: with one inversion per BLOCK (k_open_pass1) short runs cost nothing extra
     uint32_t E = n >> 16;
     if (E < 4) E = 4;
     if (E > 16) E = 16;
     uint32_t threads = (n + E - 1) / E, blocks = (threads + 127) / 128;
     uint32_t blocks2 = (n + 255) / 256;
-    ZKP_CUDA(ctx->partials.ensure((size_t)(blocks > blocks2 ? blocks : blocks2) * 32));
-    ZKP_CUDA(cudaMemsetAsync(small_at<uint32_t>(ctx, SM_HIT), 0xff, 4, st));
-    k_open_pass1<<<blocks, 128, 0, st>>>(d_f, n, E, to_dev(x), dom->wt.as<Fr>(), to_dev(dom->w_inv), ctx->fr_b.as<Fr>(),
-                                         ctx->partials.as<Fr>(), small_at<uint32_t>(ctx, SM_HIT), 0);
+    ZKP_CUDA(ctx->partials.ensure((size_t)(blocks > blocks2 ? blocks : blocks2) * count * 32));
+    uint32_t* hit = reinterpret_cast<uint32_t*>(rec(SM_HIT));
+    if (count == 1) ZKP_CUDA(cudaMemsetAsync(hit, 0xff, 4, st));  // a batch initialises its records itself (k_batch_init)
+    k_open_pass1<<<dim3(blocks, count), 128, 0, st>>>(d_f, n, E, to_dev(x), dom->wt.as<Fr>(), to_dev(dom->w_inv), ctx->fr_b.as<Fr>(),
+                                                      ctx->partials.as<Fr>(), hit, 0, d_xs);
     trace_mark(ctx, 1, st, "open_pass1");
-    k_fr_reduce<<<1, 256, 0, st>>>(ctx->partials.as<Fr>(), blocks, small_at<Fr>(ctx, SM_S1));
-    k_open_y<<<1, 32, 0, st>>>(d_f, log_n, to_dev(x), to_dev(dom->n_inv), small_at<Fr>(ctx, SM_S1), small_at<uint32_t>(ctx, SM_HIT),
-                               small_at<Fr>(ctx, SM_Y));
+    k_fr_reduce<<<dim3(1, count), 256, 0, st>>>(ctx->partials.as<Fr>(), blocks, reinterpret_cast<Fr*>(rec(SM_S1)));
+    k_open_y<<<dim3(1, count), 32, 0, st>>>(d_f, log_n, to_dev(x), to_dev(dom->n_inv), reinterpret_cast<Fr*>(rec(SM_S1)), hit,
+                                            reinterpret_cast<Fr*>(rec(SM_Y)), d_xs, n);
     trace_mark(ctx, 1, st, "open_y");
-    k_open_pass2<<<blocks2, 256, 0, st>>>(d_f, ctx->fr_b.as<Fr>(), n, small_at<Fr>(ctx, SM_Y), ctx->fr_c.as<Fr>());
+    k_open_pass2<<<dim3(blocks2, count), 256, 0, st>>>(d_f, ctx->fr_b.as<Fr>(), n, reinterpret_cast<Fr*>(rec(SM_Y)), ctx->fr_c.as<Fr>());
     trace_mark(ctx, 1, st, "open_pass2");
     // x in the domain (rare): q_m = -sum_{j != m} q_j w^(j-m); the kernels are no-ops otherwise
-    k_open_fix_partial<<<blocks2, 256, 0, st>>>(ctx->fr_c.as<Fr>(), n, dom->wt.as<Fr>(), small_at<uint32_t>(ctx, SM_HIT),
-                                                ctx->partials.as<Fr>());
-    k_fr_reduce<<<1, 256, 0, st>>>(ctx->partials.as<Fr>(), blocks2, small_at<Fr>(ctx, SM_S2));
-    k_open_fix_apply<<<1, 32, 0, st>>>(ctx->fr_c.as<Fr>(), small_at<uint32_t>(ctx, SM_HIT), small_at<Fr>(ctx, SM_S2));
+    k_open_fix_partial<<<dim3(blocks2, count), 256, 0, st>>>(ctx->fr_c.as<Fr>(), n, dom->wt.as<Fr>(), hit, ctx->partials.as<Fr>());
+    k_fr_reduce<<<dim3(1, count), 256, 0, st>>>(ctx->partials.as<Fr>(), blocks2, reinterpret_cast<Fr*>(rec(SM_S2)));
+    k_open_fix_apply<<<dim3(1, count), 32, 0, st>>>(ctx->fr_c.as<Fr>(), hit, reinterpret_cast<Fr*>(rec(SM_S2)), n);
     ctx->launches += 7;
+    ZKP_CUDA(cudaGetLastError());
     return ZKP_OK;
 }
 
 // upload poly (big-endian), convert to Montgomery in fr_a; leaves the raw bytes in ctx->scalars
 int convert_poly(zkp_ctx* ctx, size_t n);
+int ntt_device(zkp_ctx* ctx, const Fr* in, Fr* out, uint32_t log_n, int inverse);
 int upload_poly(zkp_ctx* ctx, const uint8_t* poly_be, size_t n) {
     int rc = upload_scalars(ctx, poly_be, n, ctx->scalars);
     if (rc) return rc;
     return convert_poly(ctx, n);
 }
-// raw big-endian bytes in ctx->scalars -> Montgomery form in fr_a (flags non-canonical elements)
+// raw big-endian bytes in ctx->scalars -> Montgomery form in fr_a (flags non-canonical elements).  With
+// zkp_set_poly_form(ctx, 1) the bytes are COEFFICIENTS and fr_a receives their evaluations (one forward NTT): everything
+// downstream works on evaluations either way.
 int convert_poly(zkp_ctx* ctx, size_t n) {
     int rc = ensure_small(ctx);
     if (rc) return rc;
@@ -111,7 +127,16 @@ int convert_poly(zkp_ctx* ctx, size_t n) {
     k_fr_from_be<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(ctx->scalars.as<uint32_t>(), n, ctx->fr_a.as<Fr>(),
                                                                        small_at<uint32_t>(ctx, SM_BAD));
     ctx->launches++;
+    if (ctx->coeff_form) {
+        if (!is_pow2(n)) return fail(ZKP_ERR_ARG, "a polynomial in coefficient form must have a power-of-two length");
+        return ntt_device(ctx, ctx->fr_a.as<Fr>(), ctx->fr_a.as<Fr>(), ilog2(n), 0);
+    }
     return ZKP_OK;
+}
+// the scalars of the commitment MSM: the raw bytes as uploaded (evaluation form) or the NTT output (coefficient form)
+const uint32_t* commit_scalars(zkp_ctx* ctx, int* fmt) {
+    *fmt = ctx->coeff_form ? SCALAR_MONT : SCALAR_BE;
+    return ctx->coeff_form ? ctx->fr_a.as<uint32_t>() : ctx->scalars.as<uint32_t>();
 }
 
 // read back y (big-endian) and the bad-encoding flag
@@ -146,11 +171,78 @@ int open_checks(zkp_ctx* ctx, uint32_t i, const void* poly, size_t n, const uint
 }
 
 // The full device part of commit (optional) + open with the polynomial already resident (raw bytes in
-// ctx->scalars, Montgomery form in fr_a, both produced on lane 0).  The commitment MSM runs on lane 0, the
-// opening (field kernels + its MSM) on lane 1; the host folds the commitment while lane 1 is still busy.
+// ctx->scalars, Montgomery form in fr_a, both produced on lane 0).
+//
+// Two shapes, same bytes out:
+//  * two lanes (large n): the commitment MSM runs on lane 0, the opening (field kernels + its MSM) on lane 1; the host
+//    folds the commitment while lane 1 is still busy.  Each accumulation fills the machine for milliseconds, and what
+//    the second stream buys is the tail of one MSM hidden under the accumulation of the other.
+//  * fused (small n; zkp_set_fuse): the two MSMs are two GROUPS of one launch set -- one sort, one accumulation grid,
+//    one chain of slot levels, one row/column reduction, one bit-plane launch, one read-back.  At the mainnet row size
+//    (2^16) half of a lone MSM is latency-bound tail (ten dependent slot levels, reduction launches over few buckets),
+//    and a commit+open pays for that tail once instead of twice.  The commitment's digits are counted on lane 0 while
+//    the opening's field kernels (which produce the scalars of the proof group) run on lane 1.
+bool fuse_wanted(zkp_ctx* ctx, size_t n) {
+    if (ctx->fuse_mode >= 0) return ctx->fuse_mode != 0;
+    return n <= ((size_t)1 << ZKP_FUSE_MAX_LOG);
+}
+int commit_open_fused(zkp_ctx* ctx, uint32_t i, size_t n, const Fr64& x, uint8_t* commitment48, uint8_t eval_be[32], uint8_t proof48[48],
+                      host::G1J* com_jac, host::G1J* proof_jac, bool* done) {
+    *done = false;
+    cudaStream_t s0 = ctx->stream, s1 = ctx->stream2;
+    int rc = open_buffers(ctx, (uint32_t)n, 1);
+    if (rc) return rc;
+    int cfmt;
+    const uint32_t* csc = commit_scalars(ctx, &cfmt);
+    MsmJob jobs[2] = {{i, csc, cfmt}, {i, ctx->fr_c.as<uint32_t>(), SCALAR_MONT}};
+    MsmPlan plan;
+    MsmGroups gs;
+    const G1Affine* pts = nullptr;
+    bool grouped = false;
+    rc = msm_plan_jobs(ctx, jobs, 2, n, &plan, &gs, &pts, &grouped);
+    if (rc) return rc;
+    if (!grouped) return ZKP_OK;  // no tables: the caller takes the two-lane path
+    *done = true;
+    ZKP_CUDA(cudaEventRecord(ctx->ev_ready, s0));
+    ZKP_CUDA(cudaStreamWaitEvent(s1, ctx->ev_ready, 0));
+    rc = msm_prep_begin(ctx, 0, plan);
+    if (!rc) rc = msm_prep_count(ctx, 0, plan, gs, 0, 1);
+    trace_mark(ctx, 1, s1, "open_begin");
+    if (!rc) rc = open_device(ctx, s1, ctx->fr_a.as<Fr>(), (uint32_t)n, x);
+    trace_mark(ctx, 1, s1, "open_field_kernels");
+    if (!rc) {
+        ZKP_CUDA(cudaEventRecord(ctx->ev_join, s1));
+        ZKP_CUDA(cudaStreamWaitEvent(s0, ctx->ev_join, 0));
+        rc = msm_prep_count(ctx, 0, plan, gs, 1, 1);
+    }
+    if (!rc) rc = msm_prep_finish(ctx, 0, plan, gs);
+    if (!rc) rc = msm_enqueue_main(ctx, 0, plan, pts);
+    if (!rc) rc = fetch_y_enqueue(ctx, s0);
+    if (!rc) rc = msm_wait(ctx, 0, 2);
+    else { cudaStreamSynchronize(s0); cudaStreamSynchronize(s1); }
+    msm_unpin_all(ctx);
+    if (rc) return rc;
+    const G1Xyzz* hw = ctx->ws.h_window;
+    host::G1J c = msm_fold_group(plan, hw, 0), p = msm_fold_group(plan, hw, 1);
+    if (commitment48) host::g1_compress(commitment48, c);
+    if (proof48) host::g1_compress(proof48, p);
+    if (com_jac) *com_jac = c;
+    if (proof_jac) *proof_jac = p;
+    ctx->last_com = c;
+    ctx->last_proof = p;
+    ctx->have_last = true;
+    return fetch_y_finish(ctx, eval_be);
+}
+
 int commit_open_resident(zkp_ctx* ctx, uint32_t i, size_t n, const Fr64& x, uint8_t* commitment48, uint8_t eval_be[32],
-                         uint8_t proof48[48]) {
+                         uint8_t proof48[48], host::G1J* com_jac = nullptr, host::G1J* proof_jac = nullptr) {
     int rc;
+    const bool want_com = commitment48 || com_jac;
+    if (want_com && fuse_wanted(ctx, n) && tables_wanted(ctx, n)) {
+        bool done = false;
+        rc = commit_open_fused(ctx, i, n, x, commitment48, eval_be, proof48, com_jac, proof_jac, &done);
+        if (rc || done) return rc;
+    }
     MsmPlan plan_c, plan_o;
     cudaStream_t s0 = ctx->stream, s1 = ctx->stream2;
     ZKP_CUDA(cudaEventRecord(ctx->ev_ready, s0));
@@ -162,30 +254,45 @@ int commit_open_resident(zkp_ctx* ctx, uint32_t i, size_t n, const Fr64& x, uint
     // the front half of lane 1 and the reduction tail of lane 0 are real work; hiding them under an accumulation
     // slows that accumulation by about as much as running them in the open would cost.
     const G1Affine *pts_c = nullptr, *pts_o = nullptr;
-    if (commitment48) {
-        rc = msm_device_prep(ctx, 0, i, ctx->scalars.as<uint32_t>(), SCALAR_BE, n, &plan_c, &pts_c);
-        if (rc) return rc;
+    auto bail = [&](int code) {
+        cudaStreamSynchronize(s0);
+        cudaStreamSynchronize(s1);
+        msm_unpin_all(ctx);
+        return code;
+    };
+    if (want_com) {
+        int cfmt;
+        const uint32_t* csc = commit_scalars(ctx, &cfmt);
+        rc = msm_device_prep(ctx, 0, i, csc, cfmt, n, &plan_c, &pts_c);
+        if (rc) return bail(rc);
     }
     trace_mark(ctx, 1, s1, "open_begin");
     rc = open_device(ctx, s1, ctx->fr_a.as<Fr>(), (uint32_t)n, x);
-    if (rc) return rc;
+    if (rc) return bail(rc);
     trace_mark(ctx, 1, s1, "open_field_kernels");
     rc = msm_device_prep(ctx, 1, i, ctx->fr_c.as<uint32_t>(), SCALAR_MONT, n, &plan_o, &pts_o);
-    if (rc) return rc;
-    if (commitment48) {
+    if (rc) return bail(rc);
+    if (want_com) {
         rc = msm_enqueue_main(ctx, 0, plan_c, pts_c);
-        if (rc) return rc;
+        if (rc) return bail(rc);
     }
     rc = msm_enqueue_main(ctx, 1, plan_o, pts_o);
-    if (rc) return rc;
+    if (rc) return bail(rc);
     rc = fetch_y_enqueue(ctx, s1);
-    if (rc) return rc;
-    if (commitment48) {
-        rc = msm_device_finish(ctx, 0, plan_c, commitment48);
-        if (rc) { cudaStreamSynchronize(s1); return rc; }
+    if (rc) return bail(rc);
+    host::G1J cj = host::G1J::infinity(), pj;
+    if (want_com) {
+        rc = msm_device_finish(ctx, 0, plan_c, commitment48, &cj);
+        if (rc) return bail(rc);
     }
-    rc = msm_device_finish(ctx, 1, plan_o, proof48);
+    rc = msm_device_finish(ctx, 1, plan_o, proof48, &pj);
+    msm_unpin_all(ctx);
     if (rc) return rc;
+    if (com_jac) *com_jac = cj;
+    if (proof_jac) *proof_jac = pj;
+    ctx->last_com = cj;
+    ctx->last_proof = pj;
+    ctx->have_last = want_com;
     return fetch_y_finish(ctx, eval_be);
 }
 
@@ -417,7 +524,7 @@ int zkp_srs_generate_monomial(zkp_ctx* ctx, const uint8_t tau_x_be[32], uint32_t
     ZKP_CUDA(ctx->fr_c.ensure((size_t)n * 32));
     ZKP_CUDA(ctx->ws.buckets.ensure((size_t)n * sizeof(G1Xyzz)));
     ZKP_CUDA(ctx->ws.pool.ensure((size_t)n * sizeof(Fq)));
-    k_power_scalars<<<((n + 7) / 8 + 127) / 128, 128, 0, st>>>(ctx->partials.as<Fr>(), n, ctx->fr_c.as<Fr>());
+    k_power_scalars<<<((n + 7) / 8 + 127) / 128, 128, 0, st>>>(ctx->partials.as<Fr>(), n, ctx->fr_c.as<Fr>(), to_dev(Fr64::one()));
     k_fixed_base_mul<<<(n + 127) / 128, 128, 0, st>>>(ctx->fr_c.as<Fr>(), n, ctx->fixed_base.as<G1Affine>(), ctx->ws.buckets.as<G1Xyzz>());
     uint32_t EA = 16, ta = (n + EA - 1) / EA;
     k_xyzz_to_affine<<<(ta + 127) / 128, 128, 0, st>>>(ctx->ws.buckets.as<G1Xyzz>(), n, EA, ctx->ws.pool.as<Fq>(), ctx->srs.as<G1Affine>());
@@ -444,6 +551,22 @@ int zkp_g1_sum(const uint8_t* points48, size_t count, uint8_t out48[48]) {
     for (size_t k = 0; k < count; k++) {
         host::G1J p;
         if (!host::g1_decompress(p, points48 + 48 * k, false)) return fail(ZKP_ERR_ENCODING, "bad G1 point");
+        acc = acc.add(p);
+    }
+    host::g1_compress(out48, acc);
+    return ZKP_OK;
+}
+
+// The same sum for inputs that come from OTHER parties (Client.master_commit / master_open aggregate what workers sent):
+// every point is checked to lie in the prime-order subgroup before it enters the aggregate.  zkp_g1_sum stays the
+// unchecked variant for partials produced by this process.
+int zkp_g1_sum_checked(const uint8_t* points48, size_t count, uint8_t out48[48]) {
+    if (!points48 || !out48) return fail(ZKP_ERR_ARG, "null argument");
+    host::G1J acc = host::G1J::infinity();
+    for (size_t k = 0; k < count; k++) {
+        host::G1J p;
+        if (!host::g1_decompress(p, points48 + 48 * k, true))
+            return fail(ZKP_ERR_ENCODING, "point " + std::to_string(k) + " is malformed, off the curve or outside the subgroup");
         acc = acc.add(p);
     }
     host::g1_compress(out48, acc);
@@ -599,6 +722,43 @@ int zkp_worker_open_resident(zkp_ctx* ctx, uint32_t i, size_t n, const uint8_t x
     return commit_open_resident(ctx, i, n, x, nullptr, eval_be, proof48);
 }
 
+// The same, bound to ONE upload: `generation` is the value zkp_resident_generation returned right after the caller's
+// own zkp_worker_commit / zkp_worker_open / zkp_worker_commit_open.  Any later call that rewrites the staged scalars --
+// from another client of a shared context, another thread, a raw zkp_msm_g1 -- changes the generation, and this
+// entry then fails with ZKP_ERR_STATE instead of opening somebody else's polynomial.
+int zkp_worker_open_resident_gen(zkp_ctx* ctx, uint32_t i, size_t n, uint64_t generation, const uint8_t x_be[32], uint8_t eval_be[32],
+                                 uint8_t proof48[48]) {
+    Fr64 x;
+    int rc = open_checks(ctx, i, x_be /* any non-null pointer */, n, x_be, &x);
+    if (rc) return rc;
+    if (!eval_be || !proof48) return fail(ZKP_ERR_ARG, "null output");
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    DeviceGuard g(ctx->device);
+    if (ctx->resident_n != n || ctx->resident_gen != generation)
+        return fail(ZKP_ERR_STATE, "the polynomial of that upload is no longer resident on the device");
+    rc = convert_poly(ctx, n);
+    if (rc) return rc;
+    return commit_open_resident(ctx, i, n, x, nullptr, eval_be, proof48);
+}
+// The commitment and the proof of the last zkp_worker_commit_open / zkp_bench_commit_open on this context as 2 x 96
+// bytes ZCash-UNCOMPRESSED: what a rank of a multi-process job contributes to the cross-GPU sum, so that the combining
+// rank adds affine points (zkp_g1_sum_uncompressed) and nobody takes a square root.
+int zkp_last_points_uncompressed(zkp_ctx* ctx, uint8_t out192[192]) {
+    if (!ctx || !out192) return fail(ZKP_ERR_ARG, "null argument");
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    if (!ctx->have_last) return fail(ZKP_ERR_STATE, "no commit+open has completed on this context");
+    host::g1_serialize96(out192, ctx->last_com);
+    host::g1_serialize96(out192 + 96, ctx->last_proof);
+    return ZKP_OK;
+}
+int zkp_resident_generation(zkp_ctx* ctx, uint64_t* generation, size_t* n) {
+    if (!ctx || !generation) return fail(ZKP_ERR_ARG, "null argument");
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    *generation = ctx->resident_gen;
+    if (n) *n = ctx->resident_n;
+    return ZKP_OK;
+}
+
 int zkp_worker_commit_open(zkp_ctx* ctx, uint32_t i, const uint8_t* poly_be, size_t n, const uint8_t x_be[32],
                            uint8_t commitment48[48], uint8_t eval_be[32], uint8_t proof48[48]) {
     Fr64 x;
@@ -612,6 +772,170 @@ int zkp_worker_commit_open(zkp_ctx* ctx, uint32_t i, const uint8_t* poly_be, siz
     rc = commit_open_resident(ctx, i, n, x, commitment48, eval_be, proof48);
     if (rc == ZKP_OK) ctx->resident_n = n;
     return rc;
+}
+
+// ---------------------------------------------------------------------------------------------- batch
+// `count` independent commit+open requests of one row length in ONE launch set (the live workload: 2^16-element rows,
+// reference Makefile:64-74, several validators' requests in flight, base/miner.py:66-70).  Request r: row rows[r],
+// evaluations polys_be[r] (n x 32 bytes), point xs_be + 32 r.  The 2 count MSMs are groups of one grouped pipeline
+// (msm.cuh MsmGroups): a single sort, accumulation grid, slot chain and reduction for the whole batch, so the
+// latency-bound tail of a 2^16 MSM is paid once per batch and the accumulation grid is large enough to fill the machine.
+// status[r] = ZKP_OK or the error of request r (a non-canonical element fails that request only); the return value
+// is the first hard failure (CUDA, arguments).  Outputs of failed requests are zeroed.
+namespace {
+__global__ void k_batch_init(uint8_t* __restrict__ records, uint32_t count) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= count * (uint32_t)(SM_BYTES / 4)) return;
+    reinterpret_cast<uint32_t*>(records)[i] = (i % (SM_BYTES / 4)) == SM_HIT / 4 ? HIT_NONE : 0u;
+}
+constexpr size_t BATCH_MAX = MSM_MAX_GROUPS / 2;
+
+int batch_chunk(zkp_ctx* ctx, size_t count, const uint32_t* rows, const uint8_t* const* polys_be, size_t n, const uint8_t* xs_be,
+                uint8_t* commitments48, uint8_t* evals_be, uint8_t* proofs48, int* status, bool* done) {
+    *done = false;
+    cudaStream_t s0 = ctx->stream, s1 = ctx->stream2;
+    const uint32_t nn = (uint32_t)n, cnt = (uint32_t)count;
+    // evaluation points (Montgomery) and host staging for the records
+    const size_t hb = count * (SM_BYTES + 32);
+    if (ctx->h_batch_cap < hb) {
+        if (ctx->h_batch) cudaFreeHost(ctx->h_batch);
+        ctx->h_batch = nullptr;
+        ctx->h_batch_cap = 0;
+        ZKP_CUDA(cudaMallocHost(&ctx->h_batch, BATCH_MAX * (SM_BYTES + 32)));
+        ctx->h_batch_cap = BATCH_MAX * (SM_BYTES + 32);
+    }
+    uint8_t* h_x = ctx->h_batch + BATCH_MAX * SM_BYTES;
+    for (size_t r = 0; r < count; r++) {
+        Fr64 x;
+        if (!Fr64::from_be(x, xs_be + 32 * r)) { status[r] = ZKP_ERR_ENCODING; x = Fr64::zero(); }
+        memcpy(h_x + 32 * r, x.v, 32);
+    }
+    ctx->resident_n = 0;
+    ctx->resident_gen++;
+    ZKP_CUDA(ctx->scalars.ensure(n * count * 32));
+    ZKP_CUDA(ctx->fr_a.ensure(n * count * 32));
+    ZKP_CUDA(ctx->batch_small.ensure(BATCH_MAX * SM_BYTES));
+    ZKP_CUDA(ctx->batch_x.ensure(BATCH_MAX * 32));
+    int rc = open_buffers(ctx, nn, cnt);
+    if (rc) return rc;
+    // groups 0..count-1: commitments (raw big-endian scalars); count..2 count-1: proofs (Montgomery quotients)
+    MsmJob jobs[MSM_MAX_GROUPS];
+    for (uint32_t r = 0; r < cnt; r++) {
+        jobs[r] = {rows[r], ctx->scalars.as<uint32_t>() + (size_t)r * n * 8, SCALAR_BE};
+        jobs[cnt + r] = {rows[r], ctx->fr_c.as<uint32_t>() + (size_t)r * n * 8, SCALAR_MONT};
+    }
+    MsmPlan plan;
+    MsmGroups gs;
+    const G1Affine* pts = nullptr;
+    bool grouped = false;
+    rc = msm_plan_jobs(ctx, jobs, 2 * cnt, n, &plan, &gs, &pts, &grouped);
+    if (rc) return rc;
+    if (!grouped) return ZKP_OK;
+    *done = true;
+    uint8_t* rec = ctx->batch_small.as<uint8_t>();
+    for (uint32_t r = 0; r < cnt; r++)
+        ZKP_CUDA(cudaMemcpyAsync(ctx->scalars.as<uint8_t>() + (size_t)r * n * 32, polys_be[r], n * 32, cudaMemcpyHostToDevice, s0));
+    ZKP_CUDA(cudaMemcpyAsync(ctx->batch_x.p, h_x, 32 * count, cudaMemcpyHostToDevice, s0));
+    k_batch_init<<<(cnt * (unsigned)(SM_BYTES / 4) + 255) / 256, 256, 0, s0>>>(rec, cnt);
+    k_fr_from_be<<<dim3((nn + 255) / 256, cnt), 256, 0, s0>>>(ctx->scalars.as<uint32_t>(), n, ctx->fr_a.as<Fr>(),
+                                                             reinterpret_cast<uint32_t*>(rec + SM_BAD));
+    ctx->launches += 2;
+    ZKP_CUDA(cudaEventRecord(ctx->ev_ready, s0));
+    ZKP_CUDA(cudaStreamWaitEvent(s1, ctx->ev_ready, 0));
+    rc = msm_prep_begin(ctx, 0, plan);
+    if (!rc) rc = msm_prep_count(ctx, 0, plan, gs, 0, cnt);
+    if (!rc) rc = open_device(ctx, s1, ctx->fr_a.as<Fr>(), nn, Fr64::zero(), cnt, ctx->batch_x.as<Fr>(), rec);
+    if (!rc) {
+        ZKP_CUDA(cudaEventRecord(ctx->ev_join, s1));
+        ZKP_CUDA(cudaStreamWaitEvent(s0, ctx->ev_join, 0));
+        rc = msm_prep_count(ctx, 0, plan, gs, cnt, cnt);
+    }
+    if (!rc) rc = msm_prep_finish(ctx, 0, plan, gs);
+    if (!rc) rc = msm_enqueue_main(ctx, 0, plan, pts);
+    if (!rc) {
+        k_fr_to_be_records<<<(cnt + 63) / 64, 64, 0, s0>>>(rec, cnt);
+        ctx->launches++;
+        cudaMemcpyAsync(ctx->h_batch, rec, count * SM_BYTES, cudaMemcpyDeviceToHost, s0);
+        rc = msm_wait(ctx, 0, 2 * cnt, false);
+    } else {
+        cudaStreamSynchronize(s0);
+        cudaStreamSynchronize(s1);
+    }
+    msm_unpin_all(ctx);
+    if (rc) return rc;
+    // host: fold 2 count group results; a few threads when the batch is large (each fold is ~40 point operations
+    // and one field inversion)
+    const G1Xyzz* hw = ctx->ws.h_window;
+    const uint32_t* h_bad = ctx->ws.h_bad;
+    auto fold_range = [&](uint32_t lo, uint32_t hi) {
+        for (uint32_t r = lo; r < hi; r++) {
+            const uint8_t* hr = ctx->h_batch + (size_t)r * SM_BYTES;
+            const bool bad = h_bad[r] || *reinterpret_cast<const uint32_t*>(hr + SM_BAD);
+            if (status[r] == ZKP_OK && bad) status[r] = ZKP_ERR_ENCODING;
+            if (status[r] != ZKP_OK) {
+                memset(commitments48 + 48 * r, 0, 48);
+                memset(proofs48 + 48 * r, 0, 48);
+                memset(evals_be + 32 * r, 0, 32);
+                continue;
+            }
+            host::g1_compress(commitments48 + 48 * r, msm_fold_group(plan, hw, r));
+            host::g1_compress(proofs48 + 48 * r, msm_fold_group(plan, hw, cnt + r));
+            memcpy(evals_be + 32 * r, hr + SM_EVAL, 32);
+        }
+    };
+    const uint32_t nth = cnt >= 8 ? 4 : 1;
+    if (nth == 1) {
+        fold_range(0, cnt);
+    } else {
+        std::vector<std::thread> th;
+        for (uint32_t t = 1; t < nth; t++) th.emplace_back(fold_range, cnt * t / nth, cnt * (t + 1) / nth);
+        fold_range(0, cnt / nth);
+        for (auto& t : th) t.join();
+    }
+    return ZKP_OK;
+}
+}  // namespace
+
+int zkp_worker_commit_open_batch(zkp_ctx* ctx, size_t count, const uint32_t* rows, const uint8_t* const* polys_be, size_t n,
+                                 const uint8_t* xs_be, uint8_t* commitments48, uint8_t* evals_be, uint8_t* proofs48, int* status) {
+    if (!ctx || !count || !rows || !polys_be || !xs_be || !commitments48 || !evals_be || !proofs48 || !status)
+        return fail(ZKP_ERR_ARG, "null argument");
+    if (!ctx->shaped) return fail(ZKP_ERR_STATE, "SRS not loaded");
+    if (n != ((size_t)1 << ctx->log_n)) return fail(ZKP_ERR_ARG, "every request needs exactly one SRS row of evaluations");
+    if (ctx->shard_domain_log != ctx->log_n) return fail(ZKP_ERR_STATE, "not available on a point-range shard");
+    for (size_t r = 0; r < count; r++) {
+        if (!polys_be[r]) return fail(ZKP_ERR_ARG, "null polynomial");
+        if (rows[r] >= (1u << ctx->log_m) || !ctx->row_loaded[rows[r]]) return fail(ZKP_ERR_ARG, "worker index out of range");
+        status[r] = ZKP_OK;
+    }
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    DeviceGuard g(ctx->device);
+    for (size_t lo = 0; lo < count; lo += BATCH_MAX) {
+        const size_t k = count - lo < BATCH_MAX ? count - lo : BATCH_MAX;
+        bool done = false;
+        int rc = ZKP_OK;
+        if (tables_wanted(ctx, n) && !ctx->coeff_form)
+            rc = batch_chunk(ctx, k, rows + lo, polys_be + lo, n, xs_be + 32 * lo, commitments48 + 48 * lo, evals_be + 32 * lo,
+                             proofs48 + 48 * lo, status + lo, &done);
+        if (rc) return rc;
+        if (done) continue;
+        // no tables (disabled, or they do not fit): the requests one after the other on the two-lane path
+        for (size_t r = lo; r < lo + k; r++) {
+            Fr64 x;
+            if (!Fr64::from_be(x, xs_be + 32 * r)) { status[r] = ZKP_ERR_ENCODING; continue; }
+            rc = upload_poly(ctx, polys_be[r], n);
+            if (!rc) rc = commit_open_resident(ctx, rows[r], n, x, commitments48 + 48 * r, evals_be + 32 * r, proofs48 + 48 * r);
+            if (rc == ZKP_ERR_ENCODING) {
+                status[r] = rc;
+                memset(commitments48 + 48 * r, 0, 48);
+                memset(proofs48 + 48 * r, 0, 48);
+                memset(evals_be + 32 * r, 0, 32);
+            } else if (rc) {
+                return rc;
+            }
+        }
+    }
+    return ZKP_OK;
 }
 
 // ---------------------------------------------------------------------------------------------- sharded open
@@ -931,7 +1255,9 @@ int zkp_pairing_check(const uint8_t* g1_48, const uint8_t* g2_192, size_t pairs,
         if (!Fq64::from_be(x.c0, q) || !Fq64::from_be(x.c1, q + 48) || !Fq64::from_be(y.c0, q + 96) || !Fq64::from_be(y.c1, q + 144) ||
             !g2_on_curve(x, y))
             return fail(ZKP_ERR_ENCODING, "bad G2 point");
-        lines[k] = g2_precompute(G2J::from_affine(x, y));
+        const G2J q2 = G2J::from_affine(x, y);
+        if (!q2.mul(host::FR_MOD64, 4).is_inf()) return fail(ZKP_ERR_ENCODING, "G2 point outside the prime-order subgroup");
+        lines[k] = g2_precompute(q2);
         ps.push_back(g1_affine_host(p));
     }
     for (size_t k = 0; k < pairs; k++) qs.push_back(&lines[k]);
@@ -1030,6 +1356,7 @@ int zkp_random_poly(zkp_ctx* ctx, uint64_t seed, uint8_t* out_be, size_t count) 
     std::lock_guard<std::mutex> lk(ctx->mu);
     DeviceGuard g(ctx->device);
     ctx->resident_n = 0;
+    ctx->resident_gen++;
     ZKP_CUDA(ctx->scalars.ensure(count * 32));
     k_random_fr<<<(unsigned)((count + 255) / 256), 256, 0, ctx->stream>>>(seed, count, ctx->scalars.as<uint32_t>());
     ctx->launches++;
@@ -1039,6 +1366,86 @@ int zkp_random_poly(zkp_ctx* ctx, uint64_t seed, uint8_t* out_be, size_t count) 
 }
 
 int zkp_random_point(zkp_ctx* ctx, uint64_t seed, uint8_t out_be[32]) { return zkp_random_poly(ctx, seed ^ 0x706f696e74ull, out_be, 1); }
+
+// elements [first, first + count) of the stream zkp_random_poly(seed, ...) produces: lets every GPU of a sharded job
+// generate exactly its own slice of ONE global vector
+int zkp_random_poly_range(zkp_ctx* ctx, uint64_t seed, uint64_t first, uint8_t* out_be, size_t count) {
+    if (!ctx || !out_be || !count) return fail(ZKP_ERR_ARG, "bad argument");
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    DeviceGuard g(ctx->device);
+    ctx->resident_n = 0;
+    ctx->resident_gen++;
+    ZKP_CUDA(ctx->scalars.ensure(count * 32));
+    k_random_fr<<<(unsigned)((count + 255) / 256), 256, 0, ctx->stream>>>(seed, count, ctx->scalars.as<uint32_t>(), first);
+    ctx->launches++;
+    ZKP_CUDA(cudaMemcpyAsync(out_be, ctx->scalars.p, count * 32, cudaMemcpyDeviceToHost, ctx->stream));
+    ZKP_CUDA(cudaStreamSynchronize(ctx->stream));
+    return ZKP_OK;
+}
+
+// ---------------------------------------------------------------------------------------------- tables / tuning
+// Build the fixed-base tables of rows [first_row, first_row + count) now instead of inside the first request that
+// needs them (Client.start(precompute="eager")).  Rows beyond the arena's capacity are skipped; *built = tables resident.
+int zkp_srs_prebuild_tables(zkp_ctx* ctx, uint32_t first_row, uint32_t count, uint32_t* built) {
+    if (!ctx) return fail(ZKP_ERR_ARG, "null context");
+    if (!ctx->shaped) return fail(ZKP_ERR_STATE, "SRS not loaded");
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    DeviceGuard g(ctx->device);
+    uint32_t ok = 0;
+    const uint32_t rows = 1u << ctx->log_m;
+    if (ctx->use_precomp && ctx->log_n >= 8) {
+        for (uint32_t r = first_row; r < rows && r - first_row < count; r++) {
+            if (!ctx->row_loaded[r]) continue;
+            if (ok >= ctx->S.arena.row_of_slot.size() && ctx->S.arena.buf.p) break;  // arena full: leave the rest to LRU
+            int slot = -1;
+            int rc = acquire_table(ctx, r, &slot);
+            if (rc) return rc;
+            if (slot < 0) break;
+            release_table(ctx, slot);
+            ok++;
+        }
+    }
+    if (built) *built = ok;
+    return ZKP_OK;
+}
+// resident tables, slots of the arena, bytes of the arena, table builds, evictions, classic-path fallbacks so far
+int zkp_srs_table_stats(zkp_ctx* ctx, uint64_t out[6]) {
+    if (!ctx || !out) return fail(ZKP_ERR_ARG, "null argument");
+    std::lock_guard<std::recursive_mutex> lk(ctx->S.mu);
+    const TableArena& ar = ctx->S.arena;
+    uint64_t resident = 0;
+    for (int r : ar.row_of_slot) resident += r >= 0;
+    out[0] = resident;
+    out[1] = ar.row_of_slot.size();
+    out[2] = ar.buf.cap;
+    out[3] = ar.builds;
+    out[4] = ar.evictions;
+    out[5] = ar.fallbacks;
+    return ZKP_OK;
+}
+int zkp_set_table_budget(zkp_ctx* ctx, size_t bytes) {
+    if (!ctx) return fail(ZKP_ERR_ARG, "null context");
+    std::lock_guard<std::recursive_mutex> lk(ctx->S.mu);
+    ctx->S.table_budget = bytes;
+    return ZKP_OK;
+}
+// 0 (default): `poly` arguments of zkp_worker_commit / open / commit_open are EVALUATIONS on the natural-order domain
+// (what the reference's flow implies); 1: they are COEFFICIENTS (the reading of the comment at
+// reference neurons/validator.py:67) -- the library then evaluates them first (one forward NTT) and proceeds identically.
+int zkp_set_poly_form(zkp_ctx* ctx, int coefficients) {
+    if (!ctx) return fail(ZKP_ERR_ARG, "null context");
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    ctx->coeff_form = coefficients != 0;
+    ctx->resident_n = 0;
+    ctx->resident_gen++;
+    return ZKP_OK;
+}
+int zkp_set_fuse(zkp_ctx* ctx, int mode) {
+    if (!ctx || mode < -1 || mode > 1) return fail(ZKP_ERR_ARG, "fuse mode must be -1 (by size), 0 or 1");
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    ctx->fuse_mode = mode;
+    return ZKP_OK;
+}
 
 // ---------------------------------------------------------------------------------------------- codec
 int zkp_b64_decode_fr(const char* strs, size_t stride, size_t count, uint8_t* out_be) {
@@ -1231,6 +1638,7 @@ int zkp_bench_ntt(zkp_ctx* ctx, size_t n, int reps, int inverse, float* ms_per_n
     ZKP_CUDA(ctx->fr_a.ensure(n * 32));
     ZKP_CUDA(ctx->fr_b.ensure(n * 32));
     ctx->resident_n = 0;
+    ctx->resident_gen++;
     ZKP_CUDA(ctx->scalars.ensure(n * 32));
     k_random_fr<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(0xB200, n, ctx->scalars.as<uint32_t>());
     int rc = ensure_small(ctx);

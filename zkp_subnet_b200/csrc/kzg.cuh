@@ -18,6 +18,12 @@ namespace zkp {
 
 constexpr uint32_t HIT_NONE = 0xffffffffu;
 
+// Per-request device scalars of the opening: one SM_BYTES record per request (offsets in bytes).  The opening kernels
+// are batch-aware: blockIdx.y selects the request -- polynomial blockIdx.y of n elements, record blockIdx.y, evaluation
+// point xs[blockIdx.y] -- and a single request is simply gridDim.y == 1.
+constexpr size_t SM_BAD = 0, SM_HIT = 4, SM_Y = 32, SM_S1 = 64, SM_S2 = 96, SM_EVAL = 128, SM_BYTES = 256;
+constexpr uint32_t SM_STRIDE_U32 = SM_BYTES / 4, SM_STRIDE_FR = SM_BYTES / 32;
+
 __device__ __forceinline__ Fr load_fr(const Fr* p) {
     const uint4* s = reinterpret_cast<const uint4*>(p);
     uint4 a = s[0], b = s[1];
@@ -61,14 +67,23 @@ __device__ __forceinline__ void fr_bswap_store(uint32_t* w, const Fr& r) {
 __global__ void k_fr_from_be(const uint32_t* __restrict__ in, size_t n, Fr* __restrict__ out, uint32_t* __restrict__ bad) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
+    i += (size_t)blockIdx.y * n;
     Fr c = fr_bswap_load(in + i * 8);
-    if (!fr_lt_mod(c)) atomicOr(bad, 1u);
+    if (!fr_lt_mod(c)) atomicOr(bad + blockIdx.y * SM_STRIDE_U32, 1u);
     store_fr(out + i, c.to_mont());
 }
 __global__ void k_fr_to_be(const Fr* __restrict__ in, size_t n, uint32_t* __restrict__ out) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     fr_bswap_store(out + i * 8, load_fr(in + i).from_mont());
+}
+
+// one field element per request record (Montgomery, at byte offset SM_Y) -> big-endian bytes at SM_EVAL
+__global__ void k_fr_to_be_records(uint8_t* __restrict__ records, uint32_t count) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= count) return;
+    uint8_t* rec = records + (size_t)i * SM_BYTES;
+    fr_bswap_store(reinterpret_cast<uint32_t*>(rec + SM_EVAL), load_fr(reinterpret_cast<const Fr*>(rec + SM_Y)).from_mont());
 }
 
 // w^e from the table wt[k] = w^(2^k)
@@ -92,9 +107,10 @@ __device__ __forceinline__ void block_sum_store(const Fr& v, Fr* __restrict__ pa
 }
 // single block: out[0] = sum of count partials
 __global__ void k_fr_reduce(const Fr* __restrict__ partial, uint32_t count, Fr* __restrict__ out) {
+    partial += (size_t)blockIdx.y * count;
     Fr acc = Fr::zero();
     for (uint32_t i = threadIdx.x; i < count; i += blockDim.x) acc = acc + load_fr(partial + i);
-    block_sum_store(acc, out);
+    block_sum_store(acc, out + blockIdx.y * SM_STRIDE_FR);
 }
 
 // ---- opening, pass 1: inv_d[j] = 1/(w^j - x), partial sums of f_j w^j / (w^j - x).
@@ -105,10 +121,16 @@ __global__ void k_fr_reduce(const Fr* __restrict__ partial, uint32_t count, Fr* 
 // latency, times a handful of resident warps, was 1 ms of the opening's critical path at 2^20).
 __global__ void __launch_bounds__(128)
 k_open_pass1(const Fr* __restrict__ f, uint32_t n, uint32_t E, Fr x, const Fr* __restrict__ wt, Fr w_inv,
-             Fr* __restrict__ inv_d, Fr* __restrict__ partial, uint32_t* __restrict__ hit, uint64_t j0) {
+             Fr* __restrict__ inv_d, Fr* __restrict__ partial, uint32_t* __restrict__ hit, uint64_t j0,
+             const Fr* __restrict__ xs = nullptr) {
     __shared__ Fr pre[128], suf[128];
     __shared__ Fr total_inv;
     const uint32_t tid = threadIdx.x;
+    if (xs) x = load_fr(xs + blockIdx.y);
+    if (f) f += (size_t)blockIdx.y * n;
+    inv_d += (size_t)blockIdx.y * n;
+    partial += (size_t)blockIdx.y * gridDim.x;
+    hit += blockIdx.y * SM_STRIDE_U32;
     uint32_t t = blockIdx.x * blockDim.x + tid;
     uint64_t lo = (uint64_t)t * E;
     const uint32_t cnt = lo < n ? (n - lo < E ? (uint32_t)(n - lo) : E) : 0;
@@ -166,8 +188,14 @@ k_open_pass1(const Fr* __restrict__ f, uint32_t n, uint32_t E, Fr x, const Fr* _
 
 // y = f(x):  hit -> f[hit], else -(x^n - 1)/n * S1.   Single thread.
 __global__ void k_open_y(const Fr* __restrict__ f, uint32_t log_n, Fr x, Fr n_inv, const Fr* __restrict__ s1,
-                         const uint32_t* __restrict__ hit, Fr* __restrict__ y) {
+                         const uint32_t* __restrict__ hit, Fr* __restrict__ y, const Fr* __restrict__ xs = nullptr,
+                         uint32_t n = 0) {
     if (threadIdx.x || blockIdx.x) return;
+    if (xs) x = load_fr(xs + blockIdx.y);
+    f += (size_t)blockIdx.y * n;
+    s1 += blockIdx.y * SM_STRIDE_FR;
+    hit += blockIdx.y * SM_STRIDE_U32;
+    y += blockIdx.y * SM_STRIDE_FR;
     if (*hit != HIT_NONE) {
         store_fr(y, load_fr(f + *hit));
         return;
@@ -183,8 +211,9 @@ __global__ void k_open_pass2(const Fr* __restrict__ f, const Fr* __restrict__ in
                              Fr* __restrict__ q) {
     uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= n) return;
-    Fr yy = load_fr(y);
-    store_fr(q + j, (load_fr(f + j) - yy) * load_fr(inv_d + j));
+    const size_t o = (size_t)blockIdx.y * n + j;
+    Fr yy = load_fr(y + blockIdx.y * SM_STRIDE_FR);
+    store_fr(q + o, (load_fr(f + o) - yy) * load_fr(inv_d + o));
 }
 
 // ---- x = w^m: partial sums of q_j w^(j-m), j != m; then q_m = -sum
@@ -192,13 +221,15 @@ __global__ void k_open_fix_partial(const Fr* __restrict__ q, uint32_t n, const F
                                    const uint32_t* __restrict__ hit, Fr* __restrict__ partial) {
     uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
     Fr v = Fr::zero();
-    uint32_t m = *hit;
+    uint32_t m = hit[blockIdx.y * SM_STRIDE_U32];
+    q += (size_t)blockIdx.y * n;
     if (m != HIT_NONE && j < n && j != m) v = load_fr(q + j) * pow_from_table(wt, (uint64_t)((j + n - m) & (n - 1)));
-    block_sum_store(v, partial);
+    block_sum_store(v, partial + (size_t)blockIdx.y * gridDim.x);
 }
-__global__ void k_open_fix_apply(Fr* __restrict__ q, const uint32_t* __restrict__ hit, const Fr* __restrict__ s2) {
+__global__ void k_open_fix_apply(Fr* __restrict__ q, const uint32_t* __restrict__ hit, const Fr* __restrict__ s2, uint32_t n = 0) {
     if (threadIdx.x || blockIdx.x) return;
-    if (*hit != HIT_NONE) store_fr(q + *hit, load_fr(s2).neg());
+    const uint32_t m = hit[blockIdx.y * SM_STRIDE_U32];
+    if (m != HIT_NONE) store_fr(q + (size_t)blockIdx.y * n + m, load_fr(s2 + blockIdx.y * SM_STRIDE_FR).neg());
 }
 
 // ---- batched barycentric evaluation (validator challenge: every row of the random bivariate polynomial at the
@@ -265,9 +296,11 @@ k_eval_partial(const Fr* __restrict__ c, uint32_t n, uint32_t E, Fr x, const Fr*
 }
 
 // ---- challenge RNG: counter-based SplitMix64, 255-bit candidates, rejection until < r
-__global__ void k_random_fr(uint64_t seed, size_t n, uint32_t* __restrict__ out_be) {
+__global__ void k_random_fr(uint64_t seed, size_t n, uint32_t* __restrict__ out_be, uint64_t index0 = 0) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
+    out_be += i * 8;
+    i += index0;  // element i of the stream `seed`, wherever it is written
     Fr v;
     for (uint64_t attempt = 0;; attempt++) {
         uint64_t s = seed + 0x9e3779b97f4a7c15ull * (4 * (i * 64 + attempt) + 1);
@@ -284,7 +317,7 @@ __global__ void k_random_fr(uint64_t seed, size_t n, uint32_t* __restrict__ out_
         v.v[7] &= 0x7fffffffu;
         if (fr_lt_mod(v)) break;
     }
-    fr_bswap_store(out_be + i * 8, v);
+    fr_bswap_store(out_be, v);
 }
 
 }  // namespace zkp

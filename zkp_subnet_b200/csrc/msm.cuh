@@ -56,14 +56,16 @@ struct MsmPlan {
     uint32_t n = 0;        // points
     uint32_t c = 0;        // window bits
     uint32_t W = 0;        // digit positions per scalar
-    uint32_t Wb = 0;       // bucket windows: W (classic) or 1 (fixed-base tables, shared buckets)
+    uint32_t Wb = 0;       // bucket windows: W (classic) or one per GROUP (fixed-base tables: all digit positions of a
+                           // group share one bucket set; a group is one MSM of a fused launch set, see MsmGroups)
+    uint32_t groups = 1;   // MSMs sharing this launch set (same n, same c; > 1 only with fixed-base tables)
     uint32_t B = 0;        // buckets per bucket window = 2^(c-1)
     uint32_t key_bits = 0; // key bits (library radix-sort path)
     uint32_t discard = 0;  // key of zero digits
     bool precomp = false;  // vals index the table [2^(c w)] P_i at w * win_stride + i
     uint32_t win_stride = 0;
     uint32_t neg_offset = 0; // precomp: the table holds a second, negated half at +neg_offset (sign folded into the index)
-    size_t N = 0;          // entries = n * W
+    size_t N = 0;          // entries = groups * n * W
     // accumulation levels: level 0 consumes entries, level k>0 consumes the slots of level k-1
     struct Level { size_t items; uint32_t L; size_t threads; };
     std::vector<Level> levels;
@@ -90,6 +92,9 @@ constexpr uint32_t REDUCE_DIRECT_MAX = 1024;
 #endif
 #ifndef ZKP_SLOT_L1
 #define ZKP_SLOT_L1 8
+#endif
+#ifndef ZKP_FUSE_MAX_LOG
+#define ZKP_FUSE_MAX_LOG 18  // commit+open runs as ONE grouped launch set up to this row length (capi_rest.cuh commit_open_fused)
 #endif
 #ifndef ZKP_SLOT_LN
 #define ZKP_SLOT_LN 8   // slice length of the slot levels after the first
@@ -124,19 +129,21 @@ inline uint32_t msm_window_bits(uint32_t n, bool precomp) {
     return (uint32_t)c;
 }
 
-inline MsmPlan msm_make_plan(uint32_t n, int sm_count, uint32_t c, bool precomp, uint32_t win_stride, uint32_t affine_rounds = 0) {
+inline MsmPlan msm_make_plan(uint32_t n, int sm_count, uint32_t c, bool precomp, uint32_t win_stride, uint32_t affine_rounds = 0,
+                             uint32_t groups = 1) {
     MsmPlan p;
     p.n = n;
     p.c = c;
     p.W = 255 / p.c + 1;
     p.precomp = precomp;
     p.win_stride = win_stride;
-    p.Wb = precomp ? 1 : p.W;
+    p.groups = precomp ? groups : 1;
+    p.Wb = precomp ? p.groups : p.W;
     p.B = 1u << (p.c - 1);
     p.discard = p.Wb * p.B;
     p.key_bits = 1;
     while ((1ull << p.key_bits) <= p.discard) p.key_bits++;
-    p.N = (size_t)n * p.W;
+    p.N = (size_t)n * p.W * p.groups;
     p.affine_rounds = affine_rounds > AFFINE_MAX_ROUNDS ? AFFINE_MAX_ROUNDS : affine_rounds;
     p.bound[0] = p.N;
     for (uint32_t r = 0; r < p.affine_rounds; r++) p.bound[r + 1] = (p.bound[r] + p.discard + 1) / 2;  // sum ceil(len/2) <= (N + buckets)/2
@@ -198,13 +205,27 @@ enum { SCALAR_LE = 0, SCALAR_BE = 1, SCALAR_MONT = 2 };
 // the digits are recomputed in the second pass instead of being stored unsorted, written once, and read back.
 enum { DIGITS_WRITE = 0, DIGITS_COUNT = 1, DIGITS_SCATTER = 2 };
 constexpr uint32_t SORT_CHUNK_LOG = 10, SORT_CHUNK = 1u << SORT_CHUNK_LOG;  // keys per chunk of the two-level scan
+// Several MSMs of the same length over fixed-base tables can share ONE launch set (the two MSMs of a commit+open; a
+// batch of requests): group g has its own scalars and its own table (val_base = first record of the table inside
+// the arena), its keys are g * B + |digit| - 1, and everything after the digits -- sort, accumulation, slot levels,
+// reduction -- runs once over the union.  blockIdx.y selects the group (g0 + blockIdx.y).
+constexpr int MSM_MAX_GROUPS = 64;
+struct MsmGroups {
+    const uint32_t* scalars[MSM_MAX_GROUPS];
+    uint32_t val_base[MSM_MAX_GROUPS];
+    uint8_t fmt[MSM_MAX_GROUPS];
+};
 template <int MODE>
-__global__ void k_decompose(const uint32_t* __restrict__ scalars, uint32_t n, uint32_t c, uint32_t W,
-                            uint32_t B, uint32_t discard, int fmt, int precomp, uint32_t win_stride, uint32_t neg_offset,
+__global__ void k_decompose(const __grid_constant__ MsmGroups gs, uint32_t g0, uint32_t n, uint32_t c, uint32_t W,
+                            uint32_t B, uint32_t discard, int precomp, uint32_t win_stride, uint32_t neg_offset,
                             uint32_t* __restrict__ keys, uint32_t* __restrict__ vals, uint32_t* __restrict__ bad,
                             uint32_t* __restrict__ counters, const uint32_t* __restrict__ chunk_base) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
+    const uint32_t g = g0 + blockIdx.y;
+    const uint32_t* __restrict__ scalars = gs.scalars[g];
+    const int fmt = gs.fmt[g];
+    const uint32_t val_base = gs.val_base[g];
     uint32_t s[9];
     const uint4* src = reinterpret_cast<const uint4*>(scalars + (size_t)i * 8);
     uint4 a = src[0], b = src[1];
@@ -230,7 +251,7 @@ __global__ void k_decompose(const uint32_t* __restrict__ scalars, uint32_t n, ui
             uint32_t mk = FrParams::mod(k);
             if (!decided && s[k] != mk) { decided = true; lt = s[k] < mk; }
         }
-        if (!lt) atomicOr(bad, 1u);
+        if (!lt) atomicOr(bad + g, 1u);
     }
     s[8] = 0;
     uint32_t carry = 0;
@@ -247,11 +268,12 @@ __global__ void k_decompose(const uint32_t* __restrict__ scalars, uint32_t n, ui
         uint32_t neg = raw > half;
         uint32_t mag = neg ? (1u << c) - raw : raw;
         carry = neg;
-        const uint32_t key = mag ? (precomp ? 0u : w * B) + mag - 1 : discard;
+        const uint32_t key = mag ? (precomp ? g : w) * B + mag - 1 : discard;
         // with a negated table half the sign selects the half and no kernel ever negates a y-coordinate
-        const uint32_t val = neg_offset ? w * win_stride + i + (neg ? neg_offset : 0u) : ((precomp ? w * win_stride + i : i) | (neg << 31));
+        const uint32_t val = neg_offset ? val_base + w * win_stride + i + (neg ? neg_offset : 0u)
+                                        : ((precomp ? val_base + w * win_stride + i : i) | (neg << 31));
         if (MODE == DIGITS_WRITE) {
-            size_t o = (size_t)w * n + i;
+            size_t o = ((size_t)g * W + w) * n + i;
             keys[o] = key;
             vals[o] = val;
         } else {

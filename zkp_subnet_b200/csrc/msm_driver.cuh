@@ -30,7 +30,21 @@ inline bool msm_uses_bucket_sort(const zkp_ctx* ctx, const MsmPlan& plan) {
     return ctx->bucket_sort == 1 || plan.N <= ZKP_BUCKET_SORT_MAX_ENTRIES;
 }
 
-inline int msm_enqueue_prep(zkp_ctx* ctx, int lane, const MsmPlan& plan, const uint32_t* d_scalars, int fmt) {
+inline MsmGroups msm_single_group(const uint32_t* d_scalars, int fmt, uint32_t val_base = 0) {
+    MsmGroups gs;
+    memset(&gs, 0, sizeof(gs));
+    gs.scalars[0] = d_scalars;
+    gs.fmt[0] = (uint8_t)fmt;
+    gs.val_base[0] = val_base;
+    return gs;
+}
+
+// Front half in three steps so that a fused commit+open can count the digits of the commitment group while the
+// opening's field kernels (which produce the scalars of the proof group) are still running on the other stream:
+//   msm_prep_begin   workspaces, cleared counters and flags
+//   msm_prep_count   digits of groups [g0, g0 + gcount): histogram (bucket sort) or window-major write (library sort)
+//   msm_prep_finish  scan + scatter of ALL groups (bucket sort) or the radix sort
+inline int msm_prep_begin(zkp_ctx* ctx, int lane, const MsmPlan& plan) {
     MsmWorkspace& ws = lane ? ctx->ws2 : ctx->ws;
     cudaStream_t st = lane ? ctx->stream2 : ctx->stream;
     const size_t N = plan.N;
@@ -55,22 +69,47 @@ inline int msm_enqueue_prep(zkp_ctx* ctx, int lane, const MsmPlan& plan, const u
     const size_t out_records = (size_t)plan.Wb * plan.out_per_window;
     if (ws.h_window_cap < out_records) {
         if (ws.h_window) cudaFreeHost(ws.h_window);
+        ws.h_window = nullptr;
+        ws.h_window_cap = 0;
         ZKP_CUDA(cudaMallocHost(&ws.h_window, sizeof(G1Xyzz) * out_records));
         ws.h_window_cap = out_records;
     }
-    if (!ws.h_bad) ZKP_CUDA(cudaMallocHost(&ws.h_bad, 8));
-
-    // 1. digits
+    if (!ws.h_bad) ZKP_CUDA(cudaMallocHost(&ws.h_bad, 4 * MSM_MAX_GROUPS));
     trace_mark(ctx, lane, st, "msm_begin");
-    ZKP_CUDA(ws.bad.ensure(8));
-    ZKP_CUDA(cudaMemsetAsync(ws.bad.p, 0, 4, st));
+    ZKP_CUDA(ws.bad.ensure(4 * MSM_MAX_GROUPS));
+    ZKP_CUDA(cudaMemsetAsync(ws.bad.p, 0, 4 * MSM_MAX_GROUPS, st));
+    if (msm_uses_bucket_sort(ctx, plan)) {
+        const uint32_t m = plan.discard + 1, chunks = (m + SORT_CHUNK - 1) / SORT_CHUNK;
+        ZKP_CUDA(ws.sort_counters.ensure((size_t)chunks * SORT_CHUNK * 4));
+        ZKP_CUDA(ws.sort_chunks.ensure((size_t)chunks * 4));
+        ZKP_CUDA(cudaMemsetAsync(ws.sort_counters.p, 0, (size_t)chunks * SORT_CHUNK * 4, st));
+    }
+    return ZKP_OK;
+}
+
+inline int msm_prep_count(zkp_ctx* ctx, int lane, const MsmPlan& plan, const MsmGroups& gs, uint32_t g0, uint32_t gcount) {
+    MsmWorkspace& ws = lane ? ctx->ws2 : ctx->ws;
+    cudaStream_t st = lane ? ctx->stream2 : ctx->stream;
+    const dim3 grid((plan.n + 255) / 256, gcount);
+    if (!msm_uses_bucket_sort(ctx, plan))
+        k_decompose<DIGITS_WRITE><<<grid, 256, 0, st>>>(gs, g0, plan.n, plan.c, plan.W, plan.B, plan.discard, plan.precomp ? 1 : 0,
+                                                        plan.win_stride, plan.neg_offset, ws.keys_a.as<uint32_t>(),
+                                                        ws.vals_a.as<uint32_t>(), ws.bad.as<uint32_t>(), nullptr, nullptr);
+    else
+        k_decompose<DIGITS_COUNT><<<grid, 256, 0, st>>>(gs, g0, plan.n, plan.c, plan.W, plan.B, plan.discard, plan.precomp ? 1 : 0,
+                                                        plan.win_stride, plan.neg_offset, nullptr, nullptr, ws.bad.as<uint32_t>(),
+                                                        ws.sort_counters.as<uint32_t>(), nullptr);
+    ctx->launches++;
+    ZKP_CUDA(cudaGetLastError());
+    return ZKP_OK;
+}
+
+inline int msm_prep_finish(zkp_ctx* ctx, int lane, const MsmPlan& plan, const MsmGroups& gs) {
+    MsmWorkspace& ws = lane ? ctx->ws2 : ctx->ws;
+    cudaStream_t st = lane ? ctx->stream2 : ctx->stream;
+    const size_t N = plan.N;
+    trace_mark(ctx, lane, st, "decompose");
     if (!msm_uses_bucket_sort(ctx, plan)) {
-        k_decompose<DIGITS_WRITE><<<(plan.n + 255) / 256, 256, 0, st>>>(d_scalars, plan.n, plan.c, plan.W, plan.B, plan.discard, fmt,
-                                                                        plan.precomp ? 1 : 0, plan.win_stride, plan.neg_offset,
-                                                                        ws.keys_a.as<uint32_t>(), ws.vals_a.as<uint32_t>(),
-                                                                        ws.bad.as<uint32_t>(), nullptr, nullptr);
-        ctx->launches++;
-        trace_mark(ctx, lane, st, "decompose");
         // 2. sort by (window, bucket): library radix sort
         size_t temp_bytes = 0;
         ZKP_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, temp_bytes, ws.keys_a.as<uint32_t>(), ws.keys_b.as<uint32_t>(),
@@ -81,27 +120,26 @@ inline int msm_enqueue_prep(zkp_ctx* ctx, int lane, const MsmPlan& plan, const u
                                                  ws.vals_a.as<uint32_t>(), ws.vals_b.as<uint32_t>(), (int64_t)N, 0,
                                                  (int)plan.key_bits, st));
     } else {
-        // 1 + 2. hand-written bucket sort: count, scan, scatter (msm.cuh section 2)
+        // 1 + 2. hand-written bucket sort: count (done), scan, scatter (msm.cuh section 2)
         const uint32_t m = plan.discard + 1, chunks = (m + SORT_CHUNK - 1) / SORT_CHUNK;
-        ZKP_CUDA(ws.sort_counters.ensure((size_t)chunks * SORT_CHUNK * 4));
-        ZKP_CUDA(ws.sort_chunks.ensure((size_t)chunks * 4));
-        ZKP_CUDA(cudaMemsetAsync(ws.sort_counters.p, 0, (size_t)chunks * SORT_CHUNK * 4, st));
-        k_decompose<DIGITS_COUNT><<<(plan.n + 255) / 256, 256, 0, st>>>(d_scalars, plan.n, plan.c, plan.W, plan.B, plan.discard, fmt,
-                                                                        plan.precomp ? 1 : 0, plan.win_stride, plan.neg_offset, nullptr,
-                                                                        nullptr, ws.bad.as<uint32_t>(), ws.sort_counters.as<uint32_t>(),
-                                                                        nullptr);
-        trace_mark(ctx, lane, st, "decompose");
         k_sort_scan_chunks<<<chunks, SORT_CHUNK, 0, st>>>(ws.sort_counters.as<uint32_t>(), m, ws.sort_chunks.as<uint32_t>());
         k_sort_scan_sums<<<1, 1024, 0, st>>>(ws.sort_chunks.as<uint32_t>(), chunks);
-        k_decompose<DIGITS_SCATTER><<<(plan.n + 255) / 256, 256, 0, st>>>(d_scalars, plan.n, plan.c, plan.W, plan.B, plan.discard, fmt,
-                                                                          plan.precomp ? 1 : 0, plan.win_stride, plan.neg_offset,
-                                                                          ws.keys_b.as<uint32_t>(), nullptr,
-                                                                          ws.bad.as<uint32_t>(), ws.sort_counters.as<uint32_t>(),
-                                                                          ws.sort_chunks.as<uint32_t>());
-        ctx->launches += 4;
+        k_decompose<DIGITS_SCATTER><<<dim3((plan.n + 255) / 256, plan.groups), 256, 0, st>>>(
+            gs, 0, plan.n, plan.c, plan.W, plan.B, plan.discard, plan.precomp ? 1 : 0, plan.win_stride, plan.neg_offset,
+            ws.keys_b.as<uint32_t>(), nullptr, ws.bad.as<uint32_t>(), ws.sort_counters.as<uint32_t>(), ws.sort_chunks.as<uint32_t>());
+        ctx->launches += 3;
     }
     trace_mark(ctx, lane, st, "sort");
+    ZKP_CUDA(cudaGetLastError());
     return ZKP_OK;
+}
+
+inline int msm_enqueue_prep(zkp_ctx* ctx, int lane, const MsmPlan& plan, const MsmGroups& gs) {
+    int rc = msm_prep_begin(ctx, lane, plan);
+    if (rc) return rc;
+    rc = msm_prep_count(ctx, lane, plan, gs, 0, plan.groups);
+    if (rc) return rc;
+    return msm_prep_finish(ctx, lane, plan, gs);
 }
 
 // Back half: (optional batched-affine rounds,) balanced accumulation, reduction, copy of the bit-plane sums to pinned
@@ -237,20 +275,13 @@ inline int msm_enqueue_main(zkp_ctx* ctx, int lane, const MsmPlan& plan, const G
     }
     trace_mark(ctx, lane, st, "bit_sums");
     ZKP_CUDA(cudaMemcpyAsync(ws.h_window, d_out, sizeof(G1Xyzz) * out_records, cudaMemcpyDeviceToHost, st));
-    ZKP_CUDA(cudaMemcpyAsync(ws.h_bad, ws.bad.p, 4, cudaMemcpyDeviceToHost, st));
+    ZKP_CUDA(cudaMemcpyAsync(ws.h_bad, ws.bad.p, 4 * plan.groups, cudaMemcpyDeviceToHost, st));
     trace_mark(ctx, lane, st, "d2h");
     return ZKP_OK;
 }
 
-inline int msm_enqueue(zkp_ctx* ctx, int lane, const MsmPlan& plan, const uint32_t* d_scalars, int fmt,
-                       const G1Affine* d_points) {
-    int rc = msm_enqueue_prep(ctx, lane, plan, d_scalars, fmt);
-    if (rc) return rc;
-    return msm_enqueue_main(ctx, lane, plan, d_points);
-}
-
 // waits for the lane's pipeline; afterwards ws.h_window holds the bit-plane sums
-inline int msm_wait(zkp_ctx* ctx, int lane) {
+inline int msm_wait(zkp_ctx* ctx, int lane, uint32_t groups = 1, bool check_bad = true) {
     MsmWorkspace& ws = lane ? ctx->ws2 : ctx->ws;
     cudaStream_t st = lane ? ctx->stream2 : ctx->stream;
     cudaEvent_t ev0 = lane ? ctx->ev_acc2_0 : ctx->ev_acc0, ev1 = lane ? ctx->ev_acc2_1 : ctx->ev_acc1;
@@ -263,7 +294,9 @@ inline int msm_wait(zkp_ctx* ctx, int lane) {
             ctx->acc_count++;
         }
     }
-    if (*ws.h_bad) return fail(ZKP_ERR_ENCODING, "scalar is not a canonical field element (>= r)");
+    if (check_bad)
+        for (uint32_t g = 0; g < groups; g++)
+            if (ws.h_bad[g]) return fail(ZKP_ERR_ENCODING, "scalar is not a canonical field element (>= r)");
     return ZKP_OK;
 }
 
@@ -284,8 +317,21 @@ inline host::G1J horner_bits(const G1Xyzz* planes, uint32_t bits) {
     for (int j = (int)bits - 1; j >= 0; j--) acc = acc.dbl().add(xyzz_to_jac(planes[j]));
     return acc;
 }
+// result of group g of a grouped (fixed-base) launch set: one bucket window, no window fold
+inline host::G1J msm_fold_group(const MsmPlan& plan, const G1Xyzz* h_window, uint32_t g) {
+    using namespace host;
+    const G1Xyzz* rec = h_window + (size_t)g * plan.out_per_window;
+    G1J win = horner_bits(rec, plan.bits_c);
+    if (plan.bits_r) {
+        G1J r = horner_bits(rec + plan.bits_c, plan.bits_r);
+        for (uint32_t d = 0; d < plan.log_cols; d++) r = r.dbl();
+        win = win.add(r);
+    }
+    return win;
+}
 inline host::G1J msm_fold(const MsmPlan& plan, const G1Xyzz* h_window) {
     using namespace host;
+    if (plan.precomp) return msm_fold_group(plan, h_window, 0);
     G1J acc = G1J::infinity();
     for (int w = (int)plan.Wb - 1; w >= 0; w--) {
         for (uint32_t d = 0; d < plan.c && !acc.is_inf(); d++) acc = acc.dbl();

@@ -93,12 +93,13 @@ __global__ void k_lagrange_scalars(const Fr* __restrict__ inv_d, uint32_t n, con
 }
 
 // out[j] = tau^j (the scalars of the monomial SRS [tau^j]_1); tt[k] = tau^(2^k)
-__global__ void k_power_scalars(const Fr* __restrict__ tt, uint32_t n, Fr* __restrict__ out) {
+// (times `scale`: row i of the bivariate monomial SRS uses scale = tau_y^i)
+__global__ void k_power_scalars(const Fr* __restrict__ tt, uint32_t n, Fr* __restrict__ out, Fr scale) {
     constexpr uint32_t E = 8;
     uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
     uint64_t lo = (uint64_t)t * E;
     if (lo >= n) return;
-    Fr a = pow_from_table(tt, lo);
+    Fr a = pow_from_table(tt, lo) * scale;
     const Fr tau = load_fr(tt);
     for (uint32_t i = 0; i < E && lo + i < n; i++) {
         store_fr(out + lo + i, a);

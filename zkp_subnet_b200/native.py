@@ -34,6 +34,7 @@ _ctxp = ctypes.c_void_p
 # name -> argtypes (restype is int unless listed in _RESTYPES)
 _SIGNATURES = {
     "zkp_ctx_create": [ctypes.c_int, ctypes.POINTER(_ctxp)],
+    "zkp_ctx_fork": [_ctxp, ctypes.POINTER(_ctxp)],
     "zkp_ctx_destroy": [_ctxp],
     "zkp_last_error": [],
     "zkp_device_count": [],
@@ -43,7 +44,9 @@ _SIGNATURES = {
     "zkp_srs_generate_monomial": [_ctxp, _u8p, ctypes.c_uint32],
     "zkp_srs_generate_shard": [_ctxp, _u8p, _u8p, ctypes.c_uint32, ctypes.c_uint32, ctypes.c_uint32, ctypes.c_uint32],
     "zkp_g1_sum": [_u8p, ctypes.c_size_t, _u8p],
+    "zkp_g1_sum_checked": [_u8p, ctypes.c_size_t, _u8p],
     "zkp_g1_uncompress": [_u8p, _u8p],
+    "zkp_last_points_uncompressed": [_ctxp, _u8p],
     "zkp_g1_sum_uncompressed": [_u8p, ctypes.c_size_t, _u8p],
     "zkp_shard_eval_partial": [_ctxp, ctypes.c_uint32, _u8p, ctypes.c_size_t, _u8p, _u8p],
     "zkp_shard_eval_combine": [_u8p, ctypes.c_size_t, ctypes.c_uint32, _u8p, _u8p],
@@ -55,6 +58,14 @@ _SIGNATURES = {
     "zkp_master_open_y": [_ctxp, _u8p, ctypes.c_size_t, _u8p, _u8p, _u8p],
     "zkp_master_verify": [_ctxp, _u8p, _u8p, _u8p, _u8p, _u8p, _u8p, ctypes.POINTER(ctypes.c_int)],
     "zkp_srs_export_row": [_ctxp, ctypes.c_uint32, _u8p, ctypes.c_size_t],
+    "zkp_srs_import_row_compressed": [_ctxp, ctypes.c_uint32, _u8p, ctypes.c_size_t, _u8p],
+    "zkp_srs_export_row_compressed": [_ctxp, ctypes.c_uint32, _u8p, ctypes.c_size_t],
+    "zkp_srs_import_g2": [_ctxp, ctypes.c_int, _u8p],
+    "zkp_srs_export_g2": [_ctxp, ctypes.c_int, _u8p],
+    "zkp_srs_export_scale_point": [_ctxp, ctypes.c_uint32, _u8p],
+    "zkp_srs_set_shard": [_ctxp, ctypes.c_uint32, ctypes.c_uint32],
+    "zkp_srs_generate_monomial2": [_ctxp, _u8p, _u8p, ctypes.c_uint32, ctypes.c_uint32],
+    "zkp_srs_monomial_to_lagrange": [_ctxp],
     "zkp_srs_save": [_ctxp, ctypes.c_char_p],
     "zkp_srs_load": [_ctxp, ctypes.c_char_p],
     "zkp_srs_shape": [_ctxp, ctypes.POINTER(ctypes.c_uint32), ctypes.POINTER(ctypes.c_uint32)],
@@ -62,6 +73,10 @@ _SIGNATURES = {
     "zkp_worker_open": [_ctxp, ctypes.c_uint32, _u8p, ctypes.c_size_t, _u8p, _u8p, _u8p],
     "zkp_worker_open_resident": [_ctxp, ctypes.c_uint32, ctypes.c_size_t, _u8p, _u8p, _u8p],
     "zkp_worker_commit_open": [_ctxp, ctypes.c_uint32, _u8p, ctypes.c_size_t, _u8p, _u8p, _u8p, _u8p],
+    "zkp_resident_generation": [_ctxp, ctypes.POINTER(ctypes.c_uint64), ctypes.POINTER(ctypes.c_size_t)],
+    "zkp_worker_open_resident_gen": [_ctxp, ctypes.c_uint32, ctypes.c_size_t, ctypes.c_uint64, _u8p, _u8p, _u8p],
+    "zkp_worker_commit_open_batch": [_ctxp, ctypes.c_size_t, ctypes.POINTER(ctypes.c_uint32), ctypes.POINTER(ctypes.c_void_p),
+                                     ctypes.c_size_t, _u8p, _u8p, _u8p, _u8p, ctypes.POINTER(ctypes.c_int)],
     "zkp_worker_verify": [_ctxp, ctypes.c_uint32, _u8p, _u8p, _u8p, _u8p, ctypes.POINTER(ctypes.c_int)],
     "zkp_worker_verify_batch": [_ctxp, ctypes.c_size_t, ctypes.POINTER(ctypes.c_uint32), _u8p, _u8p, _u8p, _u8p, ctypes.POINTER(ctypes.c_int)],
     "zkp_fft": [_ctxp, _u8p, ctypes.c_size_t, ctypes.c_int, ctypes.c_int, _u8p],
@@ -69,6 +84,18 @@ _SIGNATURES = {
     "zkp_challenge_evals": [_ctxp, _u8p, ctypes.c_size_t, ctypes.c_size_t, _u8p, _u8p],
     "zkp_random_poly": [_ctxp, ctypes.c_uint64, _u8p, ctypes.c_size_t],
     "zkp_random_point": [_ctxp, ctypes.c_uint64, _u8p],
+    "zkp_random_poly_range": [_ctxp, ctypes.c_uint64, ctypes.c_uint64, _u8p, ctypes.c_size_t],
+    "zkp_mgpu_create": [ctypes.POINTER(ctypes.c_int), ctypes.c_int, ctypes.POINTER(_ctxp)],
+    "zkp_mgpu_destroy": [_ctxp],
+    "zkp_mgpu_device_count": [_ctxp],
+    "zkp_mgpu_ctx": [_ctxp, ctypes.c_int],
+    "zkp_mgpu_set_layout": [_ctxp, ctypes.c_int, ctypes.c_uint32, ctypes.c_uint32],
+    "zkp_mgpu_srs_generate": [_ctxp, _u8p, _u8p, ctypes.c_uint32, ctypes.c_uint32, ctypes.c_int],
+    "zkp_mgpu_prebuild_tables": [_ctxp],
+    "zkp_mgpu_msm_g1": [_ctxp, ctypes.c_uint32, _u8p, ctypes.c_size_t, ctypes.c_int, _u8p],
+    "zkp_mgpu_commit_open": [_ctxp, ctypes.c_uint32, _u8p, ctypes.c_size_t, _u8p, ctypes.c_int, _u8p, _u8p, _u8p],
+    "zkp_mgpu_pianist_commit_open": [_ctxp, ctypes.POINTER(ctypes.c_uint32), ctypes.c_size_t, _u8p, ctypes.c_size_t, _u8p,
+                                     ctypes.c_int, _u8p, _u8p, _u8p, _u8p, _u8p],
     "zkp_b64_decode_fr": [ctypes.c_char_p, ctypes.c_size_t, ctypes.c_size_t, _u8p],
     "zkp_b64_encode_fr": [_u8p, ctypes.c_size_t, ctypes.c_char_p],
     "zkp_msm_g1": [_ctxp, ctypes.c_uint32, _u8p, ctypes.c_size_t, _u8p],
@@ -87,9 +114,16 @@ _SIGNATURES = {
     "zkp_set_msm_affine_rounds": [_ctxp, ctypes.c_int],
     "zkp_msm_info": [_ctxp, ctypes.c_size_t, ctypes.POINTER(ctypes.c_uint32), ctypes.POINTER(ctypes.c_uint32),
                      ctypes.POINTER(ctypes.c_uint64)],
+    "zkp_set_fuse": [_ctxp, ctypes.c_int],
+    "zkp_set_poly_form": [_ctxp, ctypes.c_int],
+    "zkp_srs_prebuild_tables": [_ctxp, ctypes.c_uint32, ctypes.c_uint32, ctypes.POINTER(ctypes.c_uint32)],
+    "zkp_set_table_budget": [_ctxp, ctypes.c_size_t],
+    "zkp_srs_table_stats": [_ctxp, ctypes.POINTER(ctypes.c_uint64)],
     "zkp_pairing_check": [_u8p, _u8p, ctypes.c_size_t, ctypes.POINTER(ctypes.c_int)],
 }
-_RESTYPES = {"zkp_ctx_destroy": None, "zkp_last_error": ctypes.c_char_p}
+_RESTYPES = {"zkp_ctx_destroy": None, "zkp_last_error": ctypes.c_char_p, "zkp_mgpu_destroy": None, "zkp_mgpu_ctx": _ctxp}
+LAYOUT_ROWS, LAYOUT_POINT_RANGE = 1, 2
+MGPU_RESIDENT = 1
 
 EXPORTED_SYMBOLS = tuple(_SIGNATURES)
 
@@ -165,14 +199,26 @@ class Context:
     """Owns one zkp_ctx (one GPU, one resident SRS).  Mirrors the lifetime of the reference's prover
     process started by Client.start() and killed by Client.stop() (reference base/miner.py:73-84,155)."""
 
-    def __init__(self, device: int = 0):
+    def __init__(self, device: int = 0, _handle=None, _borrowed: bool = False):
+        self._borrowed = _borrowed
+        self.device = device
+        if _handle is not None:
+            self._h = _handle
+            return
         self._h = _ctxp()
         check(lib().zkp_ctx_create(device, ctypes.byref(self._h)))
 
+    def fork(self) -> "Context":
+        """A further context on the same device sharing this one's resident SRS and tables (own streams and
+        workspaces): one per request-handling thread."""
+        h = _ctxp()
+        check(lib().zkp_ctx_fork(self._h, ctypes.byref(h)))
+        return Context(self.device, _handle=h)
+
     def close(self) -> None:
-        if self._h:
+        if self._h and not self._borrowed:
             lib().zkp_ctx_destroy(self._h)
-            self._h = _ctxp()
+        self._h = _ctxp()
 
     def __enter__(self):
         return self
@@ -214,6 +260,37 @@ class Context:
         check(lib().zkp_srs_export_row(self._h, row, out, n))
         return out.raw
 
+    def srs_import_row_compressed(self, row: int, points48: bytes, scale_point48: Optional[bytes] = None) -> None:
+        check(lib().zkp_srs_import_row_compressed(self._h, row, points48, len(points48) // 48, scale_point48))
+
+    def srs_export_row_compressed(self, row: int, n: int) -> bytes:
+        out = ctypes.create_string_buffer(48 * n)
+        check(lib().zkp_srs_export_row_compressed(self._h, row, out, n))
+        return out.raw
+
+    def srs_import_g2(self, which: int, g2_192: bytes) -> None:
+        check(lib().zkp_srs_import_g2(self._h, which, g2_192))
+
+    def srs_export_g2(self, which: int) -> bytes:
+        out = ctypes.create_string_buffer(192)
+        check(lib().zkp_srs_export_g2(self._h, which, out))
+        return out.raw
+
+    def srs_export_scale_point(self, row: int) -> bytes:
+        out = ctypes.create_string_buffer(48)
+        check(lib().zkp_srs_export_scale_point(self._h, row, out))
+        return out.raw
+
+    def srs_set_shard(self, log_domain: int, shard: int) -> None:
+        check(lib().zkp_srs_set_shard(self._h, log_domain, shard))
+
+    def srs_generate_monomial2(self, tau_x: int, tau_y: int, log_n: int, log_machines: int) -> None:
+        check(lib().zkp_srs_generate_monomial2(self._h, tau_x.to_bytes(32, "big"), tau_y.to_bytes(32, "big"), log_n, log_machines))
+
+    def srs_monomial_to_lagrange(self) -> None:
+        """monomial rows [tau_x^j tau_y^i]_1 -> Lagrange rows + scale points, in place, without the trapdoor"""
+        check(lib().zkp_srs_monomial_to_lagrange(self._h))
+
     def srs_save(self, path: str) -> None:
         check(lib().zkp_srs_save(self._h, path.encode()))
 
@@ -244,6 +321,41 @@ class Context:
         proof = ctypes.create_string_buffer(48)
         check(lib().zkp_worker_open_resident(self._h, i, n, x_be, y, proof))
         return y.raw, proof.raw
+
+    def last_points_uncompressed(self) -> bytes:
+        """commitment || proof of the last commit+open, 2 x 96 bytes uncompressed (cross-process combine)"""
+        out = ctypes.create_string_buffer(192)
+        check(lib().zkp_last_points_uncompressed(self._h, out))
+        return out.raw
+
+    def resident_generation(self) -> Tuple[int, int]:
+        """(generation, n) of the polynomial the last upload left on the device; see worker_open_resident_gen."""
+        g, n = ctypes.c_uint64(), ctypes.c_size_t()
+        check(lib().zkp_resident_generation(self._h, ctypes.byref(g), ctypes.byref(n)))
+        return g.value, n.value
+
+    def worker_open_resident_gen(self, i: int, n: int, generation: int, x_be: bytes) -> Tuple[bytes, bytes]:
+        """worker_open_resident bound to one upload: ZkpError(ZKP_ERR_STATE) if anything has rewritten the staged
+        polynomial since `generation` was read."""
+        y = ctypes.create_string_buffer(32)
+        proof = ctypes.create_string_buffer(48)
+        check(lib().zkp_worker_open_resident_gen(self._h, i, n, generation, x_be, y, proof))
+        return y.raw, proof.raw
+
+    def worker_commit_open_batch(self, rows, polys, xs_be: bytes):
+        """`len(rows)` commit+open requests in one launch set.  polys: bytes or PinnedBuffer objects of n x 32 bytes
+        each; xs_be: 32 bytes per request.  Returns [(status, commitment, eval, proof)] (status 0 = OK)."""
+        k = len(rows)
+        n = len(polys[0]) // 32
+        keep = [_arg(p) for p in polys]
+        ptrs = (ctypes.c_void_p * k)(*[ctypes.cast(ctypes.c_char_p(b) if isinstance(b, bytes) else b, ctypes.c_void_p) for b in keep])
+        idx = (ctypes.c_uint32 * k)(*rows)
+        coms = ctypes.create_string_buffer(48 * k)
+        ys = ctypes.create_string_buffer(32 * k)
+        proofs = ctypes.create_string_buffer(48 * k)
+        status = (ctypes.c_int * k)()
+        check(lib().zkp_worker_commit_open_batch(self._h, k, idx, ptrs, n, xs_be, coms, ys, proofs, status))
+        return [(status[r], coms.raw[48 * r:48 * r + 48], ys.raw[32 * r:32 * r + 32], proofs.raw[48 * r:48 * r + 48]) for r in range(k)]
 
     def worker_commit_open(self, i: int, poly_be: bytes, x_be: bytes) -> Tuple[bytes, bytes, bytes]:
         com = ctypes.create_string_buffer(48)
@@ -315,6 +427,12 @@ class Context:
         check(lib().zkp_random_point(self._h, seed, out))
         return out.raw
 
+    def random_poly_range(self, seed: int, first: int, count: int) -> bytes:
+        """elements [first, first + count) of the stream random_poly(seed, ...) yields"""
+        out = ctypes.create_string_buffer(32 * count)
+        check(lib().zkp_random_poly_range(self._h, seed, first, out, count))
+        return out.raw
+
     def msm_g1(self, row: int, scalars_be: bytes) -> bytes:
         out = ctypes.create_string_buffer(48)
         check(lib().zkp_msm_g1(self._h, row, _arg(scalars_be), len(scalars_be) // 32, out))
@@ -330,6 +448,27 @@ class Context:
 
     def set_msm_mode(self, fixed_base_tables: bool) -> None:
         check(lib().zkp_set_msm_mode(self._h, int(fixed_base_tables)))
+
+    def set_poly_form(self, coefficients: bool) -> None:
+        """worker_* polynomials are evaluations (False, default) or coefficients (True)"""
+        check(lib().zkp_set_poly_form(self._h, int(coefficients)))
+
+    def set_fuse(self, mode: int) -> None:
+        """commit+open as one grouped launch set: 1 always, 0 never, -1 by row length (default)"""
+        check(lib().zkp_set_fuse(self._h, mode))
+
+    def prebuild_tables(self, first_row: int = 0, count: int = 1 << 30) -> int:
+        built = ctypes.c_uint32()
+        check(lib().zkp_srs_prebuild_tables(self._h, first_row, min(count, 0xFFFFFFFF), ctypes.byref(built)))
+        return built.value
+
+    def set_table_budget(self, nbytes: int) -> None:
+        check(lib().zkp_set_table_budget(self._h, nbytes))
+
+    def table_stats(self) -> dict:
+        out = (ctypes.c_uint64 * 6)()
+        check(lib().zkp_srs_table_stats(self._h, out))
+        return dict(zip(("resident", "slots", "arena_bytes", "builds", "evictions", "fallbacks"), [int(v) for v in out]))
 
     def set_msm_affine_rounds(self, rounds: int) -> None:
         check(lib().zkp_set_msm_affine_rounds(self._h, rounds))
@@ -378,6 +517,79 @@ class Context:
         ms = ctypes.c_float()
         check(lib().zkp_bench_ntt(self._h, n, reps, int(inverse), ctypes.byref(ms)))
         return ms.value
+
+
+class MultiContext:
+    """zkp_mgpu: the GPUs of one box behind one handle (one context + one host thread per device inside the library;
+    no torch, no NCCL).  layout LAYOUT_ROWS: whole SRS on every device, sub-polynomial k on device k mod G (Pianist);
+    LAYOUT_POINT_RANGE: one polynomial split by point range."""
+
+    def __init__(self, devices=None):
+        if devices is None:
+            devices = list(range(lib().zkp_device_count()))
+        self.devices = list(devices)
+        arr = (ctypes.c_int * len(self.devices))(*self.devices)
+        self._h = _ctxp()
+        check(lib().zkp_mgpu_create(arr, len(self.devices), ctypes.byref(self._h)))
+
+    def close(self) -> None:
+        if self._h:
+            lib().zkp_mgpu_destroy(self._h)
+            self._h = _ctxp()
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def ctx(self, k: int) -> Context:
+        """the context of device k, borrowed (owned by this MultiContext)"""
+        h = lib().zkp_mgpu_ctx(self._h, k)
+        if not h:
+            raise ZkpError(ZKP_ERR_ARG, "no such device in the MultiContext")
+        return Context(self.devices[k], _handle=_ctxp(h), _borrowed=True)
+
+    def set_layout(self, layout: int, log_n: int, log_machines: int) -> None:
+        check(lib().zkp_mgpu_set_layout(self._h, layout, log_n, log_machines))
+
+    def srs_generate(self, tau_x: int, tau_y: int, log_n: int, log_machines: int, layout: int) -> None:
+        check(lib().zkp_mgpu_srs_generate(self._h, tau_x.to_bytes(32, "big"), tau_y.to_bytes(32, "big"), log_n, log_machines, layout))
+
+    def prebuild_tables(self) -> None:
+        check(lib().zkp_mgpu_prebuild_tables(self._h))
+
+    def msm_g1(self, row: int, scalars_be, flags: int = 0) -> bytes:
+        out = ctypes.create_string_buffer(48)
+        check(lib().zkp_mgpu_msm_g1(self._h, row, _arg(scalars_be), len(scalars_be) // 32, flags, out))
+        return out.raw
+
+    def commit_open(self, row: int, poly_be, x_be: bytes, flags: int = 0) -> Tuple[bytes, bytes, bytes]:
+        com = ctypes.create_string_buffer(48)
+        y = ctypes.create_string_buffer(32)
+        proof = ctypes.create_string_buffer(48)
+        check(lib().zkp_mgpu_commit_open(self._h, row, _arg(poly_be), len(poly_be) // 32, x_be, flags, com, y, proof))
+        return com.raw, y.raw, proof.raw
+
+    def pianist_commit_open(self, rows, polys_be, alpha_be: bytes, flags: int = 0):
+        """-> (commitments [48 B each], evals [32 B each], proofs [48 B each], aggregated commitment, aggregated proof)"""
+        k = len(rows)
+        n = len(polys_be) // 32 // k
+        idx = (ctypes.c_uint32 * k)(*rows)
+        coms = ctypes.create_string_buffer(48 * k)
+        ys = ctypes.create_string_buffer(32 * k)
+        proofs = ctypes.create_string_buffer(48 * k)
+        agg_c = ctypes.create_string_buffer(48)
+        agg_p = ctypes.create_string_buffer(48)
+        check(lib().zkp_mgpu_pianist_commit_open(self._h, idx, k, _arg(polys_be), n, alpha_be, flags, coms, ys, proofs, agg_c, agg_p))
+        split = lambda b, w: [b[w * r:w * r + w] for r in range(k)]
+        return split(coms.raw, 48), split(ys.raw, 32), split(proofs.raw, 48), agg_c.raw, agg_p.raw
 
 
 def b64_decode_fr(strs: bytes, stride: int, count: int, out: Optional[PinnedBuffer] = None):
@@ -469,6 +681,13 @@ def shard_eval_combine(partials_be: bytes, log_n: int, x_be: bytes) -> bytes:
 def g1_sum(points48: bytes) -> bytes:
     out = ctypes.create_string_buffer(48)
     check(lib().zkp_g1_sum(points48, len(points48) // 48, out))
+    return out.raw
+
+
+def g1_sum_checked(points48: bytes) -> bytes:
+    """sum of points received from other parties: each is checked to be in the prime-order subgroup"""
+    out = ctypes.create_string_buffer(48)
+    check(lib().zkp_g1_sum_checked(points48, len(points48) // 48, out))
     return out.raw
 
 
