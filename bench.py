@@ -204,6 +204,8 @@ def main():
     ap.add_argument("--no-mgpu", action="store_true", help="skip the in-library multi-GPU leg")
     ap.add_argument("--no-2p24-open", action="store_true", help="skip the 2^24 commit+open line")
     ap.add_argument("--msm-log-n", type=int, default=24)
+    ap.add_argument("--combine", default="host", choices=["host", "nccl"],
+                    help="how the ranks' partial points reach rank 0: host shared memory (default) or an NCCL all_gather")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3  # timing rule: W >= 3
@@ -239,12 +241,25 @@ def main():
         if dist is not None:
             dist.barrier()
 
-    gather = Gatherer(dist, local, 192) if dist is not None else None
+    gather = None
+    if dist is not None:
+        if args.combine == "nccl":
+            g_nccl = Gatherer(dist, local, 192)
+            gather = lambda step, mine: g_nccl(mine)  # noqa: E731
+        else:
+            from zkp_subnet_b200 import sharding
+            hx = sharding.HostExchange(rank, world, 192, os.environ.get("MASTER_PORT", "0"))
+            dist.barrier()
+            hx.attach()
+            gather = hx.gather
     agg = [None]
+    step_no = [0]
 
     def combine():
-        """the cross-GPU step of the Pianist job: 192 bytes per rank, rank 0 adds 2 x N affine points"""
-        parts = gather(ctx.last_points_uncompressed())
+        """the cross-GPU step of the Pianist job: 192 bytes per rank (host-resident results, exchanged host to host),
+        rank 0 adds 2 x N affine points and compresses the two sums"""
+        step_no[0] += 1
+        parts = gather(step_no[0], ctx.last_points_uncompressed())
         if rank == 0:
             agg[0] = (native.g1_sum_uncompressed(b"".join(p[:96] for p in parts)),
                       native.g1_sum_uncompressed(b"".join(p[96:] for p in parts)))
@@ -387,13 +402,14 @@ def main():
         t_srs = time.perf_counter() - t0
         sc24 = native.PinnedBuffer(32 * n_local).write(ctx24.random_poly_range(SEED_MSM24, rank * n_local, n_local))
         ctx24.bench_msm(0, sc24, 1, True)  # builds the fixed-base tables of the shard
-        g24 = Gatherer(dist, local, 96) if dist is not None else None
+        g24 = gather
         full24 = [None]
 
         def combine24():
-            parts = g24(ctx24.last_points_uncompressed()[:96])
+            step_no[0] += 1
+            parts = g24(step_no[0], ctx24.last_points_uncompressed())
             if rank == 0:
-                full24[0] = native.g1_sum_uncompressed(b"".join(parts))
+                full24[0] = native.g1_sum_uncompressed(b"".join(p[:96] for p in parts))
         if g24:
             combine24()
         barrier()
@@ -524,8 +540,11 @@ def main():
         "msm_sharded": msm24,
         "mgpu_in_library": mgpu,
         "combine_ms_per_step": t_comb_max / args.steps,
-        "combine_note": "measured INSIDE the timed loop of `value` (and of e2e) at N > 1: pinned 192-byte H2D, NCCL all_gather, "
-                        "D2H, 2 x N affine additions + 2 compressions on rank 0",
+        "combine_note": "measured INSIDE the timed loop of `value` (and of e2e) at N > 1: every rank serialises its two partial "
+                        "points (192 bytes, uncompressed, no square root) and publishes them; rank 0 waits for all ranks, adds "
+                        "2 x N affine points, compresses the two sums.  transport = " + args.combine +
+                        " (host: POSIX shared memory -- the partials are host-resident, the window fold runs on the host; "
+                        "nccl: H2D + all_gather + D2H of the same bytes)",
         "table_prebuild_s": t_tables,
         "checks": checks,
         "verified": bool(ok), "worker_verify_ms_per_call_host": verify_ms,

@@ -25,3 +25,4 @@ def gpu_ctx():
     ctx = native.Context(0)  # raises ZkpError without a GPU: there is no CPU fallback
     yield ctx
     ctx.close()
+

@@ -109,17 +109,19 @@ int open_device(zkp_ctx* ctx, cudaStream_t st, const Fr* d_f, uint32_t n, const 
 }
 
 // upload poly (big-endian), convert to Montgomery in fr_a; leaves the raw bytes in ctx->scalars
-int convert_poly(zkp_ctx* ctx, size_t n);
+// worker_poly: the bytes are the `poly` of a worker_commit / worker_open call, i.e. subject to zkp_set_poly_form;
+// everything else (fft, eval, challenge rows, shard slices) is taken as it comes
+int convert_poly(zkp_ctx* ctx, size_t n, bool worker_poly = false);
 int ntt_device(zkp_ctx* ctx, const Fr* in, Fr* out, uint32_t log_n, int inverse);
-int upload_poly(zkp_ctx* ctx, const uint8_t* poly_be, size_t n) {
+int upload_poly(zkp_ctx* ctx, const uint8_t* poly_be, size_t n, bool worker_poly = false) {
     int rc = upload_scalars(ctx, poly_be, n, ctx->scalars);
     if (rc) return rc;
-    return convert_poly(ctx, n);
+    return convert_poly(ctx, n, worker_poly);
 }
 // raw big-endian bytes in ctx->scalars -> Montgomery form in fr_a (flags non-canonical elements).  With
 // zkp_set_poly_form(ctx, 1) the bytes are COEFFICIENTS and fr_a receives their evaluations (one forward NTT): everything
 // downstream works on evaluations either way.
-int convert_poly(zkp_ctx* ctx, size_t n) {
+int convert_poly(zkp_ctx* ctx, size_t n, bool worker_poly) {
     int rc = ensure_small(ctx);
     if (rc) return rc;
     ZKP_CUDA(ctx->fr_a.ensure(n * 32));
@@ -127,7 +129,7 @@ int convert_poly(zkp_ctx* ctx, size_t n) {
     k_fr_from_be<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(ctx->scalars.as<uint32_t>(), n, ctx->fr_a.as<Fr>(),
                                                                        small_at<uint32_t>(ctx, SM_BAD));
     ctx->launches++;
-    if (ctx->coeff_form) {
+    if (ctx->coeff_form && worker_poly) {
         if (!is_pow2(n)) return fail(ZKP_ERR_ARG, "a polynomial in coefficient form must have a power-of-two length");
         return ntt_device(ctx, ctx->fr_a.as<Fr>(), ctx->fr_a.as<Fr>(), ilog2(n), 0);
     }
@@ -702,7 +704,7 @@ int zkp_worker_open(zkp_ctx* ctx, uint32_t i, const uint8_t* poly_be, size_t n, 
     if (!eval_be || !proof48) return fail(ZKP_ERR_ARG, "null output");
     std::lock_guard<std::mutex> lk(ctx->mu);
     DeviceGuard g(ctx->device);
-    rc = upload_poly(ctx, poly_be, n);
+    rc = upload_poly(ctx, poly_be, n, true);
     if (rc) return rc;
     rc = commit_open_resident(ctx, i, n, x, nullptr, eval_be, proof48);
     if (rc == ZKP_OK) ctx->resident_n = n;
@@ -717,7 +719,7 @@ int zkp_worker_open_resident(zkp_ctx* ctx, uint32_t i, size_t n, const uint8_t x
     std::lock_guard<std::mutex> lk(ctx->mu);
     DeviceGuard g(ctx->device);
     if (ctx->resident_n != n) return fail(ZKP_ERR_STATE, "no polynomial of this size is resident on the device");
-    rc = convert_poly(ctx, n);
+    rc = convert_poly(ctx, n, true);
     if (rc) return rc;
     return commit_open_resident(ctx, i, n, x, nullptr, eval_be, proof48);
 }
@@ -736,7 +738,7 @@ int zkp_worker_open_resident_gen(zkp_ctx* ctx, uint32_t i, size_t n, uint64_t ge
     DeviceGuard g(ctx->device);
     if (ctx->resident_n != n || ctx->resident_gen != generation)
         return fail(ZKP_ERR_STATE, "the polynomial of that upload is no longer resident on the device");
-    rc = convert_poly(ctx, n);
+    rc = convert_poly(ctx, n, true);
     if (rc) return rc;
     return commit_open_resident(ctx, i, n, x, nullptr, eval_be, proof48);
 }
@@ -767,7 +769,7 @@ int zkp_worker_commit_open(zkp_ctx* ctx, uint32_t i, const uint8_t* poly_be, siz
     if (!commitment48 || !eval_be || !proof48) return fail(ZKP_ERR_ARG, "null output");
     std::lock_guard<std::mutex> lk(ctx->mu);
     DeviceGuard g(ctx->device);
-    rc = upload_poly(ctx, poly_be, n);
+    rc = upload_poly(ctx, poly_be, n, true);
     if (rc) return rc;
     rc = commit_open_resident(ctx, i, n, x, commitment48, eval_be, proof48);
     if (rc == ZKP_OK) ctx->resident_n = n;
@@ -923,7 +925,7 @@ int zkp_worker_commit_open_batch(zkp_ctx* ctx, size_t count, const uint32_t* row
         for (size_t r = lo; r < lo + k; r++) {
             Fr64 x;
             if (!Fr64::from_be(x, xs_be + 32 * r)) { status[r] = ZKP_ERR_ENCODING; continue; }
-            rc = upload_poly(ctx, polys_be[r], n);
+            rc = upload_poly(ctx, polys_be[r], n, true);
             if (!rc) rc = commit_open_resident(ctx, rows[r], n, x, commitments48 + 48 * r, evals_be + 32 * r, proofs48 + 48 * r);
             if (rc == ZKP_ERR_ENCODING) {
                 status[r] = rc;
@@ -1508,7 +1510,7 @@ int zkp_bench_commit_open(zkp_ctx* ctx, uint32_t row, const uint8_t* poly_be, si
     if (!ms_per_iter || !commitment48 || !eval_be || !proof48 || reps < 1) return fail(ZKP_ERR_ARG, "bad argument");
     std::lock_guard<std::mutex> lk(ctx->mu);
     DeviceGuard g(ctx->device);
-    rc = upload_poly(ctx, poly_be, n);  // resident in HBM before the timed region
+    rc = upload_poly(ctx, poly_be, n, true);  // resident in HBM before the timed region
     if (rc) return rc;
     ZKP_CUDA(cudaStreamSynchronize(ctx->stream));
     cudaEvent_t e0, e1;
@@ -1549,7 +1551,7 @@ int zkp_bench_trace(zkp_ctx* ctx, uint32_t row, const uint8_t* poly_be, size_t n
     if (!out || out_cap < 64) return fail(ZKP_ERR_ARG, "bad argument");
     std::lock_guard<std::mutex> lk(ctx->mu);
     DeviceGuard g(ctx->device);
-    rc = upload_poly(ctx, poly_be, n);
+    rc = upload_poly(ctx, poly_be, n, true);
     if (rc) return rc;
     uint8_t c48[48], y32[32], p48[48];
     for (int r = 0; r < warm && !rc; r++) rc = commit_open_resident(ctx, row, n, x, c48, y32, p48);

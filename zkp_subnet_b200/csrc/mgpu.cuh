@@ -96,6 +96,7 @@ int mgpu_check(zkp_mgpu* mg, int layout) {
 int shard_phase1(zkp_ctx* ctx, uint32_t row, const uint8_t* slice_be, size_t nl, const Fr64& x, bool resident, zkp_mgpu::Phase* ph) {
     ph->lock = std::unique_lock<std::mutex>(ctx->mu);
     DeviceGuard g(ctx->device);
+    if (ctx->coeff_form) return fail(ZKP_ERR_STATE, "coefficient form is not available on point-range shards (a distributed NTT)");
     int rc;
     if (resident) {
         if (ctx->resident_n != nl) return fail(ZKP_ERR_STATE, "no polynomial slice resident on this device");
@@ -398,9 +399,9 @@ int zkp_mgpu_pianist_commit_open(zkp_mgpu* mg, const uint32_t* rows, size_t coun
             int r;
             if (resident) {
                 if (ctx->resident_n != n) return fail(ZKP_ERR_STATE, "no polynomial resident on this device");
-                r = convert_poly(ctx, n);
+                r = convert_poly(ctx, n, true);
             } else {
-                r = upload_poly(ctx, polys_be + 32 * n * k, n);
+                r = upload_poly(ctx, polys_be + 32 * n * k, n, true);
             }
             host::G1J cj, pj;
             if (!r) r = commit_open_resident(ctx, rows[k], n, x, commitments48 + 48 * k, evals_be + 32 * k, proofs48 + 48 * k, &cj, &pj);

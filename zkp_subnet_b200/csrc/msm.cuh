@@ -94,7 +94,12 @@ constexpr uint32_t REDUCE_DIRECT_MAX = 1024;
 #define ZKP_SLOT_L1 8
 #endif
 #ifndef ZKP_FUSE_MAX_LOG
-#define ZKP_FUSE_MAX_LOG 18  // commit+open runs as ONE grouped launch set up to this row length (capi_rest.cuh commit_open_fused)
+// A SINGLE commit+open runs as one grouped launch set (capi_rest.cuh commit_open_fused) up to this row length.  Measured
+// on B200 (tools/fuse_sweep.py, profiles/r2_fuse_sweep.txt): the two-lane form already hides the tail of the first MSM
+// under the accumulation of the second, while the fused form puts the opening's field kernels in front of the shared
+// sort -- 1.77 vs 1.53 ms at 2^16 -- so a lone request never fuses by default; grouping pays for BATCHES
+// (zkp_worker_commit_open_batch), where 2k tails collapse into one.  zkp_set_fuse(ctx, 1) forces it.
+#define ZKP_FUSE_MAX_LOG 0
 #endif
 #ifndef ZKP_SLOT_LN
 #define ZKP_SLOT_LN 8   // slice length of the slot levels after the first

@@ -539,7 +539,7 @@ extern "C" int zkp_worker_commit(zkp_ctx* ctx, uint32_t i, const uint8_t* poly_b
     if (n != ((size_t)1 << ctx->log_n)) return fail(ZKP_ERR_ARG, "coefficient form needs exactly one SRS row of coefficients");
     std::lock_guard<std::mutex> lk(ctx->mu);
     DeviceGuard g(ctx->device);
-    rc = upload_poly(ctx, poly_be, n);
+    rc = upload_poly(ctx, poly_be, n, true);
     if (rc) return rc;
     rc = msm_device(ctx, i, ctx->fr_a.as<uint32_t>(), SCALAR_MONT, n, commitment48);
     if (rc) return rc;

@@ -29,6 +29,81 @@ def gather_bytes(dist, mine: bytes, device: str = "cpu") -> List[bytes]:
     return [raw[r * n:(r + 1) * n] for r in range(world)]
 
 
+class HostExchange:
+    """Gather of a small fixed-size byte string from every rank of ONE node to rank 0 through a POSIX shared-memory
+    segment -- no device round trip, no collective launch.  The partial results of this path are HOST-resident (the
+    window fold of an MSM runs on the host, see msm_driver.cuh), so the cross-GPU combine of a multi-process job is a
+    host-to-host exchange of ~200 bytes per rank; going through NCCL means an H2D copy, a kernel launch and a D2H copy
+    for data that never needed to be on the device (measured: 0.30 ms per step against ~20 us here).  Each rank owns one
+    64-byte-aligned slot: [u64 sequence | payload].  gather(step, mine) publishes this rank's payload under `step`; on
+    rank 0 it returns every rank's payload once all have published that step, elsewhere it returns None at once --
+    after waiting until rank 0 has consumed the step before last (two buffers per rank, so a writer is never more than
+    one step ahead of the reader).  The process group (NCCL) stays in charge of barriers and reductions."""
+
+    SLOT = 512
+
+    def __init__(self, rank: int, world: int, nbytes: int, tag: str):
+        from multiprocessing import shared_memory
+        import struct
+        if nbytes + 8 > self.SLOT:
+            raise ValueError("payload too large for a slot")
+        self.rank, self.world, self.n, self.struct = rank, world, nbytes, struct
+        size = self.SLOT * (2 * world + 1)
+        name = f"zkpb200_{tag}"
+        if rank == 0:
+            try:
+                old = shared_memory.SharedMemory(name=name)
+                old.close()
+                old.unlink()
+            except FileNotFoundError:
+                pass
+            self.shm = shared_memory.SharedMemory(name=name, create=True, size=size)
+            self.shm.buf[:size] = bytes(size)
+        else:
+            self.shm = None
+        self.name, self.size = name, size
+
+    def attach(self) -> None:
+        """non-zero ranks: call after a barrier that follows rank 0's constructor"""
+        if self.shm is None:
+            from multiprocessing import shared_memory
+            self.shm = shared_memory.SharedMemory(name=self.name)
+
+    def _slot(self, rank: int, step: int) -> int:
+        return self.SLOT * (2 * rank + (step & 1))
+
+    def gather(self, step: int, mine: bytes):
+        """step = 1, 2, 3, ... (strictly increasing, the same on every rank)"""
+        buf, st = self.shm.buf, self.struct
+        ack = self.SLOT * 2 * self.world
+        if self.rank != 0:
+            while st.unpack_from("<Q", buf, ack)[0] + 2 < step:  # rank 0 still reads the buffer this step reuses
+                pass
+        o = self._slot(self.rank, step)
+        buf[o + 8:o + 8 + self.n] = mine
+        st.pack_into("<Q", buf, o, step)
+        if self.rank != 0:
+            return None
+        out = []
+        for r in range(self.world):
+            o = self._slot(r, step)
+            while st.unpack_from("<Q", buf, o)[0] != step:
+                pass
+            out.append(bytes(buf[o + 8:o + 8 + self.n]))
+        st.pack_into("<Q", buf, ack, step)
+        return out
+
+    def close(self) -> None:
+        if self.shm is not None:
+            self.shm.close()
+            if self.rank == 0:
+                try:
+                    self.shm.unlink()
+                except FileNotFoundError:
+                    pass
+            self.shm = None
+
+
 def combine_partials(parts: Sequence[bytes]) -> Tuple[bytes, ...]:
     """Each part is k concatenated 48-byte points (e.g. commitment || proof); returns the k sums."""
     if not parts:
