@@ -279,6 +279,9 @@ int zkp_msm_info(zkp_ctx* ctx, size_t n, uint32_t* c, uint32_t* windows, uint64_
  * neurons/validator.py:67).  In coefficient form the library evaluates first (one forward NTT) and proceeds identically;
  * the polynomial must then fill the row exactly. */
 int zkp_set_poly_form(zkp_ctx* ctx, int coefficients);
+/* Experiment switch: the contiguous pass-2 tile of the NTT fetched by ONE bulk async copy (TMA: cp.async.bulk +
+ * mbarrier) instead of per-thread 16-byte loads.  Identical results; off by default because it measured slower. */
+int zkp_set_ntt_tma(zkp_ctx* ctx, int on);
 /* commit+open as ONE grouped launch set (both MSMs share the sort, the accumulation grid, the slot levels and the
  * reduction): 1 = always, 0 = never (two streams, two launch sets), -1 (default) = by row length.  Same bytes out. */
 int zkp_set_fuse(zkp_ctx* ctx, int mode);

@@ -443,6 +443,22 @@ def test_client_switches_pool_and_batch(golden):
         base.stop()
 
 
+@pytest.mark.parametrize("log_n", [12, 16, 20])
+def test_ntt_bulk_copy_variant_gives_the_same_transform(gpu_ctx, log_n):
+    n = 1 << log_n
+    v = gpu_ctx.random_poly(0x77 + log_n, n)
+    try:
+        gpu_ctx.set_ntt_tma(False)
+        f0, i0 = gpu_ctx.fft(v, True, False), gpu_ctx.fft(v, True, True)
+        gpu_ctx.set_ntt_tma(True)
+        assert gpu_ctx.fft(v, True, False) == f0 and gpu_ctx.fft(v, True, True) == i0
+        assert gpu_ctx.fft(f0, True, True) == v
+    finally:
+        gpu_ctx.set_ntt_tma(False)
+    if log_n == 12:
+        assert f0 == ref.ntt(v, False)
+
+
 def _device_sets():
     n = native.lib().zkp_device_count()
     sets = [[0]]

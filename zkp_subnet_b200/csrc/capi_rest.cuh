@@ -315,7 +315,9 @@ int ntt_device(zkp_ctx* ctx, const Fr* in, Fr* out, uint32_t log_n, int inverse)
     if (rc) return rc;
     const Fr n_inv = to_dev(dom->n_inv);
     // shared memory of a pass: the tile (32 B per element) + the butterfly twiddles of the sub-transform (m/2 x 32 B)
-    auto smem_for = [](uint32_t log_tile, uint32_t log_m) -> size_t { return ((size_t)32 << log_tile) + ((size_t)16 << log_m); };
+    auto smem_for = [](uint32_t log_tile, uint32_t log_m, bool tma = false) -> size_t {
+        return ((size_t)32 << log_tile) + ((size_t)16 << log_m) + (tma ? (size_t)32 << log_tile : 0);
+    };
     auto sub_table = [&](uint32_t log_m, const Fr** out_tw) -> int {
         if (log_m == 0) { *out_tw = dom->tw.as<Fr>(); return ZKP_OK; }
         zkp_ctx::Domain* d;
@@ -338,7 +340,7 @@ int ntt_device(zkp_ctx* ctx, const Fr* in, Fr* out, uint32_t log_n, int inverse)
         return lc;
     };
     if (log_n <= NTT_MAX_TILE_LOG) {
-        NttPass p = {log_n, 0, 1, 1, 0, 1, 0, 1, log_n, 0, (uint32_t)inverse, (uint32_t)inverse};
+        NttPass p = {log_n, 0, 1, 1, 0, 1, 0, 1, log_n, 0, (uint32_t)inverse, (uint32_t)inverse, 0};
         k_ntt_pass<<<1, threads_for(log_n), smem_for(log_n, log_n), ctx->stream>>>(in, out, dom->tw.as<Fr>(), dom->tw.as<Fr>(), p, n_inv);
         ctx->launches++;
         return ZKP_OK;
@@ -354,11 +356,14 @@ int ntt_device(zkp_ctx* ctx, const Fr* in, Fr* out, uint32_t log_n, int inverse)
     Fr* tmp = ctx->ntt_tmp.as<Fr>();
     uint32_t lc1 = cols_for(l1, l2), lc2 = cols_for(l2, l1);
     // pass 1: columns i2 (n2 of them), rows i1; element (r, c) at r*n2 + c; twiddle w^(c*k)
-    NttPass p1 = {l1, lc1, (uint32_t)n2, n2, 1, n2, 1, 0, log_n, 1, (uint32_t)inverse, 0};
+    NttPass p1 = {l1, lc1, (uint32_t)n2, n2, 1, n2, 1, 0, log_n, 1, (uint32_t)inverse, 0, 0};
     k_ntt_pass<<<(unsigned)(n2 >> lc1), threads_for(l1 + lc1), smem_for(l1 + lc1, l1), ctx->stream>>>(in, tmp, dom->tw.as<Fr>(), tw1, p1, n_inv);
     // pass 2: columns k1 (n1 of them), rows i2; element (r, c) at c*n2 + r; output (k2, c) at k2*n1 + c
-    NttPass p2 = {l2, lc2, (uint32_t)n1, 1, n2, n1, 1, 1, log_n, 0, (uint32_t)inverse, (uint32_t)inverse};
-    k_ntt_pass<<<(unsigned)(n1 >> lc2), threads_for(l2 + lc2), smem_for(l2 + lc2, l2), ctx->stream>>>(tmp, out, dom->tw.as<Fr>(), tw2, p2, n_inv);
+    // pass 2 reads one contiguous column per CTA when lc2 == 0: the only tile of this transform that a 1-D bulk copy
+    // (TMA) can fetch; off by default (zkp_set_ntt_tma, measured slower: DESIGN.md section 4)
+    const bool tma2 = ctx->ntt_tma && lc2 == 0 && l2 <= 11;
+    NttPass p2 = {l2, lc2, (uint32_t)n1, 1, n2, n1, 1, 1, log_n, 0, (uint32_t)inverse, (uint32_t)inverse, tma2 ? 1u : 0u};
+    k_ntt_pass<<<(unsigned)(n1 >> lc2), threads_for(l2 + lc2), smem_for(l2 + lc2, l2, tma2), ctx->stream>>>(tmp, out, dom->tw.as<Fr>(), tw2, p2, n_inv);
     ctx->launches += 2;
     return ZKP_OK;
 }
@@ -1440,6 +1445,14 @@ int zkp_set_poly_form(zkp_ctx* ctx, int coefficients) {
     ctx->coeff_form = coefficients != 0;
     ctx->resident_n = 0;
     ctx->resident_gen++;
+    return ZKP_OK;
+}
+// Experiment switch: fetch the pass-2 tile of the NTT with one bulk async copy (TMA, cp.async.bulk + mbarrier) instead of
+// per-thread 16-byte loads.  Same results; measured slower on B200, hence off by default.
+int zkp_set_ntt_tma(zkp_ctx* ctx, int on) {
+    if (!ctx) return fail(ZKP_ERR_ARG, "null context");
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    ctx->ntt_tma = on != 0;
     return ZKP_OK;
 }
 int zkp_set_fuse(zkp_ctx* ctx, int mode) {

@@ -252,7 +252,10 @@ inline int msm_enqueue_main(zkp_ctx* ctx, int lane, const MsmPlan& plan, const G
         uint32_t q_c = per_thread ? (rows + per_thread - 1) / per_thread : 1, q_r = per_thread ? (cols + per_thread - 1) / per_thread : 1;
         if (q_c > 2 * RC_LANES) q_c = 2 * RC_LANES;
         if (q_r > 2 * RC_LANES) q_r = 2 * RC_LANES;
-        if (q_c >= 4 && q_r >= 4) {
+        // (>= 2 shares per sum: with many bucket windows -- a batch of requests -- two shares already give one balanced
+        // wave; the one-warp-per-sum kernel below ran the 64-window reduction of a 32-request batch at 15.8 G Fq-mul/s
+        // against ~25 for this pair, profiles/r2_launches_summary.txt)
+        if (q_c >= 2 && q_r >= 2) {
             const uint32_t shares = cols * q_c + rows * q_r;
             ZKP_CUDA(ws.pool.ensure((size_t)plan.Wb * shares * sizeof(G1Xyzz)));
             k_rowcol_partial<<<dim3((shares + 127) / 128, plan.Wb), 128, 0, st>>>(ws.buckets.as<G1Xyzz>(), plan.log_rows, plan.log_cols,

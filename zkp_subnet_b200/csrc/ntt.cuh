@@ -50,7 +50,37 @@ struct NttPass {
     uint32_t twiddle;     // 1: multiply output (k, c) by w_n^(c*k)
     uint32_t inverse;
     uint32_t scale;       // 1: multiply output by n_inv
+    uint32_t tma;         // 1: the tile is ONE contiguous run in global memory (pass 2, one column per CTA) and is brought
+                          // in by a single bulk copy (cp.async.bulk -> mbarrier) into a staging area, then permuted into
+                          // the bit-reversed two-plane layout.  Experiment (zkp_set_ntt_tma): DESIGN.md section 4.
 };
+
+// ---- TMA (bulk async copy) helpers: one elected thread arms the barrier with the byte count and issues the copy; every
+// thread waits on the barrier's phase.  SASS: UBLKCP.S.G + SYNCS.ARRIVE.TRANS64 (B200_PROFILING.md).
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void tma_load_1d(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst_smem)),
+                 "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred P1;\n"
+        "LAB_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+        "@P1 bra DONE;\n"
+        "bra LAB_WAIT;\n"
+        "DONE:\n"
+        "}" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
 
 // tw: w_n^e (e < n/2) for the inter-pass twiddle; tw_sub: w_m^e (e < m/2), contiguous, for the butterflies
 // (a 16 KB table that stays in L1 instead of one 128-byte line per twiddle of the big table)
@@ -65,6 +95,20 @@ k_ntt_pass(const Fr* __restrict__ in, Fr* __restrict__ out, const Fr* __restrict
     const uint32_t c0 = blockIdx.x * cols;
     const uint32_t half_n = 1u << (p.log_n - 1);
 
+    if (p.tma) {
+        // one bulk copy of the whole (contiguous) tile into the staging area behind the twiddles, then the permutation
+        __shared__ __align__(8) uint64_t bar;
+        uint4* stage = smem + 2 * tile + m;
+        if (threadIdx.x == 0) mbar_init(&bar, 1);
+        __syncthreads();
+        if (threadIdx.x == 0) tma_load_1d(stage, in + (uint64_t)c0 * p.in_cs, tile * 32u, &bar);
+        mbar_wait(&bar, 0);
+        for (uint32_t r = threadIdx.x; r < tile; r += NTT_THREADS) {
+            const uint32_t pos = p.log_m ? (__brev(r) >> (32 - p.log_m)) : 0;
+            lo[pos] = stage[2 * r];
+            hi[pos] = stage[2 * r + 1];
+        }
+    } else
     // load, rows bit-reversed
     for (uint32_t idx = threadIdx.x; idx < tile; idx += NTT_THREADS) {
         uint32_t r, c;

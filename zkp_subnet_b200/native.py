@@ -115,6 +115,7 @@ _SIGNATURES = {
     "zkp_msm_info": [_ctxp, ctypes.c_size_t, ctypes.POINTER(ctypes.c_uint32), ctypes.POINTER(ctypes.c_uint32),
                      ctypes.POINTER(ctypes.c_uint64)],
     "zkp_set_fuse": [_ctxp, ctypes.c_int],
+    "zkp_set_ntt_tma": [_ctxp, ctypes.c_int],
     "zkp_set_poly_form": [_ctxp, ctypes.c_int],
     "zkp_srs_prebuild_tables": [_ctxp, ctypes.c_uint32, ctypes.c_uint32, ctypes.POINTER(ctypes.c_uint32)],
     "zkp_set_table_budget": [_ctxp, ctypes.c_size_t],
@@ -452,6 +453,10 @@ class Context:
     def set_poly_form(self, coefficients: bool) -> None:
         """worker_* polynomials are evaluations (False, default) or coefficients (True)"""
         check(lib().zkp_set_poly_form(self._h, int(coefficients)))
+
+    def set_ntt_tma(self, on: bool) -> None:
+        """NTT pass-2 tile by one bulk async copy (TMA) instead of per-thread loads (experiment; same results)"""
+        check(lib().zkp_set_ntt_tma(self._h, int(on)))
 
     def set_fuse(self, mode: int) -> None:
         """commit+open as one grouped launch set: 1 always, 0 never, -1 by row length (default)"""

@@ -66,8 +66,12 @@ class HostExchange:
     def attach(self) -> None:
         """non-zero ranks: call after a barrier that follows rank 0's constructor"""
         if self.shm is None:
-            from multiprocessing import shared_memory
+            from multiprocessing import resource_tracker, shared_memory
             self.shm = shared_memory.SharedMemory(name=self.name)
+            try:  # the segment belongs to rank 0: keep this process's tracker from unlinking (and warning about) it
+                resource_tracker.unregister(self.shm._name, "shared_memory")
+            except Exception:
+                pass
 
     def _slot(self, rank: int, step: int) -> int:
         return self.SLOT * (2 * rank + (step & 1))
