@@ -31,6 +31,24 @@ if rank == 0:
     # identical rows: sum_i R_i(tau_y) = 1, so the aggregate equals the commitment / proof under the plain SRS
     ok = com.hex() == golden["B_eval_form"]["commitment"] and proof.hex() == golden["B_eval_form"]["proof"]
     print("COMBINE_OK" if ok else "COMBINE_BAD", flush=True)
+# the host-to-host exchange bench.py uses for the per-step combine (POSIX shared memory; NCCL / gloo only for barriers):
+# several steps in a row, rank 0 must see every rank's payload of THAT step
+hx = sharding.HostExchange(rank, world, 192, "test_" + os.environ.get("MASTER_PORT", "0"))
+dist.barrier()
+hx.attach()
+exp96 = sharding.expand_partials(mine_c + mine_p)
+for step in range(1, 41):
+    got = hx.gather(step, exp96[:184] + step.to_bytes(8, "little"))
+    if rank == 0:
+        assert [g[184:] for g in got] == [step.to_bytes(8, "little")] * world and got[rank][:184] == exp96[:184]
+        if step == 40:
+            ok = ok and [g[:184] for g in got] == [p[:184] for p in parts96]
+    else:
+        assert got is None
+dist.barrier()
+hx.close()
+if rank == 0:
+    print("EXCHANGE_OK" if ok else "EXCHANGE_BAD", flush=True)
 dist.barrier()
 dist.destroy_process_group()
 sys.exit(0 if ok else 1)

@@ -1,6 +1,7 @@
 """CPU: host-side parts of the product library that need no device -- the base64 wire codec, the G1 sum
 used to combine per-GPU partial points, and the pairing behind worker_verify -- against the oracle."""
 import base64
+import os
 
 import pytest
 
@@ -164,3 +165,58 @@ def test_wire_decoder_every_byte_at_every_position():
     raw = bytes(rng.randrange(256) for _ in range(32 * 5000))
     strs = [base64.b64encode(raw[32 * i:32 * i + 32]).decode().rstrip("=") for i in range(5000)]
     assert native.wire_decode_list(strs) == raw
+
+
+# ---- round 2: the shim's start-up rules and the SRS file recognition need no GPU
+def test_client_refuses_a_missing_srs_before_touching_the_gpu(tmp_path, monkeypatch):
+    from zkp_subnet_b200 import native
+    from zkp_subnet_b200.client import Client, _bitrev, _truthy
+    monkeypatch.delenv("ZKP_B200_TEST_SRS", raising=False)
+    c = Client(port=1337, bin="./prover", uncompressed="true", setup_path=str(tmp_path / "setup_24_8.uncompressed"),
+               precompute_path=str(tmp_path / "precompute_24_8.uncompressed"))
+    assert c.uncompressed is True
+    with pytest.raises(native.ZkpError) as e:
+        c.start(scale=24, machines_scale=8)
+    assert e.value.code == native.ZKP_ERR_IO and "ZKP_B200_TEST_SRS" in str(e.value)
+    assert not os.listdir(tmp_path)  # nothing was written
+    with pytest.raises(ValueError):
+        Client(poly_form="wavelets")
+    with pytest.raises(ValueError):
+        Client().start(scale=4, machines_scale=5)
+    assert [_bitrev(i, 3) for i in range(8)] == [0, 4, 2, 6, 1, 5, 3, 7]
+    assert _truthy("true") and _truthy(True) and not _truthy("false") and not _truthy("0") and not _truthy("")
+
+
+def test_srs_file_recognition(tmp_path):
+    from zkp_subnet_b200 import native, srsfile
+    scale, ms = 6, 2
+    count = 1 << scale
+    setup, pre = tmp_path / "setup", tmp_path / "pre"
+    assert srsfile.find_source(str(setup), str(pre), True, scale, ms) is None
+    setup.write_bytes(bytes(96 * count + 384))
+    src = srsfile.find_source(str(setup), str(pre), False, scale, ms)  # the size decides, the flag only breaks ties
+    assert (src.kind, src.point_bytes, src.precompute_path, src.log_n, src.log_m) == ("raw", 96, None, 4, 2)
+    pre.write_bytes(bytes(48 * count + 48 * 4))
+    src = srsfile.find_source(str(setup), str(pre), True, scale, ms)
+    assert (src.precompute_path, src.pre_point_bytes) == (str(pre), 48)
+    setup.write_bytes(bytes(100))
+    with pytest.raises(native.ZkpError) as e:
+        srsfile.find_source(str(setup), None, True, scale, ms)
+    assert "neither" in str(e.value)
+    setup.write_bytes(b"ZKPB200S" + bytes(40))
+    assert srsfile.find_source(str(setup), None, True, scale, ms).kind == "native"
+
+
+def test_setup_cli_argument_checks(tmp_path):
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    base = [sys.executable, "-m", "zkp_subnet_b200.setup", "--setup-path", str(tmp_path / "s"), "--precompute-path", str(tmp_path / "p"),
+            "--scale", "6", "--machines-scale", "2"]
+    r = subprocess.run(base, cwd=root, capture_output=True, text=True)
+    assert r.returncode == 1 and "nothing to do" in r.stderr
+    (tmp_path / "s").write_bytes(b"x")
+    r = subprocess.run(base + ["--generate-setup"], cwd=root, capture_output=True, text=True)
+    assert r.returncode == 1 and "--overwrite" in r.stderr and (tmp_path / "s").read_bytes() == b"x"
+    r = subprocess.run(base[:-4] + ["--scale", "2", "--machines-scale", "3", "--generate-setup"], cwd=root, capture_output=True, text=True)
+    assert r.returncode == 2

@@ -27,7 +27,8 @@ def run_two_ranks(script: str, port_base: int):
 
 
 def test_two_rank_combine_gloo():
-    assert "COMBINE_OK" in run_two_ranks("rank_combine.py", 29500)
+    out = run_two_ranks("rank_combine.py", 29500)
+    assert "COMBINE_OK" in out and "EXCHANGE_OK" in out
 
 
 def test_two_rank_sharded_open_gloo():

@@ -16,7 +16,7 @@
 //   * Montgomery reduction limb by limb: m = (column mod 2^48) * (-p^-1) mod 2^48, add m * p.
 // Cost: 128 limb products x 4 FP64 operations + ~150 for the reduction bookkeeping and normalisation.
 #pragma once
-#include "ff.cuh"
+#include "../zkp_subnet_b200/csrc/ff.cuh"
 
 namespace zkp {
 namespace fp64 {

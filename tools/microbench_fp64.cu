@@ -1,10 +1,10 @@
-// FP64-pipe Fq product (csrc/fq_fp64.cuh): exactness against the integer product of ff.cuh on random and edge
+// FP64-pipe Fq product (tools/fq_fp64.cuh): exactness against the integer product of ff.cuh on random and edge
 // inputs, throughput alone, and throughput of a kernel whose warps alternate between the two formulations.
 #include <cstdio>
 #include <cstdlib>
 #include <vector>
 #include <cuda_runtime.h>
-#include "../zkp_subnet_b200/csrc/fq_fp64.cuh"
+#include "fq_fp64.cuh"
 using namespace zkp;
 #define CK(x) do { cudaError_t e = (x); if (e != cudaSuccess) { printf("CUDA error %s at %s:%d\n", cudaGetErrorString(e), __FILE__, __LINE__); exit(1); } } while (0)
 

@@ -42,6 +42,7 @@
 #include <cub/device/device_radix_sort.cuh>
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdlib.h>
 #include <vector>
 
 #include "g1_coop.cuh"
@@ -160,7 +161,12 @@ inline MsmPlan msm_make_plan(uint32_t n, int sm_count, uint32_t c, bool precomp,
 #ifndef ZKP_L0_TARGET
 #define ZKP_L0_TARGET 48
 #endif
-    size_t waves = (p.acc_items + resident * ZKP_L0_TARGET - 1) / (resident * ZKP_L0_TARGET);
+    static const size_t l0_target = [] {
+        const char* e = getenv("ZKP_L0_TARGET");  // tuning runs only (tools/shard_tail.py)
+        size_t v = e ? (size_t)strtoull(e, nullptr, 10) : 0;
+        return v ? v : (size_t)ZKP_L0_TARGET;
+    }();
+    size_t waves = (p.acc_items + resident * l0_target - 1) / (resident * l0_target);
     if (waves < 1) waves = 1;
     uint32_t L0 = (uint32_t)((p.acc_items + waves * resident - 1) / (waves * resident));
 #ifndef ZKP_MIN_L0
