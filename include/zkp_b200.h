@@ -150,6 +150,19 @@ int zkp_worker_open_resident(zkp_ctx* ctx, uint32_t i, size_t n, const uint8_t x
 int zkp_resident_generation(zkp_ctx* ctx, uint64_t* generation, size_t* n);
 int zkp_worker_open_resident_gen(zkp_ctx* ctx, uint32_t i, size_t n, uint64_t generation, const uint8_t x_be[32],
                                  uint8_t eval_be[32], uint8_t proof48[48]);
+/* Staged upload: the polynomial goes to the device in chunks while the host is still producing it (the shim decodes the
+ * List[str] of the Prove synapse, reference base/protocol.py:35-40, chunk by chunk, and every finished chunk is on its way
+ * over PCIe while the next is being decoded).  zkp_stage_begin names the upload; zkp_stage_chunk enqueues the asynchronous
+ * copy of elements [first, first + count) taken from base + 32 first (page-locked memory; the argument order makes it the
+ * per-chunk callback of the wire decoder); zkp_stage_end marks the polynomial resident.  zkp_worker_commit_resident,
+ * zkp_worker_open_resident_gen and zkp_worker_commit_open_resident then work on that upload (or on the one an earlier
+ * zkp_worker_* call left) and fail with ZKP_ERR_STATE if anything has replaced it. */
+int zkp_stage_begin(zkp_ctx* ctx, size_t n, uint64_t* generation);
+int zkp_stage_chunk(zkp_ctx* ctx, size_t first, const uint8_t* base, size_t count);
+int zkp_stage_end(zkp_ctx* ctx, uint64_t generation);
+int zkp_worker_commit_resident(zkp_ctx* ctx, uint32_t i, size_t n, uint64_t generation, uint8_t commitment48[48]);
+int zkp_worker_commit_open_resident(zkp_ctx* ctx, uint32_t i, size_t n, uint64_t generation, const uint8_t x_be[32],
+                                    uint8_t commitment48[48], uint8_t eval_be[32], uint8_t proof48[48]);
 /* Miner.rpc_commit_and_open fused (reference neurons/miner.py:56-61): one upload, both MSMs */
 int zkp_worker_commit_open(zkp_ctx* ctx, uint32_t i, const uint8_t* poly_be, size_t n, const uint8_t x_be[32],
                            uint8_t commitment48[48], uint8_t eval_be[32], uint8_t proof48[48]);

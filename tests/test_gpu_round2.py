@@ -459,6 +459,52 @@ def test_ntt_bulk_copy_variant_gives_the_same_transform(gpu_ctx, log_n):
         assert f0 == ref.ntt(v, False)
 
 
+def test_staged_upload_in_chunks_matches_plain_upload(golden):
+    """Large lists go through the chunked decode + staged upload (zkp_stage_*): same answers as the plain path, the
+    two-call flow still recognises the resident polynomial, a malformed element is still a 400, and a superseded upload
+    is refused."""
+    from fourier import Client
+    from zkp_subnet_b200.client import encode_poly
+    lg = 17
+    n = 1 << lg
+    c = Client(test_srs=True, contexts=1, staged_upload=True)
+    c.start(scale=lg, machines_scale=0)
+    try:
+        assert n >= c.STAGE_MIN
+        ctx = c._need()
+        raw = ctx.random_poly(0x5146, n)
+        x = ctx.random_point(3)
+        xs = base64.b64encode(x).decode().rstrip("=")
+        strs = encode_poly(raw)
+        want = ctx.worker_commit_open(0, raw, x)
+        r = c.worker_commit_and_open(0, strs, xs).json()
+        assert (base64.b64decode(r["commitment"]), base64.b64decode(r["eval"] + "="), base64.b64decode(r["proof"])) == want
+        assert base64.b64decode(c.worker_commit(0, strs).json()["commitment"]) == want[0]
+        o1 = c.worker_open(0, strs, xs).json()          # speculative: the staged polynomial is the resident one
+        o2 = c.worker_open(0, list(strs), xs).json()
+        assert o1 == o2 and base64.b64decode(o1["proof"]) == want[2]
+        other = encode_poly(ctx.random_poly(0x5147, n))
+        o3 = c.worker_open(0, other, xs).json()         # another polynomial: staged afresh
+        assert base64.b64decode(o3["proof"]) == ctx.worker_open(0, ctx.random_poly(0x5147, n), x)[1]
+        bad = list(strs)
+        bad[n - 7] = "!" * 43
+        assert c.worker_commit(0, bad).status_code == 400
+        assert c.worker_commit_and_open(0, bad, xs).status_code == 400
+        assert base64.b64decode(c.worker_commit(0, strs).json()["commitment"]) == want[0]
+        # the C entries directly: chunks in any order; a superseded generation is refused
+        pin = native.PinnedBuffer(32 * n).write(raw)
+        gen = ctx.stage_list(strs, pin, chunk=5000)
+        assert pin.tobytes() == raw and ctx.worker_commit_open_resident(0, n, gen, x) == want
+        assert ctx.worker_commit_resident(0, n, gen) == want[0]
+        ctx.fft(raw[:32 * 16], True, False)             # anything that rewrites the staged scalars
+        with pytest.raises(native.ZkpError) as e:
+            ctx.worker_commit_resident(0, n, gen)
+        assert e.value.code == native.ZKP_ERR_STATE
+        pin.close()
+    finally:
+        c.stop()
+
+
 def _device_sets():
     n = native.lib().zkp_device_count()
     sets = [[0]]

@@ -758,6 +758,75 @@ int zkp_last_points_uncompressed(zkp_ctx* ctx, uint8_t out192[192]) {
     host::g1_serialize96(out192 + 96, ctx->last_proof);
     return ZKP_OK;
 }
+// ---- staged upload: the polynomial reaches the device in CHUNKS while the host is still producing it (the shim decodes a
+// List[str] of base64 strings chunk by chunk: every finished chunk is already on its way over PCIe while the next one is
+// being decoded).  zkp_stage_begin names the upload (generation), zkp_stage_chunk enqueues one asynchronous copy of
+// elements [first, first + count) from base + 32 first (its argument order makes it usable as the per-chunk callback of
+// the wire decoder), zkp_stage_end marks the polynomial resident; the *_resident entries then work on it.
+int zkp_stage_begin(zkp_ctx* ctx, size_t n, uint64_t* generation) {
+    if (!ctx || !n || !generation) return fail(ZKP_ERR_ARG, "bad argument");
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    DeviceGuard g(ctx->device);
+    ctx->resident_n = 0;
+    ctx->resident_gen++;
+    ZKP_CUDA(ctx->scalars.ensure(n * 32));
+    ctx->staging_n = n;
+    ctx->staging_gen = ctx->resident_gen;
+    *generation = ctx->resident_gen;
+    return ZKP_OK;
+}
+int zkp_stage_chunk(zkp_ctx* ctx, size_t first, const uint8_t* base, size_t count) {
+    if (!ctx || !base) return fail(ZKP_ERR_ARG, "null argument");
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    if (!ctx->staging_n || ctx->staging_gen != ctx->resident_gen) return fail(ZKP_ERR_STATE, "no staged upload in progress on this context");
+    if (first + count > ctx->staging_n) return fail(ZKP_ERR_ARG, "chunk outside the staged polynomial");
+    DeviceGuard g(ctx->device);
+    ZKP_CUDA(cudaMemcpyAsync(ctx->scalars.as<uint8_t>() + 32 * first, base + 32 * first, 32 * count, cudaMemcpyHostToDevice, ctx->stream));
+    return ZKP_OK;
+}
+int zkp_stage_end(zkp_ctx* ctx, uint64_t generation) {
+    if (!ctx) return fail(ZKP_ERR_ARG, "null context");
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    if (!ctx->staging_n || ctx->staging_gen != generation || ctx->resident_gen != generation)
+        return fail(ZKP_ERR_STATE, "the staged upload was superseded by another call on this context");
+    ctx->resident_n = ctx->staging_n;  // the copies are ordered before everything enqueued on the context's stream afterwards
+    ctx->staging_n = 0;
+    return ZKP_OK;
+}
+// worker_commit / fused commit+open on the polynomial of upload `generation` (staged, or left by an earlier call)
+int zkp_worker_commit_resident(zkp_ctx* ctx, uint32_t i, size_t n, uint64_t generation, uint8_t commitment48[48]) {
+    int rc = check_row(ctx, i, n);
+    if (rc) return rc;
+    if (!commitment48) return fail(ZKP_ERR_ARG, "null output");
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    DeviceGuard g(ctx->device);
+    if (ctx->resident_n != n || ctx->resident_gen != generation)
+        return fail(ZKP_ERR_STATE, "the polynomial of that upload is no longer resident on the device");
+    if (!ctx->coeff_form) return msm_device(ctx, i, ctx->scalars.as<uint32_t>(), SCALAR_BE, n, commitment48);
+    if (n != ((size_t)1 << ctx->log_n)) return fail(ZKP_ERR_ARG, "coefficient form needs exactly one SRS row of coefficients");
+    rc = convert_poly(ctx, n, true);
+    if (rc) return rc;
+    rc = msm_device(ctx, i, ctx->fr_a.as<uint32_t>(), SCALAR_MONT, n, commitment48);
+    if (rc) return rc;
+    uint32_t bad = 0;
+    ZKP_CUDA(cudaMemcpy(&bad, small_at<uint32_t>(ctx, SM_BAD), 4, cudaMemcpyDeviceToHost));
+    if (bad) return fail(ZKP_ERR_ENCODING, "polynomial holds a non-canonical field element");
+    return ZKP_OK;
+}
+int zkp_worker_commit_open_resident(zkp_ctx* ctx, uint32_t i, size_t n, uint64_t generation, const uint8_t x_be[32],
+                                    uint8_t commitment48[48], uint8_t eval_be[32], uint8_t proof48[48]) {
+    Fr64 x;
+    int rc = open_checks(ctx, i, x_be /* any non-null pointer */, n, x_be, &x);
+    if (rc) return rc;
+    if (!commitment48 || !eval_be || !proof48) return fail(ZKP_ERR_ARG, "null output");
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    DeviceGuard g(ctx->device);
+    if (ctx->resident_n != n || ctx->resident_gen != generation)
+        return fail(ZKP_ERR_STATE, "the polynomial of that upload is no longer resident on the device");
+    rc = convert_poly(ctx, n, true);
+    if (rc) return rc;
+    return commit_open_resident(ctx, i, n, x, commitment48, eval_be, proof48);
+}
 int zkp_resident_generation(zkp_ctx* ctx, uint64_t* generation, size_t* n) {
     if (!ctx || !generation) return fail(ZKP_ERR_ARG, "null argument");
     std::lock_guard<std::mutex> lk(ctx->mu);

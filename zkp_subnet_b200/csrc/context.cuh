@@ -188,6 +188,8 @@ struct zkp_ctx {
     // the generation of ITS upload (zkp_resident_generation) cannot be handed another caller's polynomial.
     size_t resident_n = 0;
     uint64_t resident_gen = 0;
+    size_t staging_n = 0;                     // > 0: a chunked upload (zkp_stage_begin .. zkp_stage_end) is in progress
+    uint64_t staging_gen = 0;
     zkp::MsmWorkspace ws;                     // lane 0 workspace (runs on `stream`)
     // lane 1: second stream + workspace so that the two MSMs of a commit+open (and their
     // latency-bound reduction tails) overlap on the device

@@ -37,12 +37,19 @@ static inline bool decode_one(const char* p, uint8_t* out, bool avx2, bool strea
     (void)stream;
     return codec::b64_decode32(p, out);
 }
+// decodes elements [first, first + count) of the list into out + 32 first (every index below is relative to `first`)
+static long long decode_range_impl(PyObject** items_all, size_t first, Py_ssize_t n, uint8_t* out_all, const uint8_t* ref_all, int* same);
 static long long decode_list_impl(PyObject* seq, uint8_t* out, size_t capacity, const uint8_t* ref, int* same) {
     const long long BAD_ARG = -(1ll << 40);
     if (!seq || !out || !(PyList_Check(seq) || PyTuple_Check(seq))) return BAD_ARG;
     const Py_ssize_t n = PySequence_Fast_GET_SIZE(seq);
     if ((size_t)n * 32 > capacity) return BAD_ARG - 1;
-    PyObject** items = PySequence_Fast_ITEMS(seq);
+    return decode_range_impl(PySequence_Fast_ITEMS(seq), 0, n, out, ref, same);
+}
+static long long decode_range_impl(PyObject** items_all, size_t first, Py_ssize_t n, uint8_t* out_all, const uint8_t* ref_all, int* same) {
+    PyObject** items = items_all + first;
+    uint8_t* out = out_all + 32 * first;
+    const uint8_t* ref = ref_all ? ref_all + 32 * first : nullptr;
     // Walk AND decode on the host threads.  The calling thread holds the GIL for the whole call, so no other
     // Python code runs and the list keeps every element alive; the workers only READ immutable object fields
     // through macros (type flags, length, the inline buffer of a compact ASCII str / of a bytes object) -- no
@@ -117,6 +124,24 @@ static long long decode_list_impl(PyObject* seq, uint8_t* out, size_t capacity, 
 }
 long long zkp_wire_decode_list(PyObject* seq, uint8_t* out, size_t capacity) {
     return decode_list_impl(seq, out, capacity, nullptr, nullptr);
+}
+// The same in chunks of `chunk` elements: after each chunk, on_chunk(user, first, out, count) is called on the calling
+// thread (the shim passes zkp_stage_chunk of libzkp_b200.so and its context: the chunk's host-to-device copy is enqueued
+// and runs while the next chunk is being decoded).  A non-zero return of the callback aborts with BAD_ARG - 2.
+typedef int (*zkp_wire_chunk_fn)(void* user, size_t first, const uint8_t* base, size_t count);
+long long zkp_wire_decode_list_chunked(PyObject* seq, uint8_t* out, size_t capacity, size_t chunk, zkp_wire_chunk_fn on_chunk, void* user) {
+    const long long BAD_ARG = -(1ll << 40);
+    if (!seq || !out || !chunk || !on_chunk || !(PyList_Check(seq) || PyTuple_Check(seq))) return BAD_ARG;
+    const Py_ssize_t n = PySequence_Fast_GET_SIZE(seq);
+    if ((size_t)n * 32 > capacity) return BAD_ARG - 1;
+    PyObject** items = PySequence_Fast_ITEMS(seq);
+    for (size_t first = 0; first < (size_t)n; first += chunk) {
+        const size_t count = (size_t)n - first < chunk ? (size_t)n - first : chunk;
+        const long long r = decode_range_impl(items, first, (Py_ssize_t)count, out, nullptr, nullptr);
+        if (r != (long long)count) return r < 0 && r > BAD_ARG ? r - (long long)first : r;  // index of the bad element, list-relative
+        if (on_chunk(user, first, out, count) != 0) return BAD_ARG - 2;
+    }
+    return (long long)n;
 }
 long long zkp_wire_decode_list_cmp(PyObject* seq, uint8_t* out, size_t capacity, const uint8_t* ref, int* same) {
     if (!ref || !same) return -(1ll << 40);

@@ -74,6 +74,11 @@ _SIGNATURES = {
     "zkp_worker_open_resident": [_ctxp, ctypes.c_uint32, ctypes.c_size_t, _u8p, _u8p, _u8p],
     "zkp_worker_commit_open": [_ctxp, ctypes.c_uint32, _u8p, ctypes.c_size_t, _u8p, _u8p, _u8p, _u8p],
     "zkp_resident_generation": [_ctxp, ctypes.POINTER(ctypes.c_uint64), ctypes.POINTER(ctypes.c_size_t)],
+    "zkp_stage_begin": [_ctxp, ctypes.c_size_t, ctypes.POINTER(ctypes.c_uint64)],
+    "zkp_stage_chunk": [_ctxp, ctypes.c_size_t, _u8p, ctypes.c_size_t],
+    "zkp_stage_end": [_ctxp, ctypes.c_uint64],
+    "zkp_worker_commit_resident": [_ctxp, ctypes.c_uint32, ctypes.c_size_t, ctypes.c_uint64, _u8p],
+    "zkp_worker_commit_open_resident": [_ctxp, ctypes.c_uint32, ctypes.c_size_t, ctypes.c_uint64, _u8p, _u8p, _u8p, _u8p],
     "zkp_worker_open_resident_gen": [_ctxp, ctypes.c_uint32, ctypes.c_size_t, ctypes.c_uint64, _u8p, _u8p, _u8p],
     "zkp_worker_commit_open_batch": [_ctxp, ctypes.c_size_t, ctypes.POINTER(ctypes.c_uint32), ctypes.POINTER(ctypes.c_void_p),
                                      ctypes.c_size_t, _u8p, _u8p, _u8p, _u8p, ctypes.POINTER(ctypes.c_int)],
@@ -328,6 +333,39 @@ class Context:
         out = ctypes.create_string_buffer(192)
         check(lib().zkp_last_points_uncompressed(self._h, out))
         return out.raw
+
+    def stage_list(self, strs, staging: "PinnedBuffer", chunk: int = 1 << 18) -> int:
+        """Decode a List[str] of base64 field elements into `staging` (page-locked) in chunks, every finished chunk being
+        copied to the device while the next one is decoded; returns the generation of the upload, to be handed to
+        worker_commit_resident / worker_open_resident_gen / worker_commit_open_resident.  ValueError on a malformed element."""
+        if not isinstance(strs, (list, tuple)):
+            strs = list(strs)
+        n = len(strs)
+        if staging.capacity < 32 * n:
+            raise ValueError("PinnedBuffer too small")
+        gen = ctypes.c_uint64()
+        check(lib().zkp_stage_begin(self._h, n, ctypes.byref(gen)))
+        cb = ctypes.cast(lib().zkp_stage_chunk, ctypes.c_void_p)
+        rc = wire().zkp_wire_decode_list_chunked(strs, ctypes.addressof(staging.buf), staging.capacity, chunk, cb, self._h)
+        if rc != n:
+            if rc <= -(1 << 40):
+                raise ValueError("wire decode: bad argument" if rc > -(1 << 40) - 2 else f"staged upload failed: {last_error()}")
+            raise ValueError(f"element {-1 - rc} is not a base64 field element of 43/44 characters")
+        check(lib().zkp_stage_end(self._h, gen.value))
+        staging.used = 32 * n
+        return gen.value
+
+    def worker_commit_resident(self, i: int, n: int, generation: int) -> bytes:
+        out = ctypes.create_string_buffer(48)
+        check(lib().zkp_worker_commit_resident(self._h, i, n, generation, out))
+        return out.raw
+
+    def worker_commit_open_resident(self, i: int, n: int, generation: int, x_be: bytes) -> Tuple[bytes, bytes, bytes]:
+        com = ctypes.create_string_buffer(48)
+        y = ctypes.create_string_buffer(32)
+        proof = ctypes.create_string_buffer(48)
+        check(lib().zkp_worker_commit_open_resident(self._h, i, n, generation, x_be, com, y, proof))
+        return com.raw, y.raw, proof.raw
 
     def resident_generation(self) -> Tuple[int, int]:
         """(generation, n) of the polynomial the last upload left on the device; see worker_open_resident_gen."""
@@ -634,6 +672,9 @@ def wire() -> ctypes.PyDLL:
         h.zkp_wire_decode_list_cmp.argtypes = [ctypes.py_object, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p,
                                                ctypes.POINTER(ctypes.c_int)]
         h.zkp_wire_decode_list_cmp.restype = ctypes.c_longlong
+        h.zkp_wire_decode_list_chunked.argtypes = [ctypes.py_object, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_size_t,
+                                                   ctypes.c_void_p, ctypes.c_void_p]
+        h.zkp_wire_decode_list_chunked.restype = ctypes.c_longlong
         h.zkp_wire_encode_list.argtypes = [ctypes.c_char_p, ctypes.c_size_t]
         h.zkp_wire_encode_list.restype = ctypes.py_object
         _wire = h
