@@ -97,6 +97,18 @@ class ClockSampler:
                 "power_w_max": max(power) if power else None, "samples": len(sm), "reasons": sorted(reasons)}
 
 
+def workload_config(log_n: int, world: int) -> dict:
+    """`config` of the JSON line: ONE description of the workload, identical for our arm and for --impl reference"""
+    return {"workload": f"KZG commit+open of a random degree-2^{log_n} polynomial in evaluation form over BLS12-381 "
+                        f"(BASELINE configs[2]); Lagrange SRS from the public test trapdoor; "
+                        f"N>1 = Pianist split of ONE global vector, one sub-polynomial per GPU, 192-byte exchange + sum "
+                        f"inside every timed step",
+            "log_n": log_n, "rows": 1 << (world - 1).bit_length(),
+            "l2": "GPU arm: flushed (256 MiB memset) before every timed iteration of `value`; e2e working set "
+                  "(fixed-base tables 3.25 GiB gathered at random + sorted entry pairs 104 MiB + buckets 96 MiB) exceeds the 126 MB L2",
+            "seed": "0xB200+3 (one global stream; rank r owns elements [r n, (r+1) n))"}
+
+
 def dist_env():
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -152,9 +164,9 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": sec_per_step * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "u64", "data": "synthetic",
-        "config": {"workload": f"KZG commit+open of a random degree-2^{log_n} polynomial in evaluation form over BLS12-381 "
-                               f"(BASELINE configs[2]); CPU restatement of the reference prover (the Rust `fourier` binary "
-                               f"cannot be built offline), every step at the full size", "log_n": log_n},
+        "config": workload_config(log_n, max(1, args.gpus)),
+        "arm": "CPU restatement of the reference prover (the Rust `fourier` binary cannot be built offline); every step is a "
+               "commit+open at the full size on all host threads; at N > 1 rank 0 alone runs it (one sub-polynomial)",
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port",
                          "sample": f"{args.steps} real commit+open steps at n=2^{log_n} on {threads} host threads "
                                    f"({sec_per_step:.2f} s each, min {min(times):.2f} max {max(times):.2f}); "
@@ -501,14 +513,8 @@ def main():
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": t_job / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "u32", "data": "synthetic",
-        "config": {"workload": f"KZG commit+open of a random degree-2^{log_n} polynomial in evaluation form over BLS12-381 "
-                               f"(BASELINE configs[2]); Lagrange SRS from the public test trapdoor; "
-                               f"N>1 = Pianist split of ONE global vector, one sub-polynomial per GPU, 192-byte gather + sum "
-                               f"inside every timed step",
-                   "log_n": log_n, "msm_window_bits": c, "msm_windows": W, "rows": 1 << log_m,
-                   "l2": "flushed (256 MiB memset) before every timed iteration of `value`; e2e working set "
-                         "(fixed-base tables 3.25 GiB gathered at random + sorted entry pairs 104 MiB + buckets 96 MiB) exceeds the 126 MB L2",
-                   "seed": "0xB200+3 (one global stream; rank r owns elements [r n, (r+1) n))"},
+        "config": workload_config(log_n, world),
+        "msm_plan": {"window_bits": c, "windows": W, "fixed_base_tables": True},
         "gpu_launches": int(launches) * args.steps,
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": n * 32 + 32,
