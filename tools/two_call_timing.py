@@ -18,7 +18,7 @@ cl.worker_open(0, strs, xs)  # allocates the second page-locked staging buffer (
 for rep in range(3):
     a, r1 = t(lambda: cl.worker_commit(0, strs))
     b, r2 = t(lambda: cl.worker_open(0, strs, xs))
-    ctx.random_point(1); cl._resident_n = 0
+    ctx.random_point(1); cl._slots[0].resident_n = 0
     c, r3 = t(lambda: cl.worker_open(0, strs, xs))
     d, r4 = t(lambda: cl.worker_commit_and_open(0, strs, xs))
     assert r2.json() == r3.json() and r4.json()["proof"] == r2.json()["proof"]
