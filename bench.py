@@ -9,10 +9,10 @@ A step = one commit + open of one random degree-2^20 polynomial given in evaluat
 configs[2]; the largest single-GPU configuration on which the metric is quoted).  For N > 1 the job is the
 Pianist split of north_star / configs[4]: ONE global vector of N x 2^20 evaluations, sub-polynomial (SRS row) r on
 GPU r, no collective on the inner loop; EVERY timed step ends with the cross-GPU combine (each rank contributes its
-two partial points uncompressed, 192 bytes, rank 0 adds them) -- measured inside the loop, not added afterwards -- and
+two partial points as Jacobian coordinates, 288 bytes, rank 0 adds them and compresses once) -- measured inside the loop, not added afterwards -- and
 after the loop rank 0 checks the aggregate against the oracle and with the master node's pairing check.  Weak scaling.
 Launch for N > 1:  python -m torch.distributed.run --nproc-per-node N bench.py ...   (torch is used only for the
-process group: barrier, max-over-ranks, the 192-byte gather).
+process group: barrier, max-over-ranks; the 288-byte exchange itself goes through host shared memory).
 
 The same jobs are then run through the IN-LIBRARY multi-GPU entries (zkp_mgpu_*: one process, one host thread per
 device, no torch) by rank 0 over all N devices while the other ranks wait, and must give the same bytes
@@ -101,7 +101,7 @@ def workload_config(log_n: int, world: int) -> dict:
     """`config` of the JSON line: ONE description of the workload, identical for our arm and for --impl reference"""
     return {"workload": f"KZG commit+open of a random degree-2^{log_n} polynomial in evaluation form over BLS12-381 "
                         f"(BASELINE configs[2]); Lagrange SRS from the public test trapdoor; "
-                        f"N>1 = Pianist split of ONE global vector, one sub-polynomial per GPU, 192-byte exchange + sum "
+                        f"N>1 = Pianist split of ONE global vector, one sub-polynomial per GPU, 288-byte exchange + sum "
                         f"inside every timed step",
             "log_n": log_n, "rows": 1 << (world - 1).bit_length(),
             "l2": "GPU arm: flushed (256 MiB memset) before every timed iteration of `value`; e2e working set "
@@ -253,14 +253,14 @@ def main():
         if dist is not None:
             dist.barrier()
 
-    gather = None
+    gather = hx = None
     if dist is not None:
         if args.combine == "nccl":
-            g_nccl = Gatherer(dist, local, 192)
+            g_nccl = Gatherer(dist, local, 288)
             gather = lambda step, mine: g_nccl(mine)  # noqa: E731
         else:
             from zkp_subnet_b200 import sharding
-            hx = sharding.HostExchange(rank, world, 192, os.environ.get("MASTER_PORT", "0"))
+            hx = sharding.HostExchange(rank, world, 288, os.environ.get("MASTER_PORT", "0"))
             dist.barrier()
             hx.attach()
             gather = hx.gather
@@ -268,13 +268,13 @@ def main():
     step_no = [0]
 
     def combine():
-        """the cross-GPU step of the Pianist job: 192 bytes per rank (host-resident results, exchanged host to host),
-        rank 0 adds 2 x N affine points and compresses the two sums"""
+        """the cross-GPU step of the Pianist job: 288 bytes per rank (host-resident results, exchanged host to host),
+        rank 0 adds 2 x N Jacobian points and compresses the two sums (two field inversions per step in the whole job)"""
         step_no[0] += 1
-        parts = gather(step_no[0], ctx.last_points_uncompressed())
+        parts = gather(step_no[0], ctx.last_points_jacobian())  # 2 x 144 bytes per rank, no inversion on the ranks
         if rank == 0:
-            agg[0] = (native.g1_sum_uncompressed(b"".join(p[:96] for p in parts)),
-                      native.g1_sum_uncompressed(b"".join(p[96:] for p in parts)))
+            cat = b"".join(parts)
+            agg[0] = (native.g1_sum_jacobian(cat, world, 288), native.g1_sum_jacobian(cat[144:], world, 288))
 
     # ---- device-timed value: polynomial resident in HBM, L2 flushed between iterations; at N > 1 every step
     #      includes its combine (wall clock of gather + sum, added to the device time of the same step)
@@ -419,9 +419,9 @@ def main():
 
         def combine24():
             step_no[0] += 1
-            parts = g24(step_no[0], ctx24.last_points_uncompressed())
+            parts = g24(step_no[0], ctx24.last_points_jacobian())
             if rank == 0:
-                full24[0] = native.g1_sum_uncompressed(b"".join(p[:96] for p in parts))
+                full24[0] = native.g1_sum_jacobian(b"".join(parts), world, 288)
         if g24:
             combine24()
         barrier()
@@ -472,6 +472,9 @@ def main():
         if dist is not None:
             dist.barrier(group=host_group)
 
+    if hx is not None:
+        dist.barrier()
+        hx.close()
     if rank != 0:
         if dist is not None:
             dist.barrier()
@@ -546,9 +549,9 @@ def main():
         "msm_sharded": msm24,
         "mgpu_in_library": mgpu,
         "combine_ms_per_step": t_comb_max / args.steps,
-        "combine_note": "measured INSIDE the timed loop of `value` (and of e2e) at N > 1: every rank serialises its two partial "
-                        "points (192 bytes, uncompressed, no square root) and publishes them; rank 0 waits for all ranks, adds "
-                        "2 x N affine points, compresses the two sums.  transport = " + args.combine +
+        "combine_note": "measured INSIDE the timed loop of `value` (and of e2e) at N > 1: every rank publishes its two partial "
+                        "points as Jacobian coordinates (288 bytes, no inversion, no square root); rank 0 waits for all ranks, adds "
+                        "2 x N points, compresses the two sums.  transport = " + args.combine +
                         " (host: POSIX shared memory -- the partials are host-resident, the window fold runs on the host; "
                         "nccl: H2D + all_gather + D2H of the same bytes)",
         "table_prebuild_s": t_tables,
@@ -600,16 +603,27 @@ def mgpu_leg(native, args, world, log_n, log_m, x, all_parts, single, agg, msm24
         polys = native.PinnedBuffer(32 * n * world).write(mg.ctx(0).random_poly_range(SEED_POLY, 0, n * world))
         rows = list(range(world))
         res = mg.pianist_commit_open(rows, polys, x)  # uploads; warm
+        ctxs = [mg.ctx(k) for k in range(world)]
+
+        def flush_all():  # the L2 rule of the main loop: every device's L2 flushed between timed calls (outside the timing)
+            for c in ctxs:
+                c.bench_flush_l2()
         for _ in range(3):
             mg.pianist_commit_open(rows, polys, x, native.MGPU_RESIDENT)
-        t0 = time.perf_counter()
+        dt = 0.0
         for _ in range(K):
+            flush_all()
+            t0 = time.perf_counter()
             res_r = mg.pianist_commit_open(rows, polys, x, native.MGPU_RESIDENT)
-        dt = (time.perf_counter() - t0) / K
-        t0 = time.perf_counter()
+            dt += time.perf_counter() - t0
+        dt /= K
+        dte = 0.0
         for _ in range(K):
+            flush_all()
+            t0 = time.perf_counter()
             res_e = mg.pianist_commit_open(rows, polys, x)
-        dte = (time.perf_counter() - t0) / K
+            dte += time.perf_counter() - t0
+        dte /= K
         assert res == res_r == res_e
         if all_parts is not None:
             assert [c + y + p for c, y, p in zip(res[0], res[1], res[2])] == all_parts, "in-library and per-rank answers differ"
@@ -619,7 +633,8 @@ def mgpu_leg(native, args, world, log_n, log_m, x, all_parts, single, agg, msm24
         out["pianist"] = {"commit_open_per_s_resident": world / dt, "ms_per_step_resident": dt * 1e3,
                           "commit_open_per_s_e2e_pinned": world / dte, "ms_per_step_e2e": dte * 1e3, "steps": K,
                           "matches_per_rank_run": True,
-                          "note": "wall clock around the library call, host-side fold + sum + compression included; "
+                          "note": "wall clock around each library call (L2 of every device flushed between calls, outside the "
+                                  "timing), host-side fold + sum + compression included; "
                                   "resident = ZKP_MGPU_RESIDENT (no upload); e2e = N x 32 MiB from page-locked memory every step"}
         polys.close()
     # one polynomial split by point range over the N GPUs: 2^20 commit+open latency and the 2^24 MSM
@@ -629,16 +644,23 @@ def mgpu_leg(native, args, world, log_n, log_m, x, all_parts, single, agg, msm24
             mg.prebuild_tables()
             p1 = native.PinnedBuffer(32 * n).write(mg.ctx(0).random_poly_range(SEED_POLY, 0, n))
             r0 = mg.commit_open(0, p1, x)
+            ctxs = [mg.ctx(k) for k in range(world)]
             for _ in range(3):
                 mg.commit_open(0, p1, x, native.MGPU_RESIDENT)
-            t0 = time.perf_counter()
+            dt = dte = 0.0
             for _ in range(K):
+                for c in ctxs:
+                    c.bench_flush_l2()
+                t0 = time.perf_counter()
                 r1 = mg.commit_open(0, p1, x, native.MGPU_RESIDENT)
-            dt = (time.perf_counter() - t0) / K
-            t0 = time.perf_counter()
+                dt += time.perf_counter() - t0
             for _ in range(K):
+                for c in ctxs:
+                    c.bench_flush_l2()
+                t0 = time.perf_counter()
                 r2 = mg.commit_open(0, p1, x)
-            dte = (time.perf_counter() - t0) / K
+                dte += time.perf_counter() - t0
+            dt, dte = dt / K, dte / K
             assert r0 == r1 == r2
             if world == 1 or log_m == 0:
                 assert r0 == single, "point-range split differs from the single-GPU answer"
@@ -652,14 +674,18 @@ def mgpu_leg(native, args, world, log_n, log_m, x, all_parts, single, agg, msm24
                 sc = native.PinnedBuffer(32 << lg24).write(mg.ctx(0).random_poly_range(SEED_MSM24, 0, 1 << lg24))
                 c0 = mg.msm_g1(0, sc)  # uploads, builds the tables
                 mg.msm_g1(0, sc, native.MGPU_RESIDENT)
-                t0 = time.perf_counter()
+                dt = 0.0
                 for _ in range(3):
+                    for k in range(world):
+                        mg.ctx(k).bench_flush_l2()
+                    t0 = time.perf_counter()
                     c1 = mg.msm_g1(0, sc, native.MGPU_RESIDENT)
-                dt = (time.perf_counter() - t0) / 3
+                    dt += time.perf_counter() - t0
+                dt /= 3
                 assert c0 == c1 and c0.hex() == msm24["commitment"], "in-library sharded MSM differs from the per-rank run"
                 out["msm_2p24"] = {"ms_resident": dt * 1e3, "mpts_per_s": (1 << lg24) / dt / 1e6, "matches_per_rank_run": True,
                                    "note": "wall clock around zkp_mgpu_msm_g1 (host fold, sum of N Jacobian partials and one "
-                                           "compression included), scalars resident, no L2 flush"}
+                                           "compression included), scalars resident, L2 flushed between calls"}
                 sc.close()
     return out
 

@@ -99,6 +99,12 @@ int zkp_g1_uncompress(const uint8_t in48[48], uint8_t out96[96]);
 /* commitment || proof of the last commit+open on this context, 2 x 96 bytes uncompressed (no square root anywhere in
  * a cross-process combine: every rank contributes these, rank 0 adds them with zkp_g1_sum_uncompressed) */
 int zkp_last_points_uncompressed(zkp_ctx* ctx, uint8_t out192[192]);
+/* the same as two JACOBIAN points (X, Y, Z: 3 x 48 bytes of this library's Montgomery limbs each; Z = 0 = infinity): no
+ * field inversion on the contributing rank at all.  zkp_g1_sum_jacobian adds `count` such records (`stride` >= 144
+ * bytes apart; each checked to be on the curve) and compresses the sum.  Internal representation: only for exchange
+ * between processes of the same build on one box (the multi-process combine of bench.py). */
+int zkp_last_points_jacobian(zkp_ctx* ctx, uint8_t out288[288]);
+int zkp_g1_sum_jacobian(const uint8_t* points, size_t count, size_t stride, uint8_t out48[48]);
 int zkp_g1_sum_uncompressed(const uint8_t* points96, size_t count, uint8_t out48[48]);
 /* import one row from 96-byte ZCash-uncompressed points (validated on curve), and its scale point */
 int zkp_srs_set_shape(zkp_ctx* ctx, uint32_t log_n, uint32_t log_machines);
@@ -264,6 +270,8 @@ int zkp_bench_commit_open(zkp_ctx* ctx, uint32_t row, const uint8_t* poly_be, si
                           int reps, int flush_l2, float* ms_per_iter, float* ms_msm_kernel, uint32_t* launches,
                           uint8_t commitment48[48], uint8_t eval_be[32], uint8_t proof48[48]);
 int zkp_bench_last_kernel_ms(zkp_ctx* ctx, float* ms);
+/* flush the L2 of the context's device (256 MiB memset) and wait: for timing loops outside the library */
+int zkp_bench_flush_l2(zkp_ctx* ctx);
 /* stage timeline of one commit+open (CUDA events between the pipeline stages of both lanes): text lines
  * "<lane> <stage> <ms since request start>" and a final "host total <ms>" */
 int zkp_bench_trace(zkp_ctx* ctx, uint32_t row, const uint8_t* poly_be, size_t n, const uint8_t x_be[32], int warm,

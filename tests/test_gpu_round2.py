@@ -197,6 +197,33 @@ def test_forked_contexts_share_the_srs_and_run_concurrently(gpu_ctx):
     assert gpu_ctx.worker_commit_open(0, polys[0], x) == want[0]
 
 
+def test_partial_point_exports_for_the_multi_process_combine(gpu_ctx):
+    """zkp_last_points_uncompressed / _jacobian and their sums: what the ranks of bench.py exchange per step."""
+    log_n = 8
+    n = 1 << log_n
+    gpu_ctx.srs_generate(TAU_X, TAU_Y, log_n, 1)
+    outs, unc, jac = [], [], []
+    for i in range(2):
+        outs.append(gpu_ctx.worker_commit_open(i, ref.random_scalars(40 + i, n), ref.random_scalars(50, 1)))
+        unc.append(gpu_ctx.last_points_uncompressed())
+        jac.append(gpu_ctx.last_points_jacobian())
+    want_c = native.g1_sum(outs[0][0] + outs[1][0])
+    want_p = native.g1_sum(outs[0][2] + outs[1][2])
+    assert native.g1_sum_uncompressed(unc[0][:96] + unc[1][:96]) == want_c
+    assert native.g1_sum_uncompressed(unc[0][96:] + unc[1][96:]) == want_p
+    cat = jac[0] + jac[1]
+    assert native.g1_sum_jacobian(cat, 2, 288) == want_c and native.g1_sum_jacobian(cat[144:], 2, 288) == want_p
+    assert native.g1_sum_jacobian(jac[0], 1, 288) == outs[0][0]
+    bad = bytearray(cat)
+    bad[5] ^= 1
+    with pytest.raises(native.ZkpError):
+        native.g1_sum_jacobian(bytes(bad), 2, 288)
+    gpu_ctx.msm_g1(0, ref.random_scalars(41, n))        # an MSM alone: commitment slot = the result, proof slot = infinity
+    j = gpu_ctx.last_points_jacobian()
+    assert native.g1_sum_jacobian(j, 1, 288) == gpu_ctx.msm_g1(0, ref.random_scalars(41, n))
+    assert native.g1_sum_jacobian(j[144:], 1, 144) == b"\xc0" + bytes(47)
+
+
 def test_resident_open_is_bound_to_its_upload(gpu_ctx):
     log_n = 8
     n = 1 << log_n

@@ -827,6 +827,44 @@ int zkp_worker_commit_open_resident(zkp_ctx* ctx, uint32_t i, size_t n, uint64_t
     if (rc) return rc;
     return commit_open_resident(ctx, i, n, x, commitment48, eval_be, proof48);
 }
+// The same two results as JACOBIAN points (X, Y, Z as 3 x 48 bytes of Montgomery limbs each, Z = 0 for infinity; 288
+// bytes): a rank of a multi-process job hands these over without ANY field inversion, and zkp_g1_sum_jacobian on the
+// combining rank adds them and compresses once.  The bytes are this library's internal representation: only for
+// exchange between processes running the same build on the same box.
+int zkp_last_points_jacobian(zkp_ctx* ctx, uint8_t out288[288]) {
+    if (!ctx || !out288) return fail(ZKP_ERR_ARG, "null argument");
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    if (!ctx->have_last) return fail(ZKP_ERR_STATE, "no commit+open has completed on this context");
+    const host::G1J* pts[2] = {&ctx->last_com, &ctx->last_proof};
+    for (int k = 0; k < 2; k++) {
+        memcpy(out288 + 144 * k, pts[k]->x.v, 48);
+        memcpy(out288 + 144 * k + 48, pts[k]->y.v, 48);
+        memcpy(out288 + 144 * k + 96, pts[k]->z.v, 48);
+    }
+    return ZKP_OK;
+}
+// sum of `count` Jacobian points of `stride` bytes each (the first 144 bytes of every record are read) -> compressed
+int zkp_g1_sum_jacobian(const uint8_t* points, size_t count, size_t stride, uint8_t out48[48]) {
+    if (!points || !out48 || stride < 144) return fail(ZKP_ERR_ARG, "bad argument");
+    host::G1J acc = host::G1J::infinity();
+    for (size_t k = 0; k < count; k++) {
+        host::G1J p;
+        memcpy(p.x.v, points + stride * k, 48);
+        memcpy(p.y.v, points + stride * k + 48, 48);
+        memcpy(p.z.v, points + stride * k + 96, 48);
+        for (int i = 0; i < 3; i++) {
+            const uint64_t* v = i == 0 ? p.x.v : (i == 1 ? p.y.v : p.z.v);
+            if (Fq64::geq_mod(v)) return fail(ZKP_ERR_ENCODING, "coordinate out of range");
+        }
+        if (!p.is_inf()) {  // on the curve:  Y^2 = X^3 + 4 Z^6
+            Fq64 z2 = p.z.sqr(), z6 = z2.sqr() * z2;
+            if (p.y.sqr() != p.x.sqr() * p.x + host::fq_b4() * z6) return fail(ZKP_ERR_ENCODING, "point " + std::to_string(k) + " is not on the curve");
+        }
+        acc = acc.add(p);
+    }
+    host::g1_compress(out48, acc);
+    return ZKP_OK;
+}
 int zkp_resident_generation(zkp_ctx* ctx, uint64_t* generation, size_t* n) {
     if (!ctx || !generation) return fail(ZKP_ERR_ARG, "null argument");
     std::lock_guard<std::mutex> lk(ctx->mu);
@@ -1668,6 +1706,17 @@ int zkp_bench_trace(zkp_ctx* ctx, uint32_t row, const uint8_t* poly_be, size_t n
     if (text.size() + 1 > out_cap) return fail(ZKP_ERR_ARG, "trace buffer too small");
     memcpy(out, text.c_str(), text.size() + 1);
     return rc;
+}
+
+// write a buffer larger than the L2 (256 MiB) and wait: what the bench entries do between their timed iterations, exposed
+// for timing loops that live outside the library (bench.py around the zkp_mgpu_* entries)
+int zkp_bench_flush_l2(zkp_ctx* ctx) {
+    if (!ctx) return fail(ZKP_ERR_ARG, "null context");
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    DeviceGuard g(ctx->device);
+    flush_l2(ctx);
+    ZKP_CUDA(cudaStreamSynchronize(ctx->stream));
+    return ZKP_OK;
 }
 
 // measured issue peaks on this device: IMAD.WIDE.U32 per second (whole chip) and dependent-chain Fq

@@ -11,6 +11,8 @@
 //                           polynomial is split by point range: zkp_mgpu_msm_g1, zkp_mgpu_commit_open.
 // Included at the end of zkp_b200.cu (uses the internals of capi_rest.cuh).
 #pragma once
+#include <atomic>
+#include <chrono>
 #include <condition_variable>
 #include <functional>
 #include <thread>
@@ -21,12 +23,17 @@ struct zkp_mgpu {
     int layout = 0;
     uint32_t log_n = 0, log_m = 0, log_shards = 0;  // log_n = FULL row length
     std::mutex mu;                                   // one multi-device call at a time
+    // Job handoff: a mutex + condition variable for the idle case, and an atomic sequence pair that both sides SPIN on
+    // for a bounded time first -- a futex wake of a sleeping thread costs 50-100 us each way, which is most of what a
+    // multi-device call adds to a 12 ms step; a worker that has just finished a job spins ~200 us for the next one (a
+    // prover in a loop) before it goes to sleep, the caller spins for completion (it has nothing else to do).
     struct Worker {
         std::thread th;
         std::mutex m;
         std::condition_variable cv;
         std::function<int()> job;
-        bool has_job = false, done = false, quit = false;
+        std::atomic<uint64_t> posted{0}, finished{0};  // jobs handed over / completed
+        bool quit = false;
         int rc = 0;
         std::string err;
     };
@@ -45,37 +52,48 @@ namespace {
 
 void mgpu_worker_main(zkp_mgpu::Worker* w, int device) {
     cudaSetDevice(device);
-    std::unique_lock<std::mutex> lk(w->m);
+    uint64_t seen = 0;
     for (;;) {
-        w->cv.wait(lk, [&] { return w->has_job || w->quit; });
-        if (w->quit) return;
-        w->has_job = false;
-        lk.unlock();
+        // wait for job number seen + 1: spin briefly, then sleep
+        const auto spin_until = std::chrono::steady_clock::now() + std::chrono::microseconds(200);
+        bool got = false;
+        while (std::chrono::steady_clock::now() < spin_until) {
+            if (w->posted.load(std::memory_order_acquire) > seen) { got = true; break; }
+        }
+        if (!got) {
+            std::unique_lock<std::mutex> lk(w->m);
+            w->cv.wait(lk, [&] { return w->posted.load(std::memory_order_acquire) > seen || w->quit; });
+            if (w->quit) return;
+        }
+        seen++;
         int rc = w->job();
-        std::string err = rc ? tls_error() : std::string();
-        lk.lock();
         w->rc = rc;
-        w->err = err;
-        w->done = true;
-        w->cv.notify_all();
+        w->err = rc ? tls_error() : std::string();
+        w->finished.store(seen, std::memory_order_release);
     }
 }
 
 // run fn(k) on the worker of device k for k < count; the first failure (message included) is returned to the caller
 int mgpu_run(zkp_mgpu* mg, uint32_t count, const std::function<int(uint32_t)>& fn) {
+    std::vector<uint64_t> want(count);
     for (uint32_t k = 0; k < count; k++) {
         zkp_mgpu::Worker& w = *mg->workers[k];
-        std::lock_guard<std::mutex> lk(w.m);
-        w.job = [&fn, k] { return fn(k); };
-        w.done = false;
-        w.has_job = true;
+        {
+            std::lock_guard<std::mutex> lk(w.m);  // orders the job object before the sequence number for a sleeping worker
+            w.job = [&fn, k] { return fn(k); };
+            want[k] = w.posted.load(std::memory_order_relaxed) + 1;
+            w.posted.store(want[k], std::memory_order_release);
+        }
         w.cv.notify_all();
     }
     int rc = ZKP_OK;
     for (uint32_t k = 0; k < count; k++) {
         zkp_mgpu::Worker& w = *mg->workers[k];
-        std::unique_lock<std::mutex> lk(w.m);
-        w.cv.wait(lk, [&] { return w.done; });
+        while (w.finished.load(std::memory_order_acquire) < want[k]) {
+#if defined(__x86_64__)
+            __builtin_ia32_pause();
+#endif
+        }
         if (w.rc && !rc) rc = fail(w.rc, "device " + std::to_string(mg->devices[k]) + ": " + w.err);
     }
     return rc;
@@ -205,8 +223,8 @@ void zkp_mgpu_destroy(zkp_mgpu* mg) {
         {
             std::lock_guard<std::mutex> lk(w->m);
             w->quit = true;
-            w->cv.notify_all();
         }
+        w->cv.notify_all();
         w->th.join();
     }
     for (zkp_ctx* c : mg->ctxs) zkp_ctx_destroy(c);
@@ -391,8 +409,13 @@ int zkp_mgpu_pianist_commit_open(zkp_mgpu* mg, const uint32_t* rows, size_t coun
     std::lock_guard<std::mutex> lk(mg->mu);
     const uint32_t active = count < G ? (uint32_t)count : G;
     std::vector<host::G1J> com(active, host::G1J::infinity()), prf(active, host::G1J::infinity());
+    static const bool trace = getenv("ZKP_MGPU_TRACE") != nullptr;
+    const auto t_call = std::chrono::steady_clock::now();
+    std::vector<double> t_start(active, 0), t_conv(active, 0), t_done(active, 0);
+    auto since = [&] { return std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - t_call).count(); };
     rc = mgpu_run(mg, active, [&](uint32_t g) -> int {
         zkp_ctx* ctx = mg->ctxs[g];
+        t_start[g] = since();
         std::lock_guard<std::mutex> lk2(ctx->mu);
         DeviceGuard dg(ctx->device);
         for (size_t k = g; k < count; k += G) {
@@ -404,7 +427,9 @@ int zkp_mgpu_pianist_commit_open(zkp_mgpu* mg, const uint32_t* rows, size_t coun
                 r = upload_poly(ctx, polys_be + 32 * n * k, n, true);
             }
             host::G1J cj, pj;
+            t_conv[g] = since();
             if (!r) r = commit_open_resident(ctx, rows[k], n, x, commitments48 + 48 * k, evals_be + 32 * k, proofs48 + 48 * k, &cj, &pj);
+            t_done[g] = since();
             if (r) return r;
             ctx->resident_n = n;
             com[g] = com[g].add(cj);
@@ -418,8 +443,14 @@ int zkp_mgpu_pianist_commit_open(zkp_mgpu* mg, const uint32_t* rows, size_t coun
         c = c.add(com[g]);
         p = p.add(prf[g]);
     }
+    const double t_joined = since();
     if (agg_commitment48) host::g1_compress(agg_commitment48, c);
     if (agg_proof48) host::g1_compress(agg_proof48, p);
+    if (trace) {
+        fprintf(stderr, "zkp_mgpu_pianist: joined %.0f us, total %.0f us;", t_joined, since());
+        for (uint32_t g = 0; g < active; g++) fprintf(stderr, " dev%u start %.0f conv %.0f done %.0f;", g, t_start[g], t_conv[g], t_done[g]);
+        fprintf(stderr, "\n");
+    }
     return ZKP_OK;
 }
 

@@ -47,6 +47,8 @@ _SIGNATURES = {
     "zkp_g1_sum_checked": [_u8p, ctypes.c_size_t, _u8p],
     "zkp_g1_uncompress": [_u8p, _u8p],
     "zkp_last_points_uncompressed": [_ctxp, _u8p],
+    "zkp_last_points_jacobian": [_ctxp, _u8p],
+    "zkp_g1_sum_jacobian": [_u8p, ctypes.c_size_t, ctypes.c_size_t, _u8p],
     "zkp_g1_sum_uncompressed": [_u8p, ctypes.c_size_t, _u8p],
     "zkp_shard_eval_partial": [_ctxp, ctypes.c_uint32, _u8p, ctypes.c_size_t, _u8p, _u8p],
     "zkp_shard_eval_combine": [_u8p, ctypes.c_size_t, ctypes.c_uint32, _u8p, _u8p],
@@ -112,6 +114,7 @@ _SIGNATURES = {
     "zkp_bench_trace": [_ctxp, ctypes.c_uint32, _u8p, ctypes.c_size_t, _u8p, ctypes.c_int, ctypes.c_char_p, ctypes.c_size_t],
     "zkp_bench_ntt": [_ctxp, ctypes.c_size_t, ctypes.c_int, ctypes.c_int, ctypes.POINTER(ctypes.c_float)],
     "zkp_bench_last_kernel_ms": [_ctxp, ctypes.POINTER(ctypes.c_float)],
+    "zkp_bench_flush_l2": [_ctxp],
     "zkp_bench_peaks": [_ctxp, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_double)],
     "zkp_set_msm_mode": [_ctxp, ctypes.c_int],
     "zkp_set_msm_window": [_ctxp, ctypes.c_uint32],
@@ -367,6 +370,12 @@ class Context:
         check(lib().zkp_worker_commit_open_resident(self._h, i, n, generation, x_be, com, y, proof))
         return com.raw, y.raw, proof.raw
 
+    def last_points_jacobian(self) -> bytes:
+        """commitment || proof of the last commit+open as Jacobian points (2 x 144 bytes, internal limbs; no inversion)"""
+        out = ctypes.create_string_buffer(288)
+        check(lib().zkp_last_points_jacobian(self._h, out))
+        return out.raw
+
     def resident_generation(self) -> Tuple[int, int]:
         """(generation, n) of the polynomial the last upload left on the device; see worker_open_resident_gen."""
         g, n = ctypes.c_uint64(), ctypes.c_size_t()
@@ -545,6 +554,9 @@ class Context:
             a, b, c = line.split()
             rows.append((a, b, float(c)))
         return rows
+
+    def bench_flush_l2(self) -> None:
+        check(lib().zkp_bench_flush_l2(self._h))
 
     def bench_last_kernel_ms(self) -> float:
         ms = ctypes.c_float()
@@ -734,6 +746,13 @@ def g1_sum_checked(points48: bytes) -> bytes:
     """sum of points received from other parties: each is checked to be in the prime-order subgroup"""
     out = ctypes.create_string_buffer(48)
     check(lib().zkp_g1_sum_checked(points48, len(points48) // 48, out))
+    return out.raw
+
+
+def g1_sum_jacobian(points: bytes, count: int, stride: int) -> bytes:
+    """sum of `count` Jacobian points (records of `stride` >= 144 bytes, see Context.last_points_jacobian) -> compressed"""
+    out = ctypes.create_string_buffer(48)
+    check(lib().zkp_g1_sum_jacobian(points, count, stride, out))
     return out.raw
 
 
