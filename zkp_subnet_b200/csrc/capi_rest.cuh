@@ -1676,9 +1676,13 @@ int zkp_bench_trace(zkp_ctx* ctx, uint32_t row, const uint8_t* poly_be, size_t n
     uint8_t c48[48], y32[32], p48[48];
     for (int r = 0; r < warm && !rc; r++) rc = commit_open_resident(ctx, row, n, x, c48, y32, p48);
     if (rc) return rc;
-    flush_l2(ctx);
+    // ZKP_TRACE_FLUSH: "none" = no flush, "sync" = flush and wait, default = flush enqueued right in front (as zkp_bench_*)
+    const char* fm = getenv("ZKP_TRACE_FLUSH");
+    const bool f_none = fm && !strcmp(fm, "none"), f_sync = fm && !strcmp(fm, "sync");
     ZKP_CUDA(cudaStreamSynchronize(ctx->stream));
     ZKP_CUDA(cudaStreamSynchronize(ctx->stream2));
+    if (!f_none) flush_l2(ctx);
+    if (f_sync) ZKP_CUDA(cudaStreamSynchronize(ctx->stream));
     cudaEvent_t base;
     ZKP_CUDA(cudaEventCreate(&base));
     ctx->trace.clear();
