@@ -1,5 +1,7 @@
 """Randomised differential test on the GPU: MSM / commit+open against the oracle over random sizes, window widths,
-table modes, batched-affine rounds and scalar shapes.  usage: python tools/fuzz_msm.py [cases]"""
+table modes, batched-affine rounds, scalar shapes, and the shapes of the request (two lanes, one grouped launch set, the
+batched entry, a forked context, the in-library multi-device entries on one device).
+usage: python tools/fuzz_msm.py [cases]"""
 import os, random, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from oracle import ref
@@ -45,9 +47,35 @@ for case in range(cases):
     ok = got == exp
     if ok and m == n and lg >= 3 and rng.random() < 0.4:
         x = ref.random_scalars(case, 1)
+        ctx.set_fuse(rng.choice([-1, 0, 1]))
         com, y, proof = ctx.worker_commit_open(0, sc, x)
+        ctx.set_fuse(-1)
         ey, eproof = ref.open_evals(sc, x, srs, 8)
         ok = (com, y, proof) == (exp, ey, eproof) and ctx.worker_verify(0, proof, x, y, com)
+        if ok and rng.random() < 0.5:
+            # the same request inside a batch (with a second, random polynomial), on a forked context
+            other = ref.random_scalars(1000 + case, n)
+            x2 = ref.random_scalars(2000 + case, 1)
+            ctx.set_msm_affine_rounds(-1)
+            f = ctx.fork()
+            out = f.worker_commit_open_batch([0, 0], [sc, other], x + x2)
+            f.close()
+            ok = out[0] == (0, com, y, proof) and out[1][0] == 0 and out[1][1] == ref.msm(srs, other, 8) and \
+                (out[1][2], out[1][3]) == ref.open_evals(other, x2, srs, 8)
+        if ok and rng.random() < 0.3:
+            ctx.set_msm_window(0)
+            with native.MultiContext([0]) as mg:
+                for k, layout in enumerate((native.LAYOUT_ROWS, native.LAYOUT_POINT_RANGE)):
+                    c0 = mg.ctx(0)
+                    c0.srs_set_shape(lg, 0)
+                    c0.srs_import_row(0, srs)
+                    c0.srs_import_g2_tau(TAU[0])
+                    mg.set_layout(layout, lg, 0)
+                    if layout == native.LAYOUT_ROWS:
+                        r = mg.pianist_commit_open([0], sc, x)
+                        ok = ok and (r[0][0], r[1][0], r[2][0], r[3], r[4]) == (com, y, proof, com, proof)
+                    else:
+                        ok = ok and mg.commit_open(0, sc, x) == (com, y, proof) and mg.msm_g1(0, sc) == com
     if not ok:
         bad += 1
         print(f"MISMATCH case {case}: lg={lg} shape={shape} m={m}", flush=True)
