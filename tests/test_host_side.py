@@ -220,3 +220,63 @@ def test_setup_cli_argument_checks(tmp_path):
     assert r.returncode == 1 and "--overwrite" in r.stderr and (tmp_path / "s").read_bytes() == b"x"
     r = subprocess.run(base[:-4] + ["--scale", "2", "--machines-scale", "3", "--generate-setup"], cwd=root, capture_output=True, text=True)
     assert r.returncode == 2
+
+
+def _pool_poly(n, seed):
+    import random
+    rng = random.Random(seed)
+    raw = b"".join(rng.randrange(o.R).to_bytes(32, "big") for _ in range(n))
+    return raw, encode_poly(raw)
+
+
+def test_codec_pool_concurrent_callers_and_fork():
+    """The codec's persistent worker pool (csrc/codec.hpp WorkerPool): repeated calls reuse it, callers that find it busy
+    fall back to fresh threads, and a fork()ed child (which has no workers) builds its own."""
+    import threading
+    n = 1 << 15  # enough elements for several codec threads
+    polys = [_pool_poly(n, s) for s in range(4)]
+    for raw, strs in polys:  # sequential reuse
+        for _ in range(3):
+            assert decode_poly(strs) == raw
+    # encode + decode from several Python threads at once (the decoder holds the GIL, the encoder's fill phase does
+    # too: this exercises re-entry after a busy pool more than true overlap, which libzkp_b200's callers provide)
+    errs = []
+
+    def worker(k):
+        raw, strs = polys[k]
+        try:
+            for _ in range(10):
+                assert decode_poly(strs) == raw
+                assert native.wire_encode_list(raw) == strs
+        except Exception as e:  # pragma: no cover
+            errs.append(e)
+
+    th = [threading.Thread(target=worker, args=(k,)) for k in range(4)]
+    for t in th:
+        t.start()
+    for t in th:
+        t.join()
+    assert not errs
+    # fork: the child must not wait for workers that only exist in the parent
+    pid = os.fork()
+    if pid == 0:
+        ok = False
+        try:
+            raw, strs = polys[0]
+            ok = decode_poly(strs) == raw and native.wire_encode_list(raw) == strs
+        finally:
+            os._exit(0 if ok else 1)
+    import time
+    deadline = time.time() + 60
+    while True:
+        done, status = os.waitpid(pid, os.WNOHANG)
+        if done:
+            break
+        if time.time() > deadline:  # pragma: no cover
+            os.kill(pid, 9)
+            os.waitpid(pid, 0)
+            raise AssertionError("forked child hung in the codec pool")
+        time.sleep(0.01)
+    assert os.WIFEXITED(status) and os.WEXITSTATUS(status) == 0
+    # and the parent's pool still works
+    assert decode_poly(polys[1][1]) == polys[1][0]

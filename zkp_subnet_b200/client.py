@@ -98,6 +98,35 @@ def _truthy(v) -> bool:
     return bool(v)
 
 
+class _Helper:
+    """A persistent helper thread: submit(fn) runs fn() there and returns an Event that is set when it has finished
+    (fn reports through its own closure).  Daemon, so a client that is never stop()ped does not keep the process alive."""
+
+    def __init__(self):
+        self._q: "queue.SimpleQueue" = queue.SimpleQueue()
+        self._t = threading.Thread(target=self._loop, name="zkp-b200-helper", daemon=True)
+        self._t.start()
+
+    def _loop(self):
+        while True:
+            item = self._q.get()
+            if item is None:
+                return
+            fn, done = item
+            try:
+                fn()
+            finally:
+                done.set()
+
+    def submit(self, fn) -> threading.Event:
+        done = threading.Event()
+        self._q.put((fn, done))
+        return done
+
+    def close(self):
+        self._q.put(None)
+
+
 class _Slot:
     """One pooled context with its page-locked staging buffers and what it remembers about the resident polynomial."""
 
@@ -107,9 +136,18 @@ class _Slot:
         self.staging_alt: Optional[native.PinnedBuffer] = None  # second buffer of the speculative worker_open
         self.resident_n = 0      # > 0: self.staging holds the n x 32 bytes of the polynomial this slot uploaded last
         self.resident_gen = -1   # ... and this is the library's generation of that upload
+        self._helper: Optional[_Helper] = None
+
+    def helper(self) -> "_Helper":
+        if self._helper is None:
+            self._helper = _Helper()
+        return self._helper
 
     def close(self, close_ctx: bool = True):
         self.resident_n = 0
+        if self._helper is not None:
+            self._helper.close()
+            self._helper = None
         for name in ("staging", "staging_alt"):
             if getattr(self, name) is not None:
                 getattr(self, name).close()
@@ -143,7 +181,7 @@ class Client:
                  setup_path: Optional[str] = None, precompute_path: Optional[str] = None, device: int = 0,
                  seed: Optional[int] = None, devices: Optional[Sequence[int]] = None, contexts: int = 2,
                  precompute: str = "eager", multi_gpu: str = "requests", poly_form: str = "evals",
-                 row_order: str = "natural", test_srs: Optional[bool] = None, staged_upload: bool = False):
+                 row_order: str = "natural", test_srs: Optional[bool] = None, staged_upload: Optional[bool] = None):
         if precompute not in ("eager", "lazy"):
             raise ValueError("precompute must be 'eager' or 'lazy'")
         if multi_gpu not in ("requests", "split"):
@@ -165,8 +203,10 @@ class Client:
         self.poly_form = poly_form
         self.row_order = row_order
         self.test_srs = test_srs
-        if staged_upload:
+        if staged_upload is True:
             self.STAGE_MIN = 1 << 17
+        elif staged_upload is False:
+            self.STAGE_MIN = None
         self.scale = None
         self.machines_scale = None
         self.srs_source = None     # "file:<format>" or "test-trapdoor" once started
@@ -332,11 +372,12 @@ class Client:
         return decode_poly(poly, slot.staging)
 
     # From this many elements on, the list is decoded and uploaded in chunks (native.Context.stage_list), each chunk's copy
-    # running beside the decode of the next.  OFF by default (None): measured at 2^20 on the 16-core GPU host, the chunked
-    # form is no faster (14.27 vs 14.13 ms per commit_and_open; 13.92 with two chunks, 16.2 with sixteen) -- the whole
-    # upload is 0.63 ms and every chunk costs a spawn/join of the decoder threads (~0.13 ms).  Client(staged_upload=True)
-    # turns it on (2^17 elements and up).
-    STAGE_MIN = None
+    # running beside the decode of the next.  Measured at 2^20 on the 16-core GPU host (tools/pool_ab.py,
+    # profiles/r2_pool_ab.txt), chunks of 2^18: worker_commit_and_open 13.90 -> 13.5 ms, the reference's two calls
+    # 15.3 -> 14.9 ms.  (Before the codec kept its worker threads between calls every chunk cost a spawn/join of the
+    # decoder threads, ~0.13 ms, and the chunked form was no faster: 14.27 vs 14.13 ms.)  Client(staged_upload=False)
+    # turns it off; Client(staged_upload=True) lowers the threshold to 2^17 elements.
+    STAGE_MIN: Optional[int] = 1 << 19
 
     def _stage(self, slot: _Slot, poly: Sequence[str]) -> Optional[int]:
         """Large polynomials: decode into the slot's staging buffer chunk by chunk, each chunk's host-to-device copy
@@ -430,32 +471,29 @@ class Client:
             if slot.staging_alt is not None:
                 slot.staging_alt.close()
             slot.staging_alt = native.PinnedBuffer(max(32 * n, slot.staging.capacity))
-        # The list is decoded on a helper thread and the GPU call is made from THIS thread: the decoder keeps the
-        # GIL for its whole call (ctypes.PyDLL), the prover call releases it (ctypes.CDLL), so the helper gets
-        # going the moment this thread is inside the library.  The helper waits for `go`, which is set right before
-        # the prover call: started any earlier it would take the GIL first and the decode would run BEFORE the GPU
-        # work instead of beside it (measured at 2^20: 9.5 ms per call instead of 7.1).
+        # The list is decoded on the slot's helper thread and the GPU call is made from THIS thread: the decoder keeps
+        # the GIL for its whole call (ctypes.PyDLL), the prover call releases it (ctypes.CDLL), so the helper gets
+        # going the moment this thread is inside the library.  The job is handed over right before the prover call:
+        # started any earlier the helper would take the GIL first and the decode would run BEFORE the GPU work
+        # instead of beside it (measured at 2^20: 9.5 ms per call instead of 7.1).  The helper is a persistent thread
+        # (one per slot, created on first use): creating a threading.Thread per call costs 60-100 us, a twentieth of a
+        # whole request at the mainnet row size.
         dec = {}
-        go = threading.Event()
 
         def run():
-            go.wait()
             try:
                 dec["ok"] = native.wire_decode_list(poly, slot.staging_alt, same_as=slot.staging)
             except Exception as e:
                 dec["err"] = e
 
-        t = threading.Thread(target=run)
-        t.start()
         spec = err = None
+        done = slot.helper().submit(run)   # handed over right before the prover call (see above)
         try:
-            go.set()
             spec = ctx.worker_open_resident_gen(i, n, slot.resident_gen, xb)
         except native.ZkpError as e:  # resident polynomial replaced by another call on a shared context, bad x, ...
             err = e
         finally:
-            go.set()
-            t.join()
+            done.wait()
         if "err" in dec:
             raise dec["err"]
         buf, same = dec["ok"]

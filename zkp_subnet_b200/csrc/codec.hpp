@@ -9,9 +9,15 @@
 #pragma once
 #include <stddef.h>
 #include <stdint.h>
+#include <stdlib.h>
 #include <string.h>
 
+#include <pthread.h>
+
 #include <atomic>
+#include <condition_variable>
+#include <mutex>
+#include <new>
 #include <thread>
 #include <vector>
 
@@ -149,12 +155,133 @@ inline unsigned codec_threads(size_t count) {
     return (unsigned)(by_work < hw ? by_work : hw);
 }
 
-// runs fn(begin, end) over [0, count) on codec_threads(count) host threads
+// Persistent host threads for the batch codecs.  A polynomial crosses the wire codec once or twice per request
+// (reference neurons/miner.py:56-61 ships it with worker_commit AND worker_open); creating and joining fifteen
+// std::threads costs ~0.13 ms per call on the GPU host -- a tenth of a whole request at the mainnet row size (2^16).
+// The workers are created on first use and then sleep on a condition variable between calls; after a job they keep
+// polling for ~20 us, because the second call of a request follows the first within that time.  One job at a time: a
+// caller that finds the pool busy (two requests decoding at once from different threads) spawns threads the old way.
+// A fork()ed child has no workers: the pool is dropped in the child (pthread_atfork) and rebuilt on first use.
+class WorkerPool {
+   public:
+    typedef void (*RangeFn)(void* ctx, size_t lo, size_t hi);
+    static WorkerPool*& instance() {
+        static WorkerPool* p = nullptr;
+        return p;
+    }
+    static std::mutex& guard() {
+        static std::mutex m;
+        return m;
+    }
+    // nullptr when the pool is busy with another caller's job
+    static WorkerPool* acquire(unsigned want_workers) {
+        std::mutex& g = guard();
+        if (!g.try_lock()) return nullptr;
+        WorkerPool*& p = instance();
+        if (!p) {
+            static bool hooked = false;
+            if (!hooked) {
+                hooked = true;
+                pthread_atfork(nullptr, nullptr, [] {
+                    // child: the worker threads do not exist here; forget the pool (and the lock the parent may have held)
+                    new (&guard()) std::mutex();
+                    instance() = nullptr;
+                });
+            }
+            p = new WorkerPool();
+        }
+        p->grow(want_workers);
+        return p;  // guard stays locked until release()
+    }
+    static void release() { guard().unlock(); }
+
+    // runs fn(ctx, count*t/nt, count*(t+1)/nt) for t in [0, nt): t = 0 on the calling thread, the rest on workers
+    void run(unsigned nt, size_t count, RangeFn fn, void* ctx) {
+        {
+            std::lock_guard<std::mutex> lk(m_);
+            fn_ = fn; ctx_ = ctx; count_ = count; nt_ = nt;
+            pending_.store((int)nt - 1, std::memory_order_relaxed);
+            epoch_.fetch_add(1, std::memory_order_release);
+        }
+        cv_.notify_all();
+        fn(ctx, 0, count / nt);
+        // the workers' share is a few hundred microseconds at most: poll, then sleep
+        for (int spin = 0; pending_.load(std::memory_order_acquire) > 0; spin++) {
+            if (spin < 4096) { cpu_relax(); continue; }
+            std::unique_lock<std::mutex> lk(m_);
+            done_cv_.wait(lk, [&] { return pending_.load(std::memory_order_acquire) <= 0; });
+        }
+    }
+    unsigned workers() const { return (unsigned)th_.size(); }
+
+   private:
+    static inline void cpu_relax() {
+#if defined(__x86_64__)
+        __builtin_ia32_pause();
+#endif
+    }
+    void grow(unsigned want) {
+        while (th_.size() < want) {
+            const unsigned id = (unsigned)th_.size() + 1;  // share index of this worker
+            const uint64_t seen = epoch_.load(std::memory_order_acquire);
+            th_.emplace_back([this, id, seen] { loop(id, seen); });
+            th_.back().detach();
+        }
+    }
+    void loop(unsigned id, uint64_t seen) {
+        for (;;) {
+            // short poll (the next call of the same request is microseconds away), then sleep
+            bool got = false;
+            for (int spin = 0; spin < 1000; spin++) {
+                if (epoch_.load(std::memory_order_acquire) != seen) { got = true; break; }
+                cpu_relax();
+            }
+            if (!got) {
+                std::unique_lock<std::mutex> lk(m_);
+                cv_.wait(lk, [&] { return epoch_.load(std::memory_order_acquire) != seen; });
+            }
+            RangeFn fn; void* ctx; size_t count; unsigned nt;
+            {
+                std::lock_guard<std::mutex> lk(m_);
+                seen = epoch_.load(std::memory_order_acquire);
+                fn = fn_; ctx = ctx_; count = count_; nt = nt_;
+            }
+            if (id < nt) {
+                fn(ctx, count * id / nt, count * (id + 1) / nt);
+                if (pending_.fetch_sub(1, std::memory_order_acq_rel) == 1) {
+                    std::lock_guard<std::mutex> lk(m_);
+                    done_cv_.notify_one();
+                }
+            }
+        }
+    }
+    std::mutex m_;
+    std::condition_variable cv_, done_cv_;
+    std::atomic<uint64_t> epoch_{0};
+    std::atomic<int> pending_{0};
+    RangeFn fn_ = nullptr;
+    void* ctx_ = nullptr;
+    size_t count_ = 0;
+    unsigned nt_ = 0;
+    std::vector<std::thread> th_;
+};
+
+// runs fn(begin, end) over [0, count) on codec_threads(count) host threads (the persistent pool, or freshly spawned
+// threads when the pool is serving another caller)
 template <class Fn>
 inline void parallel_ranges(size_t count, Fn fn, unsigned max_threads = 0) {
     unsigned nt = codec_threads(count);
     if (max_threads && nt > max_threads) nt = max_threads;
     if (nt <= 1) { fn((size_t)0, count); return; }
+    static const bool use_pool = [] {
+        const char* e = getenv("ZKP_CODEC_POOL");  // "0": fresh threads per call (A/B runs, tools/pool_ab.py)
+        return !(e && e[0] == '0');
+    }();
+    if (WorkerPool* pool = use_pool ? WorkerPool::acquire(nt - 1) : nullptr) {
+        struct Release { ~Release() { WorkerPool::release(); } } rel;
+        pool->run(nt, count, [](void* c, size_t lo, size_t hi) { (*static_cast<Fn*>(c))(lo, hi); }, &fn);
+        return;
+    }
     std::vector<std::thread> th;
     th.reserve(nt - 1);
     for (unsigned t = 1; t < nt; t++) th.emplace_back(fn, count * t / nt, count * (t + 1) / nt);
