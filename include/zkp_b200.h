@@ -306,6 +306,11 @@ int zkp_set_ntt_tma(zkp_ctx* ctx, int on);
 /* commit+open as ONE grouped launch set (both MSMs share the sort, the accumulation grid, the slot levels and the
  * reduction): 1 = always, 0 = never (two streams, two launch sets), -1 (default) = by row length.  Same bytes out. */
 int zkp_set_fuse(zkp_ctx* ctx, int mode);
+/* Opening (the field half of zkp_worker_open, reference neurons/miner.py:47-54) of a SINGLE request: 1 (default) = the
+ * blocks of pass 1 own cosets of the domain, whose products are closed forms x^m - w^(bm), and the one inversion
+ * 1/(x^n - 1) is done on the host; 0 = contiguous runs with one Fermat inversion per block on the device (the form batches
+ * and point-range shards always use).  Same bytes out; the first form removes ~0.2 ms of inversion latency per opening. */
+int zkp_set_open_coset(zkp_ctx* ctx, int on);
 /* Fixed-base tables live in one arena of equal slots (one per row, as many as fit the budget; least-recently-used
  * rows are evicted when the arena is smaller than the SRS).  zkp_srs_prebuild_tables builds the tables of rows
  * [first_row, first_row + count) now rather than inside the first request that needs them (*built = tables resident

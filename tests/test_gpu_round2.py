@@ -614,3 +614,35 @@ def test_client_over_several_devices_and_split_mode(golden):
                 assert c.worker_verify(i, r["proof"], golden["test_point"], r["eval"], r["commitment"]).json()["valid"]
         finally:
             c.stop()
+
+
+@pytest.mark.parametrize("log_n", [9, 10, 11, 12, 14, 16, 18, 20])
+def test_coset_opening_equals_the_general_form(gpu_ctx, log_n):
+    """Single-request opening: pass 1 on cosets with the inversion on the host (default) against the general kernels
+    (one Fermat inversion per block, zkp_set_open_coset(0)) and, where the oracle is quick, against the oracle; an x
+    inside the domain takes the general kernels either way; every (y, proof) passes the pairing check."""
+    n = 1 << log_n
+    gpu_ctx.srs_generate(TAU_X, TAU_Y, log_n, 0)
+    try:
+        w = pow(7, (R - 1) // n, R)
+        xs = [ref.random_scalars(2000 + log_n, 1), ref.fr_be(0), ref.fr_be(R - 1), ref.fr_be(2),
+              ref.fr_be(pow(w, 3, R)), ref.fr_be(1)]  # the last two lie in the domain
+        polys = {"random": ref.random_scalars(77 + log_n, n)}
+        if log_n <= 12:
+            polys["ones"] = ref.join32([1] * n)
+            polys["single"] = ref.join32([0] * (n - 1) + [5])
+        srs = gpu_ctx.srs_export_row(0, n) if log_n <= 12 else None
+        for name, poly in polys.items():
+            com = gpu_ctx.worker_commit(0, poly)
+            for x in xs:
+                gpu_ctx.set_open_coset(True)
+                a = gpu_ctx.worker_open(0, poly, x)
+                a3 = gpu_ctx.worker_commit_open(0, poly, x)
+                gpu_ctx.set_open_coset(False)
+                b = gpu_ctx.worker_open(0, poly, x)
+                assert a == b and a3 == (com,) + tuple(a), (name, x.hex())
+                if srs is not None and name == "random":
+                    assert tuple(a) == tuple(ref.open_evals(poly, x, srs, 8)), (name, x.hex())
+                assert gpu_ctx.worker_verify(0, a[1], x, a[0], com)
+    finally:
+        gpu_ctx.set_open_coset(True)

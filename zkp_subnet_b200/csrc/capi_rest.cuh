@@ -90,6 +90,37 @@ int open_device(zkp_ctx* ctx, cudaStream_t st, const Fr* d_f, uint32_t n, const 
     ZKP_CUDA(ctx->partials.ensure((size_t)(blocks > blocks2 ? blocks : blocks2) * count * 32));
     uint32_t* hit = reinterpret_cast<uint32_t*>(rec(SM_HIT));
     if (count == 1) ZKP_CUDA(cudaMemsetAsync(hit, 0xff, 4, st));  // a batch initialises its records itself (k_batch_init)
+    if (count == 1 && !d_xs && n >= 128 * E && ctx->open_coset) {
+        // single request: the host knows x, so it can tell whether x lies in the domain (x^n = 1: the general kernels
+        // below) and, if not, supply 1/(x^n - 1) -- pass 1 then runs on cosets with no inversion on the device
+        // (k_open_pass1_coset), y needs no squarings on the device, and the three kernels of the in-domain fix are
+        // not launched at all.
+        const uint32_t log_m = ilog2(128 * E), log_S = log_n - log_m, S = 1u << log_S;
+        Fr64 xm = x;
+        for (uint32_t k = 0; k < log_m; k++) xm = xm.sqr();
+        Fr64 xn = xm;
+        for (uint32_t k = 0; k < log_S; k++) xn = xn.sqr();
+        if (xn != Fr64::one()) {
+            const Fr64 xn1 = xn - Fr64::one();
+            Fr64 g_inv = dom->w_inv;
+            for (uint32_t k = 0; k < log_S; k++) g_inv = g_inv.sqr();
+            ZKP_CUDA(ctx->partials.ensure((size_t)2 * S * 32 > (size_t)blocks2 * 32 ? (size_t)2 * S * 32 : (size_t)blocks2 * 32));
+            Fr* part = ctx->partials.as<Fr>();
+            Fr* inv_blocks = part + S;
+            k_open_coset_inv<<<1, S < COSET_INV_THREADS ? S : COSET_INV_THREADS, 0, st>>>(to_dev(xm), to_dev(xn1.inverse()), dom->wt.as<Fr>(),
+                                                                                         log_m, S, inv_blocks);
+            k_open_pass1_coset<<<S, 128, 0, st>>>(d_f, E, log_S, to_dev(x), dom->wt.as<Fr>(), to_dev(g_inv), inv_blocks, ctx->fr_b.as<Fr>(), part);
+            trace_mark(ctx, 1, st, "open_pass1");
+            k_open_reduce_y<<<1, 256, 0, st>>>(part, S, to_dev(xn1 * dom->n_inv), reinterpret_cast<Fr*>(rec(SM_S1)),
+                                               reinterpret_cast<Fr*>(rec(SM_Y)));
+            trace_mark(ctx, 1, st, "open_y");
+            k_open_pass2<<<dim3(blocks2, 1), 256, 0, st>>>(d_f, ctx->fr_b.as<Fr>(), n, reinterpret_cast<Fr*>(rec(SM_Y)), ctx->fr_c.as<Fr>());
+            trace_mark(ctx, 1, st, "open_pass2");
+            ctx->launches += 4;
+            ZKP_CUDA(cudaGetLastError());
+            return ZKP_OK;
+        }
+    }
     k_open_pass1<<<dim3(blocks, count), 128, 0, st>>>(d_f, n, E, to_dev(x), dom->wt.as<Fr>(), to_dev(dom->w_inv), ctx->fr_b.as<Fr>(),
                                                       ctx->partials.as<Fr>(), hit, 0, d_xs);
     trace_mark(ctx, 1, st, "open_pass1");
@@ -1566,6 +1597,13 @@ int zkp_set_fuse(zkp_ctx* ctx, int mode) {
     if (!ctx || mode < -1 || mode > 1) return fail(ZKP_ERR_ARG, "fuse mode must be -1 (by size), 0 or 1");
     std::lock_guard<std::mutex> lk(ctx->mu);
     ctx->fuse_mode = mode;
+    return ZKP_OK;
+}
+
+int zkp_set_open_coset(zkp_ctx* ctx, int on) {
+    if (!ctx) return fail(ZKP_ERR_ARG, "null context");
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    ctx->open_coset = on != 0;
     return ZKP_OK;
 }
 

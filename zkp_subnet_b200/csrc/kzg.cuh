@@ -186,6 +186,118 @@ k_open_pass1(const Fr* __restrict__ f, uint32_t n, uint32_t E, Fr x, const Fr* _
     block_sum_store(s1, partial);
 }
 
+// ---- opening, pass 1 WITHOUT an inversion on the device (single request, x outside the domain).
+// The Fermat inversion of k_open_pass1 is ~0.2 ms of pure latency (255 dependent squarings on one lane) -- nothing
+// at 2^20 next to two MSMs, a tenth of a whole worker_open at the mainnet row size (2^16).  It disappears when the
+// blocks own COSETS instead of contiguous runs: with m = 128 E elements per block and S = n / m blocks, block b takes
+// j = b + k S, k < m, i.e. the points w^b z^k with z = w^S of order m, and
+//        prod_k (w^b z^k - x) = x^m - w^(b m)                      (m even)
+// is a closed form; the S block products multiply to x^n - 1, whose inverse the HOST computes (it has x; ~15 us of
+// 64-bit limb arithmetic while the device is busy with the previous kernels).  k_open_coset_inv turns that single
+// inverse into the S inverses 1/(x^m - w^(b m)) by Montgomery's trick (one block: runs of consecutive b per thread,
+// prefix and suffix scans over the thread products), and pass 1 proper runs with no inversion at all.
+// Elements of a block are strided by S in memory: 32-byte accesses, one sector each, and the blocks of the grid --
+// all resident at once -- walk neighbouring sectors at the same time.
+constexpr uint32_t COSET_INV_THREADS = 512;
+__global__ void __launch_bounds__(COSET_INV_THREADS)
+k_open_coset_inv(Fr x_m, Fr total_inv, const Fr* __restrict__ wt, uint32_t log_m, uint32_t S, Fr* __restrict__ inv_blocks) {
+    __shared__ Fr pre[COSET_INV_THREADS], suf[COSET_INV_THREADS];
+    const uint32_t tid = threadIdx.x, T = blockDim.x;  // T = min(S, 512), a power of two; R = S / T values per thread
+    const uint32_t R = S / T, lo = tid * R;
+    const Fr g = load_fr(wt + log_m);  // w^m
+    Fr a = pow_from_table(wt, (uint64_t)lo << log_m), run = Fr::one();
+    for (uint32_t i = 0; i < R; i++) {
+        run = run * (x_m - a);
+        store_fr(inv_blocks + lo + i, run);
+        if (i + 1 < R) a = a * g;
+    }
+    pre[tid] = run;
+    suf[tid] = run;
+    __syncthreads();
+    for (uint32_t s = 1; s < T; s <<= 1) {
+        Fr p = pre[tid], q = suf[tid];
+        if (tid >= s) p = pre[tid - s] * p;
+        if (tid + s < T) q = q * suf[tid + s];
+        __syncthreads();
+        pre[tid] = p;
+        suf[tid] = q;
+        __syncthreads();
+    }
+    Fr u = total_inv;
+    if (tid > 0) u = u * pre[tid - 1];
+    if (tid + 1 < T) u = u * suf[tid + 1];
+    if (R > 1) {
+        // w^-m = w^(n - m) with n = S m
+        const Fr g_inv = pow_from_table(wt, ((uint64_t)S - 1) << log_m);
+        for (int i = (int)R - 1; i >= 0; i--) {
+            const Fr d = x_m - a;
+            const Fr inv = i > 0 ? u * load_fr(inv_blocks + lo + i - 1) : u;
+            u = u * d;
+            store_fr(inv_blocks + lo + i, inv);
+            if (i > 0) a = a * g_inv;
+        }
+    } else {
+        store_fr(inv_blocks + lo, u);
+    }
+}
+// grid = S blocks of 128 threads, thread t of block b owns k in [t E, (t + 1) E): element j = b + k S.  g_inv = w^-S.
+__global__ void __launch_bounds__(128)
+k_open_pass1_coset(const Fr* __restrict__ f, uint32_t E, uint32_t log_S, Fr x, const Fr* __restrict__ wt, Fr g_inv,
+                   const Fr* __restrict__ inv_blocks, Fr* __restrict__ inv_d, Fr* __restrict__ partial) {
+    __shared__ Fr pre[128], suf[128];
+    const uint32_t tid = threadIdx.x, b = blockIdx.x, k0 = tid * E;
+    auto at = [&](uint32_t k) -> size_t { return (size_t)b + ((size_t)k << log_S); };
+    const Fr g = load_fr(wt + log_S);  // w^S
+    Fr a = pow_from_table(wt, at(k0)), run = Fr::one();
+    for (uint32_t i = 0; i < E; i++) {
+        run = run * (a - x);  // never zero: the host has checked x^n != 1
+        store_fr(inv_d + at(k0 + i), run);
+        if (i + 1 < E) a = a * g;
+    }
+    pre[tid] = run;
+    suf[tid] = run;
+    __syncthreads();
+    for (uint32_t s = 1; s < 128; s <<= 1) {
+        Fr p = pre[tid], q = suf[tid];
+        if (tid >= s) p = pre[tid - s] * p;
+        if (tid + s < 128) q = q * suf[tid + s];
+        __syncthreads();
+        pre[tid] = p;
+        suf[tid] = q;
+        __syncthreads();
+    }
+    Fr u = load_fr(inv_blocks + b);
+    if (tid > 0) u = u * pre[tid - 1];
+    if (tid < 127) u = u * suf[tid + 1];
+    Fr s1 = Fr::zero();
+    for (int i = (int)E - 1; i >= 0; i--) {
+        const Fr d = a - x;
+        const Fr inv = i > 0 ? u * load_fr(inv_d + at(k0 + i - 1)) : u;
+        u = u * d;
+        store_fr(inv_d + at(k0 + i), inv);
+        s1 = s1 + load_fr(f + at(k0 + i)) * a * inv;
+        if (i > 0) a = a * g_inv;
+    }
+    block_sum_store(s1, partial);
+}
+// y = -zn * (sum of the partials), zn = (x^n - 1)/n from the host.  One block.
+__global__ void __launch_bounds__(256)
+k_open_reduce_y(const Fr* __restrict__ partial, uint32_t count, Fr zn, Fr* __restrict__ s1_out, Fr* __restrict__ y) {
+    __shared__ Fr sh[256];
+    Fr acc = Fr::zero();
+    for (uint32_t i = threadIdx.x; i < count; i += blockDim.x) acc = acc + load_fr(partial + i);
+    sh[threadIdx.x] = acc;
+    __syncthreads();
+    for (int s = 128; s > 0; s >>= 1) {
+        if ((int)threadIdx.x < s) sh[threadIdx.x] = sh[threadIdx.x] + sh[threadIdx.x + s];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        store_fr(s1_out, sh[0]);
+        store_fr(y, (zn * sh[0]).neg());
+    }
+}
+
 // y = f(x):  hit -> f[hit], else -(x^n - 1)/n * S1.   Single thread.
 __global__ void k_open_y(const Fr* __restrict__ f, uint32_t log_n, Fr x, Fr n_inv, const Fr* __restrict__ s1,
                          const uint32_t* __restrict__ hit, Fr* __restrict__ y, const Fr* __restrict__ xs = nullptr,

@@ -363,6 +363,7 @@ int zkp_ctx_fork(zkp_ctx* parent, zkp_ctx** out) {
     (*out)->bucket_sort = parent->bucket_sort;
     (*out)->use_precomp = parent->use_precomp;
     (*out)->fuse_mode = parent->fuse_mode;
+    (*out)->open_coset = parent->open_coset;
     (*out)->coeff_form = parent->coeff_form;
     return ZKP_OK;
 }
