@@ -156,3 +156,10 @@ def test_lazy_range_proof_script():
     out = subprocess.run(["python", os.path.join(ROOT, "tools", "lazy_bounds.py")], stdout=subprocess.PIPE, check=True,
                          timeout=120).stdout.decode()
     assert "invariant box" in out and "X < 1.99" in out, out
+
+
+def test_host_inverse_binary_gcd_equals_fermat(tmp_path):
+    """csrc/host/field64.hpp F64::inverse (binary extended Euclid, what g1_compress and the opening's 1/(x^n - 1) use)
+    against the Fermat form, Fq and Fr: single-bit values, 0, 1, p - 1, small and random values."""
+    out = subprocess.check_output([build("inv64_host_test", tmp_path)]).decode().splitlines()
+    assert len(out) == 2 and all(line.split()[1] == "ok" and int(line.split()[2]) > 3000 for line in out), out

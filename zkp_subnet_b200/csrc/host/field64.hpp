@@ -92,7 +92,7 @@ struct F64 {
         }
         return acc;
     }
-    F64 inverse() const {  // a^(p-2); 0 -> 0
+    F64 inverse_fermat() const {  // a^(p-2); 0 -> 0
         uint64_t e[N];
         uint64_t borrow = 2;
         for (int i = 0; i < N; i++) {
@@ -101,6 +101,63 @@ struct F64 {
             borrow = (uint64_t)(d >> 64) & 1;
         }
         return pow(e, N);
+    }
+    // 0 -> 0.  Binary extended Euclid on the limbs (the values are public: no constant-time requirement): at most
+    // 2 log2(p) halvings and log2(p) subtractions of N-limb integers, ~7x faster than the 1.5 log2(p) Montgomery products
+    // of the Fermat form -- and the inversion inside g1_compress is what a request waits for after the last kernel of
+    // its proof MSM has finished.  Works on the Montgomery representative v = aR: w = v^-1 = a^-1 R^-1 as an integer,
+    // then two Montgomery products by R^2 give a^-1 R.
+    F64 inverse() const {
+        if (is_zero()) return zero();
+        uint64_t u[N], w[N], x1[N], x2[N];
+        memcpy(u, v, sizeof(u));
+        memcpy(w, P::MOD64, sizeof(w));
+        memset(x1, 0, sizeof(x1));
+        memset(x2, 0, sizeof(x2));
+        x1[0] = 1;
+        auto shr1 = [](uint64_t* a, uint64_t top) {
+            for (int i = 0; i < N - 1; i++) a[i] = (a[i] >> 1) | (a[i + 1] << 63);
+            a[N - 1] = (a[N - 1] >> 1) | (top << 63);
+        };
+        auto halve_mod = [&](uint64_t* x) {  // x / 2 mod p, x < p
+            uint64_t c = 0;
+            if (x[0] & 1) {
+                for (int i = 0; i < N; i++) { u128 t = (u128)x[i] + P::MOD64[i] + c; x[i] = (uint64_t)t; c = (uint64_t)(t >> 64); }
+            }
+            shr1(x, c);
+        };
+        auto geq = [](const uint64_t* a, const uint64_t* b) {
+            for (int i = N - 1; i >= 0; i--) {
+                if (a[i] > b[i]) return true;
+                if (a[i] < b[i]) return false;
+            }
+            return true;
+        };
+        auto sub = [](uint64_t* a, const uint64_t* b) -> uint64_t {  // a -= b, returns the borrow
+            uint64_t br = 0;
+            for (int i = 0; i < N; i++) { u128 d = (u128)a[i] - b[i] - br; a[i] = (uint64_t)d; br = (uint64_t)(d >> 64) & 1; }
+            return br;
+        };
+        auto sub_mod = [&](uint64_t* a, const uint64_t* b) {  // a = a - b mod p, both < p
+            if (sub(a, b)) {
+                uint64_t c = 0;
+                for (int i = 0; i < N; i++) { u128 t = (u128)a[i] + P::MOD64[i] + c; a[i] = (uint64_t)t; c = (uint64_t)(t >> 64); }
+            }
+        };
+        auto is_one = [](const uint64_t* a) {
+            uint64_t r = a[0] ^ 1;
+            for (int i = 1; i < N; i++) r |= a[i];
+            return r == 0;
+        };
+        while (!is_one(u) && !is_one(w)) {
+            while (!(u[0] & 1)) { shr1(u, 0); halve_mod(x1); }
+            while (!(w[0] & 1)) { shr1(w, 0); halve_mod(x2); }
+            if (geq(u, w)) { sub(u, w); sub_mod(x1, x2); }
+            else { sub(w, u); sub_mod(x2, x1); }
+        }
+        F64 r;
+        memcpy(r.v, is_one(u) ? x1 : x2, sizeof(r.v));
+        return (r * r2()) * r2();
     }
 
     // canonical big-endian bytes (N*8) <-> Montgomery form.  from_be returns false if >= modulus.
