@@ -644,5 +644,15 @@ def test_coset_opening_equals_the_general_form(gpu_ctx, log_n):
                 if srs is not None and name == "random":
                     assert tuple(a) == tuple(ref.open_evals(poly, x, srs, 8)), (name, x.hex())
                 assert gpu_ctx.worker_verify(0, a[1], x, a[0], com)
+        # a batch (one x per request): cosets + host inversions against the general kernels
+        if log_n <= 16:
+            k = 5
+            bp = [ref.random_scalars(900 + log_n + r, n) for r in range(k)]
+            bx = b"".join(ref.random_scalars(950 + log_n + r, 1) for r in range(k))
+            gpu_ctx.set_open_coset(True)
+            a = gpu_ctx.worker_commit_open_batch([0] * k, bp, bx)
+            gpu_ctx.set_open_coset(False)
+            assert a == gpu_ctx.worker_commit_open_batch([0] * k, bp, bx)
+            assert all(r[0] == 0 for r in a)
     finally:
         gpu_ctx.set_open_coset(True)

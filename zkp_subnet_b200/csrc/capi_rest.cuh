@@ -72,7 +72,7 @@ int open_buffers(zkp_ctx* ctx, uint32_t n, uint32_t count) {
     return ZKP_OK;
 }
 int open_device(zkp_ctx* ctx, cudaStream_t st, const Fr* d_f, uint32_t n, const Fr64& x, uint32_t count = 1, const Fr* d_xs = nullptr,
-                uint8_t* records = nullptr) {
+                uint8_t* records = nullptr, const uint8_t* h_xs = nullptr, uint8_t* h_stage = nullptr) {
     uint32_t log_n = ilog2(n);
     zkp_ctx::Domain* dom;
     int rc = get_domain(ctx, log_n, false, &dom);
@@ -90,31 +90,50 @@ int open_device(zkp_ctx* ctx, cudaStream_t st, const Fr* d_f, uint32_t n, const 
     ZKP_CUDA(ctx->partials.ensure((size_t)(blocks > blocks2 ? blocks : blocks2) * count * 32));
     uint32_t* hit = reinterpret_cast<uint32_t*>(rec(SM_HIT));
     if (count == 1) ZKP_CUDA(cudaMemsetAsync(hit, 0xff, 4, st));  // a batch initialises its records itself (k_batch_init)
-    if (count == 1 && !d_xs && n >= 128 * E && ctx->open_coset) {
-        // single request: the host knows x, so it can tell whether x lies in the domain (x^n = 1: the general kernels
-        // below) and, if not, supply 1/(x^n - 1) -- pass 1 then runs on cosets with no inversion on the device
+    if (n >= 128 * E && ctx->open_coset && (count == 1 ? !d_xs : h_xs != nullptr)) {
+        // The host knows every x, so it can tell whether one lies in the domain (x^n = 1: the general kernels below)
+        // and, if none does, supply 1/(x^n - 1) -- pass 1 then runs on cosets with no inversion on the device
         // (k_open_pass1_coset), y needs no squarings on the device, and the three kernels of the in-domain fix are
-        // not launched at all.
+        // not launched at all.  A batch hands its evaluation points over as h_xs (Montgomery, 32 bytes each) and
+        // a page-locked staging area for the per-request constants.
         const uint32_t log_m = ilog2(128 * E), log_S = log_n - log_m, S = 1u << log_S;
-        Fr64 xm = x;
-        for (uint32_t k = 0; k < log_m; k++) xm = xm.sqr();
-        Fr64 xn = xm;
-        for (uint32_t k = 0; k < log_S; k++) xn = xn.sqr();
-        if (xn != Fr64::one()) {
+        std::vector<Fr64> hv(3 * (size_t)count);
+        bool outside = true;
+        for (uint32_t r = 0; r < count && outside; r++) {
+            Fr64 xm;
+            if (count == 1) xm = x;
+            else memcpy(xm.v, h_xs + 32 * (size_t)r, 32);
+            for (uint32_t k = 0; k < log_m; k++) xm = xm.sqr();
+            Fr64 xn = xm;
+            for (uint32_t k = 0; k < log_S; k++) xn = xn.sqr();
+            if (xn == Fr64::one()) { outside = false; break; }
             const Fr64 xn1 = xn - Fr64::one();
+            hv[3 * r] = xm;
+            hv[3 * r + 1] = xn1.inverse();
+            hv[3 * r + 2] = xn1 * dom->n_inv;
+        }
+        if (outside) {
             Fr64 g_inv = dom->w_inv;
             for (uint32_t k = 0; k < log_S; k++) g_inv = g_inv.sqr();
-            ZKP_CUDA(ctx->partials.ensure((size_t)2 * S * 32 > (size_t)blocks2 * 32 ? (size_t)2 * S * 32 : (size_t)blocks2 * 32));
+            const size_t need = ((size_t)2 * S * count + 3 * (size_t)count) * 32, need2 = (size_t)blocks2 * count * 32;
+            ZKP_CUDA(ctx->partials.ensure(need > need2 ? need : need2));
             Fr* part = ctx->partials.as<Fr>();
-            Fr* inv_blocks = part + S;
-            k_open_coset_inv<<<1, S < COSET_INV_THREADS ? S : COSET_INV_THREADS, 0, st>>>(to_dev(xm), to_dev(xn1.inverse()), dom->wt.as<Fr>(),
-                                                                                         log_m, S, inv_blocks);
-            k_open_pass1_coset<<<S, 128, 0, st>>>(d_f, E, log_S, to_dev(x), dom->wt.as<Fr>(), to_dev(g_inv), inv_blocks, ctx->fr_b.as<Fr>(), part);
+            Fr* inv_blocks = part + (size_t)S * count;
+            Fr* d_hv = nullptr;
+            if (count > 1) {
+                d_hv = inv_blocks + (size_t)S * count;
+                memcpy(h_stage, hv.data(), hv.size() * 32);
+                ZKP_CUDA(cudaMemcpyAsync(d_hv, h_stage, hv.size() * 32, cudaMemcpyHostToDevice, st));
+            }
+            k_open_coset_inv<<<dim3(1, count), S < COSET_INV_THREADS ? S : COSET_INV_THREADS, 0, st>>>(
+                to_dev(hv[0]), to_dev(hv[1]), dom->wt.as<Fr>(), log_m, S, inv_blocks, d_hv);
+            k_open_pass1_coset<<<dim3(S, count), 128, 0, st>>>(d_f, E, log_S, to_dev(x), dom->wt.as<Fr>(), to_dev(g_inv), inv_blocks,
+                                                              ctx->fr_b.as<Fr>(), part, count > 1 ? d_xs : nullptr);
             trace_mark(ctx, 1, st, "open_pass1");
-            k_open_reduce_y<<<1, 256, 0, st>>>(part, S, to_dev(xn1 * dom->n_inv), reinterpret_cast<Fr*>(rec(SM_S1)),
-                                               reinterpret_cast<Fr*>(rec(SM_Y)));
+            k_open_reduce_y<<<dim3(1, count), 256, 0, st>>>(part, S, to_dev(hv[2]), reinterpret_cast<Fr*>(rec(SM_S1)),
+                                                            reinterpret_cast<Fr*>(rec(SM_Y)), d_hv);
             trace_mark(ctx, 1, st, "open_y");
-            k_open_pass2<<<dim3(blocks2, 1), 256, 0, st>>>(d_f, ctx->fr_b.as<Fr>(), n, reinterpret_cast<Fr*>(rec(SM_Y)), ctx->fr_c.as<Fr>());
+            k_open_pass2<<<dim3(blocks2, count), 256, 0, st>>>(d_f, ctx->fr_b.as<Fr>(), n, reinterpret_cast<Fr*>(rec(SM_Y)), ctx->fr_c.as<Fr>());
             trace_mark(ctx, 1, st, "open_pass2");
             ctx->launches += 4;
             ZKP_CUDA(cudaGetLastError());
@@ -243,6 +262,7 @@ int commit_open_fused(zkp_ctx* ctx, uint32_t i, size_t n, const Fr64& x, uint8_t
     trace_mark(ctx, 1, s1, "open_begin");
     if (!rc) rc = open_device(ctx, s1, ctx->fr_a.as<Fr>(), (uint32_t)n, x);
     trace_mark(ctx, 1, s1, "open_field_kernels");
+    if (!rc) rc = fetch_y_enqueue(ctx, s1);  // ordered before ev_join, i.e. before everything lane 0 does from here on
     if (!rc) {
         ZKP_CUDA(cudaEventRecord(ctx->ev_join, s1));
         ZKP_CUDA(cudaStreamWaitEvent(s0, ctx->ev_join, 0));
@@ -250,7 +270,6 @@ int commit_open_fused(zkp_ctx* ctx, uint32_t i, size_t n, const Fr64& x, uint8_t
     }
     if (!rc) rc = msm_prep_finish(ctx, 0, plan, gs);
     if (!rc) rc = msm_enqueue_main(ctx, 0, plan, pts);
-    if (!rc) rc = fetch_y_enqueue(ctx, s0);
     if (!rc) rc = msm_wait(ctx, 0, 2);
     else { cudaStreamSynchronize(s0); cudaStreamSynchronize(s1); }
     msm_unpin_all(ctx);
@@ -303,6 +322,9 @@ int commit_open_resident(zkp_ctx* ctx, uint32_t i, size_t n, const Fr64& x, uint
     rc = open_device(ctx, s1, ctx->fr_a.as<Fr>(), (uint32_t)n, x);
     if (rc) return bail(rc);
     trace_mark(ctx, 1, s1, "open_field_kernels");
+    // y is final here: its conversion and copy go in front of the proof MSM, not behind its last kernel
+    rc = fetch_y_enqueue(ctx, s1);
+    if (rc) return bail(rc);
     rc = msm_device_prep(ctx, 1, i, ctx->fr_c.as<uint32_t>(), SCALAR_MONT, n, &plan_o, &pts_o);
     if (rc) return bail(rc);
     if (want_com) {
@@ -310,8 +332,6 @@ int commit_open_resident(zkp_ctx* ctx, uint32_t i, size_t n, const Fr64& x, uint
         if (rc) return bail(rc);
     }
     rc = msm_enqueue_main(ctx, 1, plan_o, pts_o);
-    if (rc) return bail(rc);
-    rc = fetch_y_enqueue(ctx, s1);
     if (rc) return bail(rc);
     host::G1J cj = host::G1J::infinity(), pj;
     if (want_com) {
@@ -941,13 +961,14 @@ int batch_chunk(zkp_ctx* ctx, size_t count, const uint32_t* rows, const uint8_t*
     cudaStream_t s0 = ctx->stream, s1 = ctx->stream2;
     const uint32_t nn = (uint32_t)n, cnt = (uint32_t)count;
     // evaluation points (Montgomery) and host staging for the records
-    const size_t hb = count * (SM_BYTES + 32);
+    // records, evaluation points, and the per-request constants of the coset opening (open_device)
+    const size_t hb = BATCH_MAX * (SM_BYTES + 32 + 96);
     if (ctx->h_batch_cap < hb) {
         if (ctx->h_batch) cudaFreeHost(ctx->h_batch);
         ctx->h_batch = nullptr;
         ctx->h_batch_cap = 0;
-        ZKP_CUDA(cudaMallocHost(&ctx->h_batch, BATCH_MAX * (SM_BYTES + 32)));
-        ctx->h_batch_cap = BATCH_MAX * (SM_BYTES + 32);
+        ZKP_CUDA(cudaMallocHost(&ctx->h_batch, hb));
+        ctx->h_batch_cap = hb;
     }
     uint8_t* h_x = ctx->h_batch + BATCH_MAX * SM_BYTES;
     for (size_t r = 0; r < count; r++) {
@@ -989,7 +1010,7 @@ int batch_chunk(zkp_ctx* ctx, size_t count, const uint32_t* rows, const uint8_t*
     ZKP_CUDA(cudaStreamWaitEvent(s1, ctx->ev_ready, 0));
     rc = msm_prep_begin(ctx, 0, plan);
     if (!rc) rc = msm_prep_count(ctx, 0, plan, gs, 0, cnt);
-    if (!rc) rc = open_device(ctx, s1, ctx->fr_a.as<Fr>(), nn, Fr64::zero(), cnt, ctx->batch_x.as<Fr>(), rec);
+    if (!rc) rc = open_device(ctx, s1, ctx->fr_a.as<Fr>(), nn, Fr64::zero(), cnt, ctx->batch_x.as<Fr>(), rec, h_x, h_x + 32 * BATCH_MAX);
     if (!rc) {
         ZKP_CUDA(cudaEventRecord(ctx->ev_join, s1));
         ZKP_CUDA(cudaStreamWaitEvent(s0, ctx->ev_join, 0));
@@ -1028,15 +1049,13 @@ int batch_chunk(zkp_ctx* ctx, size_t count, const uint32_t* rows, const uint8_t*
             memcpy(evals_be + 32 * r, hr + SM_EVAL, 32);
         }
     };
-    const uint32_t nth = cnt >= 8 ? 4 : 1;
-    if (nth == 1) {
-        fold_range(0, cnt);
-    } else {
-        std::vector<std::thread> th;
-        for (uint32_t t = 1; t < nth; t++) th.emplace_back(fold_range, cnt * t / nth, cnt * (t + 1) / nth);
-        fold_range(0, cnt / nth);
-        for (auto& t : th) t.join();
-    }
+    // (the codec's persistent host threads: ~2 requests each, one thread below 4 requests)
+    unsigned cores = std::thread::hardware_concurrency();
+    if (cores == 0) cores = 1;
+    unsigned nth = cnt / 2;
+    if (nth > cores) nth = cores;
+    if (nth > 16) nth = 16;
+    codec::parallel_ranges_n(cnt, nth, [&](size_t lo, size_t hi) { fold_range((uint32_t)lo, (uint32_t)hi); });
     return ZKP_OK;
 }
 }  // namespace

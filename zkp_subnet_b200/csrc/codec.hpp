@@ -268,11 +268,10 @@ class WorkerPool {
 
 // runs fn(begin, end) over [0, count) on codec_threads(count) host threads (the persistent pool, or freshly spawned
 // threads when the pool is serving another caller)
+// fn(begin, end) over [0, count) split evenly over exactly nt threads (the calling thread included)
 template <class Fn>
-inline void parallel_ranges(size_t count, Fn fn, unsigned max_threads = 0) {
-    unsigned nt = codec_threads(count);
-    if (max_threads && nt > max_threads) nt = max_threads;
-    if (nt <= 1) { fn((size_t)0, count); return; }
+inline void parallel_ranges_n(size_t count, unsigned nt, Fn fn) {
+    if (nt <= 1 || count <= 1) { fn((size_t)0, count); return; }
     static const bool use_pool = [] {
         const char* e = getenv("ZKP_CODEC_POOL");  // "0": fresh threads per call (A/B runs, tools/pool_ab.py)
         return !(e && e[0] == '0');
@@ -287,6 +286,12 @@ inline void parallel_ranges(size_t count, Fn fn, unsigned max_threads = 0) {
     for (unsigned t = 1; t < nt; t++) th.emplace_back(fn, count * t / nt, count * (t + 1) / nt);
     fn((size_t)0, count / nt);
     for (auto& x : th) x.join();
+}
+template <class Fn>
+inline void parallel_ranges(size_t count, Fn fn, unsigned max_threads = 0) {
+    unsigned nt = codec_threads(count);
+    if (max_threads && nt > max_threads) nt = max_threads;
+    parallel_ranges_n(count, nt, fn);
 }
 
 // strings at base + i * stride; returns the index of the first invalid element or count

@@ -200,8 +200,14 @@ k_open_pass1(const Fr* __restrict__ f, uint32_t n, uint32_t E, Fr x, const Fr* _
 // all resident at once -- walk neighbouring sectors at the same time.
 constexpr uint32_t COSET_INV_THREADS = 512;
 __global__ void __launch_bounds__(COSET_INV_THREADS)
-k_open_coset_inv(Fr x_m, Fr total_inv, const Fr* __restrict__ wt, uint32_t log_m, uint32_t S, Fr* __restrict__ inv_blocks) {
+k_open_coset_inv(Fr x_m, Fr total_inv, const Fr* __restrict__ wt, uint32_t log_m, uint32_t S, Fr* __restrict__ inv_blocks,
+                 const Fr* __restrict__ host_vals = nullptr) {
     __shared__ Fr pre[COSET_INV_THREADS], suf[COSET_INV_THREADS];
+    if (host_vals) {  // a batch: request blockIdx.y has its own x (host_vals: x^m, 1/(x^n - 1), (x^n - 1)/n per request)
+        x_m = load_fr(host_vals + 3 * blockIdx.y);
+        total_inv = load_fr(host_vals + 3 * blockIdx.y + 1);
+        inv_blocks += (size_t)blockIdx.y * S;
+    }
     const uint32_t tid = threadIdx.x, T = blockDim.x;  // T = min(S, 512), a power of two; R = S / T values per thread
     const uint32_t R = S / T, lo = tid * R;
     const Fr g = load_fr(wt + log_m);  // w^m
@@ -243,8 +249,17 @@ k_open_coset_inv(Fr x_m, Fr total_inv, const Fr* __restrict__ wt, uint32_t log_m
 // grid = S blocks of 128 threads, thread t of block b owns k in [t E, (t + 1) E): element j = b + k S.  g_inv = w^-S.
 __global__ void __launch_bounds__(128)
 k_open_pass1_coset(const Fr* __restrict__ f, uint32_t E, uint32_t log_S, Fr x, const Fr* __restrict__ wt, Fr g_inv,
-                   const Fr* __restrict__ inv_blocks, Fr* __restrict__ inv_d, Fr* __restrict__ partial) {
+                   const Fr* __restrict__ inv_blocks, Fr* __restrict__ inv_d, Fr* __restrict__ partial,
+                   const Fr* __restrict__ xs = nullptr) {
     __shared__ Fr pre[128], suf[128];
+    if (xs) {  // a batch: request blockIdx.y
+        const size_t n = (size_t)(128 * E) << log_S;
+        x = load_fr(xs + blockIdx.y);
+        f += blockIdx.y * n;
+        inv_d += blockIdx.y * n;
+        inv_blocks += (size_t)blockIdx.y << log_S;
+        partial += (size_t)blockIdx.y << log_S;
+    }
     const uint32_t tid = threadIdx.x, b = blockIdx.x, k0 = tid * E;
     auto at = [&](uint32_t k) -> size_t { return (size_t)b + ((size_t)k << log_S); };
     const Fr g = load_fr(wt + log_S);  // w^S
@@ -282,8 +297,15 @@ k_open_pass1_coset(const Fr* __restrict__ f, uint32_t E, uint32_t log_S, Fr x, c
 }
 // y = -zn * (sum of the partials), zn = (x^n - 1)/n from the host.  One block.
 __global__ void __launch_bounds__(256)
-k_open_reduce_y(const Fr* __restrict__ partial, uint32_t count, Fr zn, Fr* __restrict__ s1_out, Fr* __restrict__ y) {
+k_open_reduce_y(const Fr* __restrict__ partial, uint32_t count, Fr zn, Fr* __restrict__ s1_out, Fr* __restrict__ y,
+                const Fr* __restrict__ host_vals = nullptr) {
     __shared__ Fr sh[256];
+    if (host_vals) {  // a batch: request blockIdx.y, outputs in its record
+        zn = load_fr(host_vals + 3 * blockIdx.y + 2);
+        partial += (size_t)blockIdx.y * count;
+        s1_out += blockIdx.y * SM_STRIDE_FR;
+        y += blockIdx.y * SM_STRIDE_FR;
+    }
     Fr acc = Fr::zero();
     for (uint32_t i = threadIdx.x; i < count; i += blockDim.x) acc = acc + load_fr(partial + i);
     sh[threadIdx.x] = acc;
