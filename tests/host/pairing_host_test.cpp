@@ -21,7 +21,26 @@ int main() {
         if (!(c.cyclotomic_sqr() == c * c)) bad_cyc++;
         if (!(c.cyclotomic_sqr().cyclotomic_sqr() == (c * c) * (c * c))) bad_cyc++;
     }
+    // sparse product by a Miller-loop line against the general product by line_eval's element
+    int bad_line = 0;
+    for (int t = 0; t < 16; t++) {
+        Fq12 f = Fq12::one();
+        for (int i = 0; i < 6; i++) {
+            Fq2& c = f.coeff(i);
+            for (int k = 0; k < 6; k++) { c.c0.v[k] = rnd(); c.c1.v[k] = rnd(); }
+            c.c0.v[5] &= 0x0fffffffffffffffull; c.c1.v[5] &= 0x0fffffffffffffffull;
+        }
+        G2Lines::Line l;
+        Fq64 px, py;
+        for (int k = 0; k < 6; k++) { l.lambda.c0.v[k] = rnd(); l.lambda.c1.v[k] = rnd(); l.c.c0.v[k] = rnd(); l.c.c1.v[k] = rnd(); px.v[k] = rnd(); py.v[k] = rnd(); }
+        l.lambda.c0.v[5] &= 0x0fffffffffffffffull; l.lambda.c1.v[5] &= 0x0fffffffffffffffull; l.c.c0.v[5] &= 0x0fffffffffffffffull;
+        l.c.c1.v[5] &= 0x0fffffffffffffffull; px.v[5] &= 0x0fffffffffffffffull; py.v[5] &= 0x0fffffffffffffffull;
+        if (t == 0) py = Fq64::zero();
+        if (t == 1) l.c = Fq2::zero();
+        if (!(f.mul_by_line(l.c, l.lambda.mul_fq(px), py.neg()) == f * line_eval(l, px, py))) bad_line++;
+    }
     printf("fq12_complex_sqr %s\n", bad_sqr ? "BAD" : "ok");
+    printf("mul_by_line %s\n", bad_line ? "BAD" : "ok");
     printf("cyclotomic_sqr %s\n", bad_cyc ? "BAD" : "ok");
     int bad_sub = 0, in = 0, out = 0;
     uint64_t e[6];

@@ -76,7 +76,7 @@ def test_host_pairing_fast_paths(tmp_path):
     """csrc/host: complex Fq12 squaring, cyclotomic squaring and the endomorphism subgroup check agree with their
     plain definitions (random Fq12 elements; curve points inside and outside the prime-order subgroup)."""
     out = subprocess.check_output([build("pairing_host_test", tmp_path)]).decode().splitlines()
-    assert len(out) == 3 and all(line.split()[1] == "ok" for line in out), out
+    assert len(out) == 4 and all(line.split()[1] == "ok" for line in out), out
 
 
 def test_lazy_field_helpers_and_madd_lazy(tmp_path):
@@ -163,3 +163,15 @@ def test_host_inverse_binary_gcd_equals_fermat(tmp_path):
     against the Fermat form, Fq and Fr: single-bit values, 0, 1, p - 1, small and random values."""
     out = subprocess.check_output([build("inv64_host_test", tmp_path)]).decode().splitlines()
     assert len(out) == 2 and all(line.split()[1] == "ok" and int(line.split()[2]) > 3000 for line in out), out
+
+
+def test_host_mont_asm_equals_portable_product(tmp_path):
+    """csrc/host/mont_asm.hpp (mulx / adcx / adox Montgomery products, Fq and Fr) against the portable product of
+    field64.hpp on 400 000 random and edge operand pairs per field; skipped by the binary on a CPU without BMI2 + ADX."""
+    out = subprocess.check_output([build("mont_asm_host_test", tmp_path)]).decode().splitlines()
+    assert len(out) == 2, out
+    for line in out:
+        name, verdict, count = line.split()
+        assert verdict in ("ok", "skipped"), out
+        if verdict == "ok":
+            assert int(count) > 300000

@@ -115,6 +115,8 @@ class _Helper:
             fn, done = item
             try:
                 fn()
+            except BaseException:  # fn reports through its own closure; the helper must outlive a failing job
+                pass
             finally:
                 done.set()
 

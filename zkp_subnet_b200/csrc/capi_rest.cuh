@@ -1215,7 +1215,6 @@ int zkp_worker_verify(zkp_ctx* ctx, uint32_t i, const uint8_t proof48[48], const
     G1J proof, com;
     Fr64 alpha, y;
     // malformed inputs are a failed verification, not an error (reference tests/test_validator.py:66,79-86)
-    if (!g1_decompress(proof, proof48) || !g1_decompress(com, commitment48)) return ZKP_OK;
     if (!Fr64::from_be(alpha, alpha_be) || !Fr64::from_be(y, eval_be)) return ZKP_OK;
     Fr64 ac = alpha.from_mont(), yc = y.from_mont();
     G1J scale;
@@ -1224,7 +1223,23 @@ int zkp_worker_verify(zkp_ctx* ctx, uint32_t i, const uint8_t proof48[48], const
         scale = ctx->scale_points[i];
     }
     // A = C - y*S_i + alpha*pi ;  e(A, g2) * e(-pi, [tau]_2) == 1
-    G1J a = com.add(scale.mul(yc.v, 4).neg()).add(proof.mul(ac.v, 4));
+    // Two independent chains of host work (decompression with its subgroup check, then a 255-bit scalar multiplication,
+    // ~0.4 ms each) run side by side: the proof's on the calling thread, the commitment's on one of the codec's threads.
+    bool ok_proof = false, ok_com = false;
+    G1J a_pi, c_ys;
+    codec::parallel_ranges_n(2, 2, [&](size_t lo, size_t hi) {
+        for (size_t t = lo; t < hi; t++) {
+            if (t == 0) {
+                ok_proof = g1_decompress(proof, proof48);
+                if (ok_proof) a_pi = proof.mul(ac.v, 4);
+            } else {
+                ok_com = g1_decompress(com, commitment48);
+                if (ok_com) c_ys = com.add(scale.mul(yc.v, 4).neg());
+            }
+        }
+    });
+    if (!ok_proof || !ok_com) return ZKP_OK;
+    G1J a = c_ys.add(a_pi);
     std::vector<G1AffineHost> ps = {g1_affine_host(a), g1_affine_host(proof.neg())};
     std::vector<const G2Lines*> qs = {&ctx->lines_g2, &ctx->lines_tau};
     *valid = pairing_product_is_one(ps, qs) ? 1 : 0;

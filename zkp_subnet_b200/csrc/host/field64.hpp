@@ -8,6 +8,10 @@
 #include <stdint.h>
 #include <string.h>
 #include "../field_params.h"
+#include "mont_asm.hpp"
+#if defined(__x86_64__) && defined(__GNUC__)
+#include <x86intrin.h>
+#endif
 
 namespace zkp {
 namespace host {
@@ -43,26 +47,69 @@ struct F64 {
             borrow = (uint64_t)(d >> 64) & 1;
         }
     }
+    // Additions are branchless (the comparison with the modulus is an unpredictable branch otherwise: a third of the time
+    // of an Fq12 product went there).  The moduli leave the top bit of the top limb clear, so a + b never carries out.
     F64 operator+(const F64& o) const {
         F64 r;
+#if defined(__x86_64__) && defined(__GNUC__)
+        unsigned long long t[N], d[N];
+        unsigned char c = 0, b = 0;
+#pragma GCC unroll 8
+        for (int i = 0; i < N; i++) c = _addcarry_u64(c, v[i], o.v[i], &t[i]);
+#pragma GCC unroll 8
+        for (int i = 0; i < N; i++) b = _subborrow_u64(b, t[i], P::MOD64[i], &d[i]);
+#pragma GCC unroll 8
+        for (int i = 0; i < N; i++) r.v[i] = b ? t[i] : d[i];  // borrow: t < p (cmov)
+#else
+        uint64_t t[N], d[N];
         uint64_t c = 0;
-        for (int i = 0; i < N; i++) { u128 s = (u128)v[i] + o.v[i] + c; r.v[i] = (uint64_t)s; c = (uint64_t)(s >> 64); }
-        if (c || geq_mod(r.v)) sub_mod_raw(r.v);
+        for (int i = 0; i < N; i++) { u128 s = (u128)v[i] + o.v[i] + c; t[i] = (uint64_t)s; c = (uint64_t)(s >> 64); }
+        uint64_t b = 0;
+        for (int i = 0; i < N; i++) { u128 e = (u128)t[i] - P::MOD64[i] - b; d[i] = (uint64_t)e; b = (uint64_t)(e >> 64) & 1; }
+        const uint64_t keep = (uint64_t)0 - b;  // all ones: t < p, keep t
+        for (int i = 0; i < N; i++) r.v[i] = (t[i] & keep) | (d[i] & ~keep);
+#endif
         return r;
     }
     F64 operator-(const F64& o) const {
         F64 r;
+#if defined(__x86_64__) && defined(__GNUC__)
+        unsigned long long t[N], d[N];
+        unsigned char b = 0, c = 0;
+#pragma GCC unroll 8
+        for (int i = 0; i < N; i++) b = _subborrow_u64(b, v[i], o.v[i], &t[i]);
+#pragma GCC unroll 8
+        for (int i = 0; i < N; i++) c = _addcarry_u64(c, t[i], P::MOD64[i], &d[i]);
+#pragma GCC unroll 8
+        for (int i = 0; i < N; i++) r.v[i] = b ? d[i] : t[i];  // borrow: add the modulus back
+#else
+        uint64_t t[N];
         uint64_t b = 0;
-        for (int i = 0; i < N; i++) { u128 d = (u128)v[i] - o.v[i] - b; r.v[i] = (uint64_t)d; b = (uint64_t)(d >> 64) & 1; }
-        if (b) {
-            uint64_t c = 0;
-            for (int i = 0; i < N; i++) { u128 s = (u128)r.v[i] + P::MOD64[i] + c; r.v[i] = (uint64_t)s; c = (uint64_t)(s >> 64); }
-        }
+        for (int i = 0; i < N; i++) { u128 d = (u128)v[i] - o.v[i] - b; t[i] = (uint64_t)d; b = (uint64_t)(d >> 64) & 1; }
+        const uint64_t mask = (uint64_t)0 - b;
+        uint64_t c = 0;
+        for (int i = 0; i < N; i++) { u128 s = (u128)t[i] + (P::MOD64[i] & mask) + c; r.v[i] = (uint64_t)s; c = (uint64_t)(s >> 64); }
+#endif
         return r;
     }
     F64 neg() const { return zero() - *this; }
     F64 dbl() const { return *this + *this; }
+    // {modulus limbs, -p^-1 mod 2^64}: the constants block of the assembly products (mont_asm.hpp)
+    static const uint64_t* asm_consts() {
+        static const struct Block { uint64_t w[N + 1]; Block() { memcpy(w, P::MOD64, 8 * N); w[N] = P::INV64; } } b;
+        return b.w;
+    }
     F64 operator*(const F64& o) const {
+#ifdef ZKP_HOST_MONT_ASM
+        if (have_mulx_adx()) {
+            F64 r;
+            if (N == 6) { zkp_host_mont_mul_6(r.v, v, o.v, asm_consts()); return r; }
+            if (N == 4) { zkp_host_mont_mul_4(r.v, v, o.v, asm_consts()); return r; }
+        }
+#endif
+        return mul_portable(o);
+    }
+    F64 mul_portable(const F64& o) const {
         uint64_t t[N + 2];
         memset(t, 0, sizeof(t));
         for (int i = 0; i < N; i++) {

@@ -77,6 +77,20 @@ struct Fq12 {
         z3 = (t2 - z3).dbl() + t2;
         return {{z0, z4, z3}, {z2, z1, z5}};
     }
+    // this * ((a + b v) + (c v) w) with c in Fq: the shape of a Miller-loop line (line_eval below), 12 Fq2-product
+    // equivalents instead of the 18 of a general product
+    static Fq6 fq6_mul_by_01(const Fq6& x, const Fq2& a, const Fq2& b) {
+        Fq2 xa = x.c0 * a, xb = x.c1 * b;
+        Fq2 r1 = (x.c0 + x.c1) * (a + b) - xa - xb;
+        return {xa + (x.c2 * b).mul_by_nonresidue(), r1, xb + x.c2 * a};
+    }
+    Fq12 mul_by_line(const Fq2& a, const Fq2& b, const Fq64& c) const {
+        Fq6 t0 = fq6_mul_by_01(c0, a, b);
+        Fq6 t1 = {c1.c2.mul_fq(c).mul_by_nonresidue(), c1.c0.mul_fq(c), c1.c1.mul_fq(c)};  // c1 * (c v)
+        Fq2 bc = {b.c0 + c, b.c1};
+        Fq6 r1 = fq6_mul_by_01(c0 + c1, a, bc) - t0 - t1;
+        return {t0 + t1.mul_by_v(), r1};
+    }
     Fq12 conj() const { return {c0, c1.neg()}; }
     Fq12 inverse() const {
         Fq6 d = (c0 * c0 - (c1 * c1).mul_by_v()).inverse();
@@ -197,8 +211,13 @@ inline bool pairing_product_is_one(const std::vector<G1AffineHost>& ps, const st
         f = f.sqr();
         for (size_t k = 0; k < ps.size(); k++) {
             if (ps[k].inf || qs[k]->infinity) continue;
-            f = f * line_eval(qs[k]->lines[cursor[k]++], ps[k].x, ps[k].y);
-            if ((BLS_X_ABS >> i) & 1) f = f * line_eval(qs[k]->lines[cursor[k]++], ps[k].x, ps[k].y);
+            const Fq64 ny = ps[k].y.neg();
+            const G2Lines::Line* l = &qs[k]->lines[cursor[k]++];
+            f = f.mul_by_line(l->c, l->lambda.mul_fq(ps[k].x), ny);
+            if ((BLS_X_ABS >> i) & 1) {
+                l = &qs[k]->lines[cursor[k]++];
+                f = f.mul_by_line(l->c, l->lambda.mul_fq(ps[k].x), ny);
+            }
         }
     }
     return final_exponentiation(f) == Fq12::one();
