@@ -25,3 +25,11 @@ for reps in (8, 32, 128):
     dt = time.perf_counter() - t
     assert all(ok)
     print(f"worker_verify_batch of {reps}: {dt * 1e3:.2f} ms = {dt / reps * 1e3:.3f} ms per response")
+# two responses of a batch of 32 carry each other's (valid-looking, wrong) proof: the combined check fails and every
+# response is verified on its own
+bad = bytearray(pr[:48 * 32]); bad[48 * 5:48 * 6], bad[48 * 6:48 * 7] = pr[48 * 6:48 * 7], pr[48 * 5:48 * 6]
+t = time.perf_counter()
+ok = ctx.worker_verify_batch(idx[:32], bytes(bad), x, ev[:32 * 32], cm[:48 * 32])
+dt = time.perf_counter() - t
+assert [k for k, v in enumerate(ok) if not v] == [5, 6]
+print(f"worker_verify_batch of 32 with two swapped proofs (fallback to single checks): {dt * 1e3:.2f} ms")

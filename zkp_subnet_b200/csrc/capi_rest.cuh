@@ -1367,15 +1367,28 @@ int zkp_worker_verify_batch(zkp_ctx* ctx, size_t count, const uint32_t* indices,
         scale = ctx->scale_points;
     }
     struct Item { size_t k; G1J proof, com; Fr64 y; };
+    // decompression (a square root and a subgroup check per point) dominates a large batch: items are independent, so
+    // they are spread over the codec's host threads, ~4 per thread
+    unsigned cores = std::thread::hardware_concurrency();
+    if (cores == 0) cores = 1;
+    unsigned nth = (unsigned)(count / 4);
+    if (nth > cores) nth = cores;
+    if (nth > 16) nth = 16;
+    if (nth < 1) nth = 1;
+    std::vector<Item> all(count);
+    std::vector<uint8_t> ok(count, 0);
+    codec::parallel_ranges_n(count, nth, [&](size_t lo, size_t hi) {
+        for (size_t k = lo; k < hi; k++) {
+            Item& it = all[k];
+            it.k = k;
+            ok[k] = g1_decompress(it.proof, proofs48 + 48 * k) && g1_decompress(it.com, commitments48 + 48 * k) &&
+                    Fr64::from_be(it.y, evals_be + 32 * k);
+        }
+    });
     std::vector<Item> items;
     items.reserve(count);
-    for (size_t k = 0; k < count; k++) {
-        Item it;
-        it.k = k;
-        if (!g1_decompress(it.proof, proofs48 + 48 * k) || !g1_decompress(it.com, commitments48 + 48 * k)) continue;
-        if (!Fr64::from_be(it.y, evals_be + 32 * k)) continue;
-        items.push_back(it);
-    }
+    for (size_t k = 0; k < count; k++)
+        if (ok[k]) items.push_back(all[k]);
     if (items.empty()) return ZKP_OK;
     const Fr64 ac = alpha.from_mont();
     auto single = [&](const Item& it) {
@@ -1390,19 +1403,49 @@ int zkp_worker_verify_batch(zkp_ctx* ctx, size_t count, const uint32_t* indices,
         return ZKP_OK;
     }
     std::random_device rd;
+    std::vector<uint64_t> rs(2 * items.size());
+    for (size_t j = 0; j < items.size(); j++) {
+        rs[2 * j] = ((uint64_t)rd() << 32) | rd();
+        rs[2 * j + 1] = ((uint64_t)rd() << 32) | rd();
+        if (!(rs[2 * j] | rs[2 * j + 1])) rs[2 * j] = 1;
+    }
+    // random linear combination: per-thread partial sums (two 128-bit scalar multiplications per item), merged below
+    const size_t n_items = items.size();
+    unsigned nth2 = (unsigned)(n_items / 4);
+    if (nth2 > nth) nth2 = nth;
+    if (nth2 < 1) nth2 = 1;
+    struct Partial { G1J sum_c, sum_pi; std::vector<Fr64> t; std::vector<uint8_t> used; };
+    std::vector<Partial> parts(nth2);
+    for (auto& pt : parts) {
+        pt.sum_c = G1J::infinity();
+        pt.sum_pi = G1J::infinity();
+        pt.t.assign(scale.size(), Fr64::zero());  // t_i = sum of r_k y_k over the items of row i
+        pt.used.assign(scale.size(), 0);
+    }
+    codec::parallel_ranges_n(nth2, nth2, [&](size_t tlo, size_t thi) {
+        for (size_t tix = tlo; tix < thi; tix++) {
+            Partial& pt = parts[tix];
+            for (size_t j = n_items * tix / nth2; j < n_items * (tix + 1) / nth2; j++) {
+                const Item& it = items[j];
+                uint64_t r[4] = {rs[2 * j], rs[2 * j + 1], 0, 0};
+                pt.sum_c = pt.sum_c.add(it.com.mul(r, 2));
+                pt.sum_pi = pt.sum_pi.add(it.proof.mul(r, 2));
+                Fr64 rk;
+                memcpy(rk.v, r, 32);
+                rk = rk.to_mont();
+                pt.t[indices[it.k]] = pt.t[indices[it.k]] + rk * it.y;
+                pt.used[indices[it.k]] = 1;
+            }
+        }
+    });
     G1J sum_c = G1J::infinity(), sum_pi = G1J::infinity();
-    std::vector<Fr64> t(scale.size(), Fr64::zero());  // t_i = sum of r_k y_k over the items of row i
+    std::vector<Fr64> t(scale.size(), Fr64::zero());
     std::vector<uint8_t> row_used(scale.size(), 0);
-    for (const Item& it : items) {
-        uint64_t r[4] = {((uint64_t)rd() << 32) | rd(), ((uint64_t)rd() << 32) | rd(), 0, 0};
-        if (!(r[0] | r[1])) r[0] = 1;
-        sum_c = sum_c.add(it.com.mul(r, 2));
-        sum_pi = sum_pi.add(it.proof.mul(r, 2));
-        Fr64 rk;
-        memcpy(rk.v, r, 32);
-        rk = rk.to_mont();
-        t[indices[it.k]] = t[indices[it.k]] + rk * it.y;
-        row_used[indices[it.k]] = 1;
+    for (const auto& pt : parts) {
+        sum_c = sum_c.add(pt.sum_c);
+        sum_pi = sum_pi.add(pt.sum_pi);
+        for (size_t i = 0; i < scale.size(); i++)
+            if (pt.used[i]) { t[i] = t[i] + pt.t[i]; row_used[i] = 1; }
     }
     G1J a = sum_c.add(sum_pi.mul(ac.v, 4));
     for (size_t i = 0; i < scale.size(); i++)
@@ -1416,7 +1459,10 @@ int zkp_worker_verify_batch(zkp_ctx* ctx, size_t count, const uint32_t* indices,
         for (const Item& it : items) valid[it.k] = 1;
         return ZKP_OK;
     }
-    for (const Item& it : items) valid[it.k] = single(it) ? 1 : 0;
+    // the combined check failed: at least one response is wrong -- every one is checked on its own (in parallel)
+    codec::parallel_ranges_n(n_items, nth, [&](size_t lo, size_t hi) {
+        for (size_t j = lo; j < hi; j++) valid[items[j].k] = single(items[j]) ? 1 : 0;
+    });
     return ZKP_OK;
 }
 
