@@ -23,6 +23,13 @@ template <class F> int check(const char* name, int iters) {
         if (x.is_zero() ? !a.is_zero() : !((x * a) == F::one())) bad++;
         done++;
     }
+    {   // a non-canonical representative of zero (the raw limbs of p itself) must terminate and answer 0
+        F one_plain = F::zero();
+        one_plain.v[0] = 1;
+        F t = F::zero() - one_plain;  // raw limbs of p - 1
+        t.v[0] += 1;                  // p is odd, so p - 1 is even: no carry
+        if (!t.inverse().is_zero()) bad++;
+    }
     printf("%s %s %d\n", name, bad ? "BAD" : "ok", done);
     return bad;
 }

@@ -616,11 +616,12 @@ def test_client_over_several_devices_and_split_mode(golden):
             c.stop()
 
 
-@pytest.mark.parametrize("log_n", [9, 10, 11, 12, 14, 16, 18, 20])
+@pytest.mark.parametrize("log_n", [9, 10, 11, 12, 14, 16, 18, 20, 22])
 def test_coset_opening_equals_the_general_form(gpu_ctx, log_n):
     """Single-request opening: pass 1 on cosets with the inversion on the host (default) against the general kernels
     (one Fermat inversion per block, zkp_set_open_coset(0)) and, where the oracle is quick, against the oracle; an x
-    inside the domain takes the general kernels either way; every (y, proof) passes the pairing check."""
+    inside the domain takes the general kernels either way; every (y, proof) passes the pairing check.  2^22 has more
+    coset blocks than k_open_coset_inv has threads (several block inverses per thread)."""
     n = 1 << log_n
     gpu_ctx.srs_generate(TAU_X, TAU_Y, log_n, 0)
     try:

@@ -196,11 +196,18 @@ struct F64 {
             for (int i = 1; i < N; i++) r |= a[i];
             return r == 0;
         };
+        auto is_nil = [](const uint64_t* a) {
+            uint64_t r = 0;
+            for (int i = 0; i < N; i++) r |= a[i];
+            return r == 0;
+        };
         while (!is_one(u) && !is_one(w)) {
             while (!(u[0] & 1)) { shr1(u, 0); halve_mod(x1); }
             while (!(w[0] & 1)) { shr1(w, 0); halve_mod(x2); }
             if (geq(u, w)) { sub(u, w); sub_mod(x1, x2); }
             else { sub(w, u); sub_mod(x2, x1); }
+            // gcd(v, p) != 1: only a non-canonical representative of 0 (v = p) gets here; answer like inverse(0)
+            if (is_nil(u) || is_nil(w)) return zero();
         }
         F64 r;
         memcpy(r.v, is_one(u) ? x1 : x2, sizeof(r.v));
