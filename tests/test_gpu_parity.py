@@ -495,3 +495,38 @@ def test_srs_file_roundtrip(gpu_ctx, tmp_path, golden):
                                    o.b64_decode(M["beta"]), o.b64_decode(M["z"]))
     finally:
         other.close()
+
+
+# Public constants of BLS12-381 (ZCash compressed encodings of the G1 generator, its double and its negative, and of
+# the point at infinity): the same bytes appear in every implementation's own tests.
+G1_GEN_HEX = "97f1d3a73197d7942695638c4fa9ac0fc3688c4f9774b905a14e3a3f171bac586c55e83ff97a1aeffb3af00adb22c6bb"
+G1_2GEN_HEX = "a572cbea904d67468808c8eb50a9450c9721db309128012543902d0ac358a62ae28f75bb8f1c7c42c39a8c5529bf0f4e"
+G1_NEG_GEN_HEX = "b7" + G1_GEN_HEX[2:]
+G1_INF_HEX = "c0" + "00" * 47
+
+
+@pytest.mark.parametrize("log_n", [0, 1, 4, 9, 12, 16, 20])
+def test_known_answers_that_need_no_trapdoor(gpu_ctx, log_n):
+    """Known answers independent of tau, of the oracle and of any implementation: the Lagrange basis sums to one, so
+    for EVERY trusted setup commit(1, 1, ..., 1) is the G1 generator, commit(2, ...) its double, commit(r - 1, ...) its
+    negative and commit(0, ...) the point at infinity -- compared here with the public compressed encodings; a constant
+    polynomial opens to itself with the point at infinity as proof, at points inside and outside the domain, through
+    both opening forms.  Two different trapdoors give the same bytes."""
+    n = 1 << log_n
+    ones, twos, zeros, neg = ref.join32([1] * n), ref.join32([2] * n), bytes(32 * n), ref.join32([R - 1] * n)
+    w = pow(7, (R - 1) // n, R)
+    xs = [ref.random_scalars(17 + log_n, 1), ref.fr_be(pow(w, 3 % n, R)), ref.fr_be(0)]
+    for tau in ((TAU_X, TAU_Y), (0x1D0C0FFEE + log_n, 0xABCDEF)):
+        gpu_ctx.srs_generate(tau[0], tau[1], log_n, 0)
+        assert gpu_ctx.worker_commit(0, ones).hex() == G1_GEN_HEX
+        assert gpu_ctx.worker_commit(0, twos).hex() == G1_2GEN_HEX
+        assert gpu_ctx.worker_commit(0, neg).hex() == G1_NEG_GEN_HEX
+        assert gpu_ctx.worker_commit(0, zeros).hex() == G1_INF_HEX
+        for coset in (True, False):
+            gpu_ctx.set_open_coset(coset)
+            for x in xs:
+                for poly, c, com in ((ones, 1, G1_GEN_HEX), (neg, R - 1, G1_NEG_GEN_HEX), (zeros, 0, G1_INF_HEX)):
+                    got = gpu_ctx.worker_commit_open(0, poly, x)
+                    assert (got[0].hex(), int.from_bytes(got[1], "big"), got[2].hex()) == (com, c, G1_INF_HEX), (log_n, coset, c)
+                    assert gpu_ctx.worker_verify(0, got[2], x, got[1], got[0])
+        gpu_ctx.set_open_coset(True)

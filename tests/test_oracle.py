@@ -152,3 +152,24 @@ def test_decompress_rejects_garbage():
     for bad in (plus_one, b"\xff" * 48, b"\x00" * 48, b"\xc0" + b"\x00" * 46 + b"\x01"):
         with pytest.raises(ValueError):
             o.g1_decompress(bad)
+
+
+def test_known_answers_that_need_no_trapdoor():
+    """The Lagrange basis sums to one: for every tau commit(1, ..., 1) is the G1 generator, commit(2, ...) its double,
+    commit(0, ...) infinity -- public constants, compared with both restatements; a constant polynomial opens to itself
+    with the point at infinity as proof."""
+    G = "97f1d3a73197d7942695638c4fa9ac0fc3688c4f9774b905a14e3a3f171bac586c55e83ff97a1aeffb3af00adb22c6bb"
+    G2x = "a572cbea904d67468808c8eb50a9450c9721db309128012543902d0ac358a62ae28f75bb8f1c7c42c39a8c5529bf0f4e"
+    INF = "c0" + "00" * 47
+    for n, tau in ((16, None), (64, 0xC0FFEE)):
+        lag = o.srs_lagrange(n) if tau is None else o.srs_lagrange(n, tau)
+        assert o.g1_compress(o.kzg_commit([1] * n, lag)).hex() == G
+        assert o.g1_compress(o.kzg_commit([2] * n, lag)).hex() == G2x
+        assert o.g1_compress(o.kzg_commit([0] * n, lag)).hex() == INF
+        y, pr = o.kzg_open_evals([7] * n, 123456789, lag)
+        assert y == 7 and o.g1_compress(pr).hex() == INF
+        srs96 = ref.srs(n, o.TEST_SECRET if tau is None else tau, "lagrange")
+        assert ref.msm(srs96, ref.join32([1] * n), 2).hex() == G
+        assert ref.msm(srs96, ref.join32([2] * n), 2).hex() == G2x
+        y, pr = ref.open_evals(ref.join32([7] * n), ref.fr_be(123456789), srs96, 2)
+        assert int.from_bytes(y, "big") == 7 and pr.hex() == INF
