@@ -33,6 +33,18 @@ with native.Context(0) as ctx:
         ctx.set_ntt_tma(tma)
         v = ctx.random_poly(3, 1 << 18)
         assert ctx.fft(ctx.fft(v, True, False), True, True) == v
+# the coset opening (rows of >= 512 elements): single requests and a batch, against the general kernels
+for lg2 in (9, 11):
+    n2 = 1 << lg2
+    with native.Context(0) as ctx:
+        ctx.srs_generate(TX, TY, lg2, 0)
+        ps = [ctx.random_poly(20 + k, n2) for k in range(3)]
+        x3 = [ctx.random_point(30 + k) for k in range(3)]
+        a = [ctx.worker_commit_open(0, ps[k], x3[k]) for k in range(3)]
+        b = ctx.worker_commit_open_batch([0, 0, 0], ps, b"".join(x3))
+        ctx.set_open_coset(False)
+        assert [ctx.worker_commit_open(0, ps[k], x3[k]) for k in range(3)] == a
+        assert [tuple(o[1:]) for o in b] == a and ctx.worker_commit_open_batch([0, 0, 0], ps, b"".join(x3)) == b
 with native.MultiContext([0]) as mg:
     mg.srs_generate(TX, TY, lg, 1, native.LAYOUT_POINT_RANGE)
     assert mg.commit_open(1, polys[1], xs[1]) == single[1]
