@@ -311,6 +311,10 @@ int zkp_set_fuse(zkp_ctx* ctx, int mode);
  * 1/(x^n - 1) is done on the host; 0 = contiguous runs with one Fermat inversion per block on the device (the form batches
  * and point-range shards always use).  Same bytes out; the first form removes ~0.2 ms of inversion latency per opening. */
 int zkp_set_open_coset(zkp_ctx* ctx, int on);
+/* Bucket reduction of an MSM over a SMALL bucket array (one request at the mainnet row size, 2^15 buckets): 1 (default) =
+ * the row / column sums are formed by four lanes per share and two warps per sum (both stages are pure latency there);
+ * 0 = the kernels used for large arrays (one thread per share, one warp per sum).  Same bytes out. */
+int zkp_set_rowcol_coop(zkp_ctx* ctx, int on);
 /* Fixed-base tables live in one arena of equal slots (one per row, as many as fit the budget; least-recently-used
  * rows are evicted when the arena is smaller than the SRS).  zkp_srs_prebuild_tables builds the tables of rows
  * [first_row, first_row + count) now rather than inside the first request that needs them (*built = tables resident

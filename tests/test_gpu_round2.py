@@ -657,3 +657,30 @@ def test_coset_opening_equals_the_general_form(gpu_ctx, log_n):
             assert all(r[0] == 0 for r in a)
     finally:
         gpu_ctx.set_open_coset(True)
+
+
+@pytest.mark.parametrize("log_n", [7, 10, 12, 13, 16])
+def test_rowcol_coop_equals_the_large_array_kernels(gpu_ctx, log_n):
+    """Bucket reduction over a small bucket array with four lanes per share and two warps per sum (default for a single
+    request up to the mainnet row size) against the kernels used for large arrays: same bytes for random, constant,
+    sparse and r - 1 scalars, with fixed-base tables (one bucket set) and without (one per window), and against the
+    oracle where it is quick."""
+    n = 1 << log_n
+    gpu_ctx.srs_generate(TAU_X, TAU_Y, log_n, 0)
+    cases = {"random": ref.random_scalars(400 + log_n, n), "constant": ref.join32([0xABCDEF + (1 << 222)] * n),
+             "single": ref.join32([0] * (n - 1) + [9]), "r_minus_1": ref.join32([R - 1] * n), "zeros": bytes(32 * n)}
+    srs = gpu_ctx.srs_export_row(0, n) if log_n <= 12 else None
+    x = ref.random_scalars(41 + log_n, 1)
+    try:
+        for tables in (True, False):
+            gpu_ctx.set_msm_mode(tables)
+            for name, poly in cases.items():
+                gpu_ctx.set_rowcol_coop(True)
+                a = gpu_ctx.worker_commit_open(0, poly, x)
+                gpu_ctx.set_rowcol_coop(False)
+                assert gpu_ctx.worker_commit_open(0, poly, x) == a, (name, tables)
+                if srs is not None and tables:
+                    assert a == oracle_commit_open(srs, poly, x), name
+    finally:
+        gpu_ctx.set_rowcol_coop(True)
+        gpu_ctx.set_msm_mode(True)

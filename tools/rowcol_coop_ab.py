@@ -1,0 +1,34 @@
+"""Bucket reduction of a small bucket array: four lanes per share + two warps per sum (default) vs the large-array kernels
+(zkp_set_rowcol_coop(0)).  worker_commit / worker_open / commit+open through the C ABI, pinned input.
+python tools/rowcol_coop_ab.py [log_n ...]"""
+import os, sys, time
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from zkp_subnet_b200 import native
+
+def med(f, reps):
+    ts = []
+    for _ in range(reps):
+        t0 = time.perf_counter(); f(); ts.append((time.perf_counter() - t0) * 1e3)
+    ts.sort()
+    return ts[len(ts) // 2], ts[0]
+
+for lg in [int(a) for a in sys.argv[1:]] or [10, 12, 14, 16]:
+    n = 1 << lg
+    ctx = native.Context(0)
+    ctx.srs_generate(1927409816240961209460912649124, 0x1234567890ABCDEF1234567890ABCDEF, lg, 0)
+    ctx.prebuild_tables()
+    pin = native.PinnedBuffer(32 * n)
+    pin.write(ctx.random_poly(0xB200 + 3, n))
+    x = ctx.random_point(5)
+    ref = None
+    for mode in (0, 1, 0, 1):
+        ctx.set_rowcol_coop(bool(mode))
+        for _ in range(3):
+            r = (ctx.worker_commit(0, pin), ctx.worker_open(0, pin, x), ctx.worker_commit_open(0, pin, x))
+        ref = ref or r
+        assert r == ref
+        a = med(lambda: ctx.worker_commit(0, pin), 101)
+        b = med(lambda: ctx.worker_open(0, pin, x), 101)
+        c = med(lambda: ctx.worker_commit_open(0, pin, x), 101)
+        print(f"2^{lg} rowcol_coop={mode}: worker_commit {a[0]:.3f}/{a[1]:.3f} | worker_open {b[0]:.3f}/{b[1]:.3f} | commit_open {c[0]:.3f}/{c[1]:.3f}  (median/min ms)", flush=True)
+    ctx.close()

@@ -1680,6 +1680,12 @@ int zkp_set_fuse(zkp_ctx* ctx, int mode) {
     return ZKP_OK;
 }
 
+int zkp_set_rowcol_coop(zkp_ctx* ctx, int on) {
+    if (!ctx) return fail(ZKP_ERR_ARG, "null context");
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    ctx->rowcol_coop = on != 0;
+    return ZKP_OK;
+}
 int zkp_set_open_coset(zkp_ctx* ctx, int on) {
     if (!ctx) return fail(ZKP_ERR_ARG, "null context");
     std::lock_guard<std::mutex> lk(ctx->mu);

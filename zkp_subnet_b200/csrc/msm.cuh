@@ -658,6 +658,78 @@ k_rowcol_finish(const G1Xyzz* __restrict__ part, uint32_t log_rows, uint32_t log
     if (lane == 0) store_xyzz(is_col ? out_c + (size_t)w * cols + s : out_r + (size_t)w * rows + (s - cols), acc);
 }
 
+// The same two stages for SMALL bucket arrays (one request at the mainnet row size: 2^15 buckets), where both are pure
+// latency -- a lone lane needs ~17 us per dependent addition, four lanes sharing it (coop_add4) ~7.5 us:
+//   k_rowcol_partial_coop   share indexing of k_rowcol_partial, four lanes per share;
+//   k_rowcol_finish_wide    TWO warps per sum (16 groups of 4 lanes): a sum of q partials is q/16 shared additions per
+//                           group, three steps inside each warp, one between the two warps.
+// Measured at 2^16 (B200): the pair 78 + 82 us -> see profiles/r2_rowcol_coop_ab.txt.
+__global__ void __launch_bounds__(128, 3)
+k_rowcol_partial_coop(const G1Xyzz* __restrict__ in, uint32_t log_rows, uint32_t log_cols, uint32_t q_c, uint32_t q_r,
+                      G1Xyzz* __restrict__ part) {
+    const uint32_t rows = 1u << log_rows, cols = 1u << log_cols, w = blockIdx.y;
+    const uint32_t n_c = cols * q_c, total = n_c + rows * q_r;
+    const uint32_t t = (blockIdx.x * blockDim.x + threadIdx.x) >> 2;
+    const int lane = threadIdx.x & 31, gl = lane & 3, gbase = lane - gl;
+    const uint32_t gmask = 0xfu << gbase;
+    if (t >= total) return;  // whole groups
+    const G1Xyzz* x = in + ((size_t)w << (log_rows + log_cols));
+    G1Xyzz acc = G1Xyzz::infinity();
+    if (t < n_c) {
+        const uint32_t s = t & (cols - 1), k = t >> log_cols;
+        for (uint32_t hi = k; hi < rows; hi += q_c) {
+            G1Xyzz p = load_xyzz(x + ((size_t)hi << log_cols) + s);
+            coop_add4(acc, p, gmask, gbase, gl);
+        }
+    } else {
+        const uint32_t u = t - n_c, hi = u / q_r, k = u - hi * q_r;
+        for (uint32_t lo = k; lo < cols; lo += q_r) {
+            G1Xyzz p = load_xyzz(x + ((size_t)hi << log_cols) + lo);
+            coop_add4(acc, p, gmask, gbase, gl);
+        }
+    }
+    if (gl == 0) store_xyzz(part + (size_t)w * total + t, acc);
+}
+constexpr int RCW_THREADS = 128, RCW_WARPS = 2, RCW_SUMS = RCW_THREADS / (32 * RCW_WARPS);  // 2 sums per block
+__global__ void __launch_bounds__(RCW_THREADS)
+k_rowcol_finish_wide(const G1Xyzz* __restrict__ part, uint32_t log_rows, uint32_t log_cols, uint32_t q_c, uint32_t q_r,
+                     G1Xyzz* __restrict__ out_c, G1Xyzz* __restrict__ out_r) {
+    __shared__ G1Xyzz sh[RCW_SUMS];
+    const uint32_t rows = 1u << log_rows, cols = 1u << log_cols, w = blockIdx.y;
+    const uint32_t n_c = cols * q_c, total = n_c + rows * q_r;
+    const int lane = threadIdx.x & 31, gl = lane & 3, gbase = lane - gl, warp = threadIdx.x >> 5;
+    const int sub = warp % RCW_WARPS, local = warp / RCW_WARPS;  // which half of the sum, which sum of the block
+    const uint32_t grp = (uint32_t)(lane >> 2) + 8u * (uint32_t)sub;  // 0..15
+    const uint32_t gmask = 0xfu << gbase;
+    const uint32_t s = blockIdx.x * RCW_SUMS + local;
+    const bool live = s < cols + rows;  // uniform per warp pair; no early return: the block meets at the barrier
+    const G1Xyzz* p = part + (size_t)w * total;
+    const bool is_col = s < cols;
+    const uint32_t q = is_col ? q_c : q_r;
+    G1Xyzz acc = G1Xyzz::infinity();
+    if (live) {
+        for (uint32_t k = grp; k < q; k += 8 * RCW_WARPS) {
+            G1Xyzz v = load_xyzz(is_col ? p + (size_t)k * cols + s : p + n_c + (size_t)(s - cols) * q_r + k);
+            coop_add4(acc, v, gmask, gbase, gl);
+        }
+        for (int st = 4; st > 0; st >>= 1) {
+            G1Xyzz o;
+            uint32_t* ov = o.x.v;
+            const uint32_t* av = acc.x.v;
+#pragma unroll
+            for (int i = 0; i < 48; i++) ov[i] = __shfl_down_sync(0xffffffffu, av[i], 4 * st);
+            if ((lane >> 2) < st) coop_add4(acc, o, gmask, gbase, gl);
+        }
+    }
+    if (live && sub == 1 && lane == 0) sh[local] = acc;
+    __syncthreads();
+    if (live && sub == 0 && lane < 4) {
+        G1Xyzz o = sh[local];
+        coop_add4(acc, o, gmask, gbase, gl);
+        if (lane == 0) store_xyzz(is_col ? out_c + (size_t)w * cols + s : out_r + (size_t)w * rows + (s - cols), acc);
+    }
+}
+
 // Bit planes: block (j, w) computes P[w][j] = sum of the inputs whose weight has bit j set.  Planes
 // j < bits_a come from array a (n_a inputs per window, weight k + 1), planes j >= bits_a from array b
 // (n_b inputs per window, weight k).  The host finishes with Horner passes (sum_j 2^j P_j).

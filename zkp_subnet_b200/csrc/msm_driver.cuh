@@ -255,7 +255,22 @@ inline int msm_enqueue_main(zkp_ctx* ctx, int lane, const MsmPlan& plan, const G
         // (>= 2 shares per sum: with many bucket windows -- a batch of requests -- two shares already give one balanced
         // wave; the one-warp-per-sum kernel below ran the 64-window reduction of a 32-request batch at 15.8 G Fq-mul/s
         // against ~25 for this pair, profiles/r2_launches_summary.txt)
-        if (q_c >= 2 && q_r >= 2) {
+        // small bucket arrays (a single request at the mainnet row size): four lanes per share and two warps per sum --
+        // both stages are latency there.  ~8 buckets per share; the groups fit the machine once.
+        const bool small = ctx->rowcol_coop && plan.Wb == 1 && elems <= (size_t)ctx->sm_count * 512 && rows >= 32 && cols >= 32;
+        if (small) {
+            // e buckets per share, the same for rows and columns, as few as one wave of groups allows (>= 4)
+            uint32_t e = (uint32_t)((elems * 4 + (size_t)ctx->sm_count * 384 - 1) / ((size_t)ctx->sm_count * 384));
+            if (e < 4) e = 4;
+            const uint32_t qc = (rows + e - 1) / e, qr = (cols + e - 1) / e;
+            const uint32_t shares = cols * qc + rows * qr;
+            ZKP_CUDA(ws.pool.ensure((size_t)shares * sizeof(G1Xyzz)));
+            k_rowcol_partial_coop<<<dim3((shares * 4 + 127) / 128, 1), 128, 0, st>>>(ws.buckets.as<G1Xyzz>(), plan.log_rows, plan.log_cols, qc, qr,
+                                                                                ws.pool.as<G1Xyzz>());
+            k_rowcol_finish_wide<<<dim3((cols + rows + RCW_SUMS - 1) / RCW_SUMS, 1), RCW_THREADS, 0, st>>>(
+                ws.pool.as<G1Xyzz>(), plan.log_rows, plan.log_cols, qc, qr, ws.sums_a.as<G1Xyzz>(), ws.sums_b.as<G1Xyzz>());
+            ctx->launches++;
+        } else if (q_c >= 2 && q_r >= 2) {
             const uint32_t shares = cols * q_c + rows * q_r;
             ZKP_CUDA(ws.pool.ensure((size_t)plan.Wb * shares * sizeof(G1Xyzz)));
             k_rowcol_partial<<<dim3((shares + 127) / 128, plan.Wb), 128, 0, st>>>(ws.buckets.as<G1Xyzz>(), plan.log_rows, plan.log_cols,

@@ -364,6 +364,7 @@ int zkp_ctx_fork(zkp_ctx* parent, zkp_ctx** out) {
     (*out)->use_precomp = parent->use_precomp;
     (*out)->fuse_mode = parent->fuse_mode;
     (*out)->open_coset = parent->open_coset;
+    (*out)->rowcol_coop = parent->rowcol_coop;
     (*out)->coeff_form = parent->coeff_form;
     return ZKP_OK;
 }

@@ -124,6 +124,7 @@ _SIGNATURES = {
                      ctypes.POINTER(ctypes.c_uint64)],
     "zkp_set_fuse": [_ctxp, ctypes.c_int],
     "zkp_set_open_coset": [_ctxp, ctypes.c_int],
+    "zkp_set_rowcol_coop": [_ctxp, ctypes.c_int],
     "zkp_set_ntt_tma": [_ctxp, ctypes.c_int],
     "zkp_set_poly_form": [_ctxp, ctypes.c_int],
     "zkp_srs_prebuild_tables": [_ctxp, ctypes.c_uint32, ctypes.c_uint32, ctypes.POINTER(ctypes.c_uint32)],
@@ -509,6 +510,10 @@ class Context:
     def set_fuse(self, mode: int) -> None:
         """commit+open as one grouped launch set: 1 always, 0 never, -1 by row length (default)"""
         check(lib().zkp_set_fuse(self._h, mode))
+
+    def set_rowcol_coop(self, on: bool) -> None:
+        """row / column sums over a small bucket array with four lanes per share (default) or the large-array kernels"""
+        check(lib().zkp_set_rowcol_coop(self._h, int(on)))
 
     def set_open_coset(self, on: bool) -> None:
         """single-request opening on cosets with the inversion on the host (default) or the general device form"""
