@@ -675,9 +675,11 @@ def test_rowcol_coop_equals_the_large_array_kernels(gpu_ctx, log_n):
         for tables in (True, False):
             gpu_ctx.set_msm_mode(tables)
             for name, poly in cases.items():
+                # lone MSMs take the cooperative kernels (a two-lane commit+open keeps the large-array ones)
                 gpu_ctx.set_rowcol_coop(True)
-                a = gpu_ctx.worker_commit_open(0, poly, x)
+                a = (gpu_ctx.worker_commit(0, poly),) + tuple(gpu_ctx.worker_open(0, poly, x))
                 gpu_ctx.set_rowcol_coop(False)
+                assert (gpu_ctx.worker_commit(0, poly),) + tuple(gpu_ctx.worker_open(0, poly, x)) == a, (name, tables)
                 assert gpu_ctx.worker_commit_open(0, poly, x) == a, (name, tables)
                 if srs is not None and tables:
                     assert a == oracle_commit_open(srs, poly, x), name

@@ -327,11 +327,13 @@ int commit_open_resident(zkp_ctx* ctx, uint32_t i, size_t n, const Fr64& x, uint
     if (rc) return bail(rc);
     rc = msm_device_prep(ctx, 1, i, ctx->fr_c.as<uint32_t>(), SCALAR_MONT, n, &plan_o, &pts_o);
     if (rc) return bail(rc);
+    ctx->two_lanes_busy = want_com;
     if (want_com) {
         rc = msm_enqueue_main(ctx, 0, plan_c, pts_c);
-        if (rc) return bail(rc);
+        if (rc) { ctx->two_lanes_busy = false; return bail(rc); }
     }
     rc = msm_enqueue_main(ctx, 1, plan_o, pts_o);
+    ctx->two_lanes_busy = false;
     if (rc) return bail(rc);
     host::G1J cj = host::G1J::infinity(), pj;
     if (want_com) {

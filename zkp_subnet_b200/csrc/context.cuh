@@ -203,6 +203,7 @@ struct zkp_ctx {
     bool use_precomp = true;
     bool coeff_form = false;                  // worker_* polynomials arrive as coefficients (zkp_set_poly_form)
     bool ntt_tma = false;                     // NTT pass 2 tile by bulk async copy (experiment, zkp_set_ntt_tma)
+    bool two_lanes_busy = false;              // set while a commit+open has both lanes' MSMs in flight (msm_enqueue_main)
     bool rowcol_coop = true;                  // small bucket arrays: cooperative row/column stages (zkp_set_rowcol_coop)
     bool open_coset = true;                   // single-request opening: coset blocks + host inversion (zkp_set_open_coset)
     int fuse_mode = -1;                       // commit+open as ONE grouped launch set: 1 always, 0 never, -1 by size

@@ -256,8 +256,9 @@ inline int msm_enqueue_main(zkp_ctx* ctx, int lane, const MsmPlan& plan, const G
         // wave; the one-warp-per-sum kernel below ran the 64-window reduction of a 32-request batch at 15.8 G Fq-mul/s
         // against ~25 for this pair, profiles/r2_launches_summary.txt)
         // small bucket arrays (a single request at the mainnet row size): four lanes per share and two warps per sum --
-        // both stages are latency there.  ~8 buckets per share; the groups fit the machine once.
-        const bool small = ctx->rowcol_coop && plan.Wb == 1 && elems <= (size_t)ctx->sm_count * 512 && rows >= 32 && cols >= 32;
+        // both stages are latency there.  Not inside a two-lane commit+open: its two tails run side by side, the cooperative
+        // form issues 1.4x the multiplies and measured no gain there (and -3% for four contexts serving such requests at once).
+        const bool small = ctx->rowcol_coop && !ctx->two_lanes_busy && plan.Wb == 1 && elems <= (size_t)ctx->sm_count * 512 && rows >= 32 && cols >= 32;
         if (small) {
             // e buckets per share, the same for rows and columns, as few as one wave of groups allows (>= 4)
             uint32_t e = (uint32_t)((elems * 4 + (size_t)ctx->sm_count * 384 - 1) / ((size_t)ctx->sm_count * 384));
