@@ -99,6 +99,33 @@ def test_g1_sum(golden):
         native.g1_sum_uncompressed(exp[:95] + bytes([exp[95] ^ 1]))
 
 
+def test_g1_sum_checked_many_points_and_first_bad_index(golden):
+    """zkp_g1_sum_checked (points received from other parties: decompression + subgroup check per point, spread over the
+    host threads): k*G for k = 1..80 sums to (80*81/2)*G; the error names the FIRST point that fails, whichever thread met
+    a bad one first; a curve point outside the prime-order subgroup is refused."""
+    from oracle import ref
+    pts = [ref.g1_mul_gen(ref.fr_be(k)) for k in range(1, 81)]
+    assert native.g1_sum_checked(b"".join(pts)) == ref.g1_mul_gen(ref.fr_be(80 * 81 // 2))
+    assert native.g1_sum_checked(b"".join(pts)) == native.g1_sum(b"".join(pts))
+    bad = list(pts)
+    bad[70] = b"\xff" * 48
+    bad[23] = b"\xff" * 48
+    with pytest.raises(native.ZkpError, match="point 23 "):
+        native.g1_sum_checked(b"".join(bad))
+    # x = 4 lies on the curve E(Fq) but not in G1 (y^2 = 68 has a root; cofactor != 1): find its compressed form
+    for x in range(2, 40):
+        y2 = (x ** 3 + 4) % o.P
+        y = pow(y2, (o.P + 1) // 4, o.P)
+        if y * y % o.P == y2 and not o.g1_in_subgroup((x, y)):
+            enc = bytearray(x.to_bytes(48, "big"))
+            enc[0] |= 0x80 | (0x20 if y > o.P - y else 0)
+            with pytest.raises(native.ZkpError, match="point 5 "):
+                native.g1_sum_checked(b"".join(pts[:5]) + bytes(enc) + b"".join(pts[5:]))
+            break
+    else:  # pragma: no cover
+        raise AssertionError("no small curve point outside the subgroup found")
+
+
 def _g2(pt):
     return b"".join(c.to_bytes(48, "big") for c in (pt[0][0], pt[0][1], pt[1][0], pt[1][1]))
 
