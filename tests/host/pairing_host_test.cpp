@@ -62,6 +62,22 @@ int main() {
         in++;
     }
     if (!g1_in_subgroup(G1J::infinity())) bad_sub++;
+    // windowed scalar multiplication against double-and-add: dense, sparse, short, zero and all-ones scalars
+    int bad_w4 = 0;
+    for (int t = 0; t < 40; t++) {
+        uint64_t k[4] = {rnd(), rnd(), rnd(), rnd() >> 2};
+        if (t == 0) k[0] = k[1] = k[2] = k[3] = 0;
+        if (t == 1) { k[0] = 1; k[1] = k[2] = k[3] = 0; }
+        if (t == 2) { k[0] = k[1] = k[2] = ~0ull; k[3] = ~0ull >> 2; }
+        if (t == 3) { k[0] = 0; k[1] = 0; k[2] = 0; k[3] = 1ull << 60; }
+        if (t == 4) { k[0] = 0xf0f0f0f0f0f0f0f0ull; k[1] = 0x0f0f0f0f0f0f0f0full; k[2] = 0x1000000000000001ull; k[3] = 0; }
+        uint64_t kk[2] = {rnd(), rnd()};
+        G1J q = g.mul(kk, 2);
+        if (!q.mul_w4(k, 4).equals(q.mul(k, 4))) bad_w4++;
+        if (!q.mul_w4(k, 2).equals(q.mul(k, 2))) bad_w4++;
+        if (!G1J::infinity().mul_w4(k, 4).is_inf()) bad_w4++;
+    }
+    printf("mul_w4 %s\n", bad_w4 ? "BAD" : "ok");
     printf("subgroup_endomorphism %s (%d inside, %d outside)\n", (bad_sub || !out) ? "BAD" : "ok", in, out);
     return 0;
 }

@@ -76,7 +76,7 @@ def test_host_pairing_fast_paths(tmp_path):
     """csrc/host: complex Fq12 squaring, cyclotomic squaring and the endomorphism subgroup check agree with their
     plain definitions (random Fq12 elements; curve points inside and outside the prime-order subgroup)."""
     out = subprocess.check_output([build("pairing_host_test", tmp_path)]).decode().splitlines()
-    assert len(out) == 4 and all(line.split()[1] == "ok" for line in out), out
+    assert len(out) == 5 and all(line.split()[1] == "ok" for line in out), out
 
 
 def test_lazy_field_helpers_and_madd_lazy(tmp_path):

@@ -1254,10 +1254,10 @@ int zkp_worker_verify(zkp_ctx* ctx, uint32_t i, const uint8_t proof48[48], const
         for (size_t t = lo; t < hi; t++) {
             if (t == 0) {
                 ok_proof = g1_decompress(proof, proof48);
-                if (ok_proof) a_pi = proof.mul(ac.v, 4);
+                if (ok_proof) a_pi = proof.mul_w4(ac.v, 4);
             } else {
                 ok_com = g1_decompress(com, commitment48);
-                if (ok_com) c_ys = com.add(scale.mul(yc.v, 4).neg());
+                if (ok_com) c_ys = com.add(scale.mul_w4(yc.v, 4).neg());
             }
         }
     });
@@ -1416,7 +1416,7 @@ int zkp_worker_verify_batch(zkp_ctx* ctx, size_t count, const uint32_t* indices,
     const Fr64 ac = alpha.from_mont();
     auto single = [&](const Item& it) {
         Fr64 yc = it.y.from_mont();
-        G1J a = it.com.add(scale[indices[it.k]].mul(yc.v, 4).neg()).add(it.proof.mul(ac.v, 4));
+        G1J a = it.com.add(scale[indices[it.k]].mul_w4(yc.v, 4).neg()).add(it.proof.mul_w4(ac.v, 4));
         std::vector<G1AffineHost> ps = {g1_affine_host(a), g1_affine_host(it.proof.neg())};
         std::vector<const G2Lines*> qs = {&ctx->lines_g2, &ctx->lines_tau};
         return pairing_product_is_one(ps, qs);
@@ -1451,8 +1451,8 @@ int zkp_worker_verify_batch(zkp_ctx* ctx, size_t count, const uint32_t* indices,
             for (size_t j = n_items * tix / nth2; j < n_items * (tix + 1) / nth2; j++) {
                 const Item& it = items[j];
                 uint64_t r[4] = {rs[2 * j], rs[2 * j + 1], 0, 0};
-                pt.sum_c = pt.sum_c.add(it.com.mul(r, 2));
-                pt.sum_pi = pt.sum_pi.add(it.proof.mul(r, 2));
+                pt.sum_c = pt.sum_c.add(it.com.mul_w4(r, 2));
+                pt.sum_pi = pt.sum_pi.add(it.proof.mul_w4(r, 2));
                 Fr64 rk;
                 memcpy(rk.v, r, 32);
                 rk = rk.to_mont();
@@ -1470,11 +1470,11 @@ int zkp_worker_verify_batch(zkp_ctx* ctx, size_t count, const uint32_t* indices,
         for (size_t i = 0; i < scale.size(); i++)
             if (pt.used[i]) { t[i] = t[i] + pt.t[i]; row_used[i] = 1; }
     }
-    G1J a = sum_c.add(sum_pi.mul(ac.v, 4));
+    G1J a = sum_c.add(sum_pi.mul_w4(ac.v, 4));
     for (size_t i = 0; i < scale.size(); i++)
         if (row_used[i]) {
             Fr64 tc = t[i].from_mont();
-            a = a.add(scale[i].mul(tc.v, 4).neg());
+            a = a.add(scale[i].mul_w4(tc.v, 4).neg());
         }
     std::vector<G1AffineHost> ps = {g1_affine_host(a), g1_affine_host(sum_pi.neg())};
     std::vector<const G2Lines*> qs = {&ctx->lines_g2, &ctx->lines_tau};
